@@ -1,0 +1,783 @@
+// geometry.cu -- graph build (radius neighbour lists + LiDAR ray cast + top-k), labels and
+// the per-agent dynamics step.  Compiled with -fmad=false: every arithmetic step keeps the
+// reference's one-rounding-per-op semantics, so index sets / hit ordering / masks are
+// bit-exact against the CPU oracle (oracle/geometry.py, oracle/envs.py).
+//
+// Replaces (reference paths): gcbfplus/env/utils.py:49-131 (get_lidar, raytracing,
+// inside_obstacles), env/obstacle.py:53-96 (Rectangle), :234-270 (Sphere),
+// env/double_integrator.py:223-264 (edge_blocks), :128-198 (step/cost), :332-338 (u_ref),
+// :356-440 (masks) and their SingleIntegrator / DubinsCar / LinearDrone twins,
+// algo/gcbf_plus.py:160-186 (safe_mask horizon labelling, act).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace gcbf {
+
+static constexpr int GB_WARPS = 8;  // agents (warps) per CTA in graph_build
+#define NO_HIT 1e6f
+
+// ------------------------------------------------------------------------------------
+// obstacle primitives
+// ------------------------------------------------------------------------------------
+// Rectangle.inside (obstacle.py:53-63); ob = 16-float packed rectangle.
+__device__ __forceinline__ bool rect_inside(const float* ob, float px, float py, float r) {
+    float rel_x = px - ob[0];
+    float rel_y = py - ob[1];
+    float rel_xx = fabsf(rel_x * ob[4] + rel_y * ob[5]) - ob[2];
+    float rel_yy = fabsf(rel_x * ob[5] - rel_y * ob[4]) - ob[3];
+    bool is_in_down = (rel_xx < r) && (rel_yy < 0.f);
+    bool is_in_up = (rel_xx < 0.f) && (rel_yy < r);
+    bool is_out_corner = (rel_xx > 0.f) && (rel_yy > 0.f);
+    bool is_in_circle = sqrtf(rel_xx * rel_xx + rel_yy * rel_yy) < r;
+    return (is_in_down || is_in_up) || (is_out_corner && is_in_circle);
+}
+
+__device__ __forceinline__ float nanmin(float a, float b) {  // jnp.min: NaN-propagating
+    return (isnan(a) || isnan(b)) ? NAN : fminf(a, b);
+}
+
+// Rectangle.raytracing (obstacle.py:65-96): min over the 4 edges.
+__device__ __forceinline__ float rect_raytrace(const float* ob, float x1, float y1, float x2, float y2) {
+    float best = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int kp = (k + 3) & 3;  // points[[-1,0,1,2]]
+        float x3 = ob[6 + 2 * k], y3 = ob[7 + 2 * k];
+        float x4 = ob[6 + 2 * kp], y4 = ob[7 + 2 * kp];
+        float det = (x1 - x2) * (y4 - y3) - (y1 - y2) * (x4 - x3);
+        float sgn = (det > 0.f) ? 1.f : ((det < 0.f) ? -1.f : det);  // jnp.sign (0 -> 0, NaN -> NaN)
+        det = sgn * fminf(fmaxf(fabsf(det), 1e-7f), 1e7f);
+        float alpha = ((y4 - y3) * (x1 - x3) - (x4 - x3) * (y1 - y3)) / det;
+        float beta = (-(y1 - y2) * (x1 - x3) + (x1 - x2) * (y1 - y3)) / det;
+        float v = ((alpha <= 1.f && alpha >= 0.f) && (beta <= 1.f && beta >= 0.f)) ? 1.f : 0.f;
+        alpha = v * alpha + (1.f - v) * NO_HIT;
+        best = (k == 0) ? alpha : nanmin(best, alpha);
+    }
+    return best;
+}
+
+// Sphere.inside / raytracing (obstacle.py:234-270); ob = cx,cy,cz,r.
+__device__ __forceinline__ bool sphere_inside(const float* ob, float px, float py, float pz, float r) {
+    float dx = px - ob[0], dy = py - ob[1], dz = pz - ob[2];
+    return sqrtf(dx * dx + dy * dy + dz * dz) <= ob[3] + r;
+}
+__device__ __forceinline__ float sphere_raytrace(const float* ob, float x1, float y1, float z1, float x2,
+                                                 float y2, float z2) {
+    float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+    float rmax = sqrtf(dx * dx + dy * dy + dz * dz);
+    float A = rmax * rmax;
+    float ex = x1 - ob[0], ey = y1 - ob[1], ez = z1 - ob[2];
+    float B = 2.f * (dx * ex + dy * ey + dz * ez);
+    float C = ex * ex + ey * ey + ez * ez - ob[3] * ob[3];
+    float delta = B * B - 4.f * A * C;
+    float valid1 = (delta >= 0.f) ? 1.f : 0.f;
+    float sq = sqrtf(delta * valid1);
+    float alpha1 = (-B - sq) / (2.f * A) * valid1 + (1.f - valid1);
+    float alpha2 = (-B + sq) / (2.f * A) * valid1 + (1.f - valid1);
+    float a1 = ((alpha1 >= 0.f) ? 1.f : 0.f) * alpha1 + ((alpha1 < 0.f) ? 1.f : 0.f) * 1.f;
+    float a2 = ((alpha2 >= 0.f) ? 1.f : 0.f) * alpha2 + ((alpha2 < 0.f) ? 1.f : 0.f) * 1.f;
+    float alphas = fminf(a1, a2);
+    alphas = fminf(fmaxf(alphas, 0.f), 1.f);
+    return valid1 * alphas + (1.f - valid1) * NO_HIT;
+}
+
+// inside_obstacles (env/utils.py:82-107) for one point against the graph's obstacle set.
+template <int PD>
+__device__ __forceinline__ bool inside_any(const float* sobs, int O, const float* p, float r) {
+    bool in = false;
+    if (PD == 2) {
+        for (int o = 0; o < O; ++o) in = in || rect_inside(sobs + 16 * o, p[0], p[1], r);
+    } else {
+        for (int o = 0; o < O; ++o) in = in || sphere_inside(sobs + 4 * o, p[0], p[1], p[2], r);
+    }
+    return in;
+}
+
+// ------------------------------------------------------------------------------------
+// stable ascending sort of 32 (alpha, idx) keys held one per lane (argsort, env/utils.py:127)
+// key order: (flag, alpha, idx); flag 0 = number, 1 = NaN (sorts last), 2 = padding lane.
+// ------------------------------------------------------------------------------------
+struct SortKey {
+    int flag;
+    float alpha;
+    int idx;
+};
+__device__ __forceinline__ bool key_less(const SortKey& a, const SortKey& b) {
+    if (a.flag != b.flag) return a.flag < b.flag;
+    if (a.flag == 0 && a.alpha != b.alpha) return a.alpha < b.alpha;
+    return a.idx < b.idx;
+}
+__device__ __forceinline__ SortKey warp_sort32(SortKey k, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            SortKey o;
+            o.flag = __shfl_xor_sync(0xffffffffu, k.flag, j);
+            o.alpha = __shfl_xor_sync(0xffffffffu, k.alpha, j);
+            o.idx = __shfl_xor_sync(0xffffffffu, k.idx, j);
+            const bool up = ((lane & size) == 0);
+            const bool lower = ((lane & j) == 0);
+            const bool keep_min = (up == lower);
+            const bool o_less = key_less(o, k);
+            if (keep_min ? o_less : !o_less) k = o;
+        }
+    }
+    return k;
+}
+
+// ------------------------------------------------------------------------------------
+// graph build: one warp per agent, GB_WARPS agents per CTA, grid = (ceil(N/GB_WARPS), G)
+// smem: positions of all N agents of the graph, its obstacles, 3-D alpha scratch.
+// ------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(GB_WARPS * 32)
+graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const float* __restrict__ obstacles,
+                   const float* __restrict__ ray_table, float* __restrict__ hits, int32_t* __restrict__ row_start,
+                   int32_t* __restrict__ row_deg, int32_t* __restrict__ edge_recv, int32_t* __restrict__ edge_src,
+                   int32_t* __restrict__ counters, const int do_cast) {
+    using T = EnvTraits<KIND>;
+    constexpr int SD = T::SD, PD = T::PD;
+    constexpr int OBW = (PD == 2) ? 16 : 4;
+    extern __shared__ float smem[];
+    const int N = d.n_agents, O = d.n_obs, R = d.n_hits;
+    float* spos = smem;                         // [N, PD]
+    float* sobs = spos + N * PD;                // [O, OBW]
+    float* stab = sobs + O * OBW;               // [n_rays, PD]
+    float* salpha = stab + d.n_rays * PD;       // 3-D only: [GB_WARPS, n_rays]
+    __shared__ int s_off[GB_WARPS + 1];
+    __shared__ int s_base;
+
+    const int g = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < N; i += blockDim.x) {
+        const float* a = agent + ((size_t)g * N + i) * SD;
+#pragma unroll
+        for (int c = 0; c < PD; ++c) spos[i * PD + c] = a[c];
+    }
+    if (O > 0) {
+        const float* ob = obstacles + (d.obs_per_graph ? (size_t)g * O * OBW : 0);
+        for (int i = tid; i < O * OBW; i += blockDim.x) sobs[i] = ob[i];
+    }
+    for (int i = tid; i < d.n_rays * PD; i += blockDim.x) stab[i] = ray_table[i];
+    __syncthreads();
+
+    const int i = blockIdx.x * GB_WARPS + warp;
+    const bool valid = i < N;
+    const int ii = valid ? i : 0;
+    float p[PD];
+#pragma unroll
+    for (int c = 0; c < PD; ++c) p[c] = spos[ii * PD + c];
+    const size_t a_glob = (size_t)g * N + ii;
+    float* my_hits = hits + a_glob * R * PD;
+
+    // ---------------- LiDAR (env/utils.py:49-131)
+    if (do_cast && valid) {
+        const bool is_in = (O > 0) ? inside_any<PD>(sobs, O, p, 0.f) : false;
+        const float keep = 1.f - (is_in ? 1.f : 0.f);
+        if (PD == 2) {
+            const bool ray_ok = lane < d.n_rays;
+            const int rl = ray_ok ? lane : 0;
+            const float x1 = p[0], y1 = p[1];
+            const float x2 = x1 + stab[rl * 2 + 0], y2 = y1 + stab[rl * 2 + 1];
+            float alpha;
+            if (O == 0) {
+                alpha = 1.f * NO_HIT;
+            } else {
+                alpha = rect_raytrace(sobs, x1, y1, x2, y2);
+                for (int o = 1; o < O; ++o) alpha = nanmin(alpha, rect_raytrace(sobs + 16 * o, x1, y1, x2, y2));
+                alpha = alpha * keep;
+            }
+            const float hx = x1 + (x2 - x1) * alpha;
+            const float hy = y1 + (y2 - y1) * alpha;
+            SortKey k;
+            k.flag = ray_ok ? (isnan(alpha) ? 1 : 0) : 2;
+            k.alpha = alpha;
+            k.idx = lane;
+            k = warp_sort32(k, lane);
+            const float shx = __shfl_sync(0xffffffffu, hx, k.idx);
+            const float shy = __shfl_sync(0xffffffffu, hy, k.idx);
+            if (lane < R) {
+                my_hits[lane * 2 + 0] = shx;
+                my_hits[lane * 2 + 1] = shy;
+            }
+        } else {
+            float* al = salpha + warp * d.n_rays;
+            const float x1 = p[0], y1 = p[1], z1 = p[PD - 1];
+            for (int r = lane; r < d.n_rays; r += 32) {
+                const float x2 = x1 + stab[r * PD + 0], y2 = y1 + stab[r * PD + 1], z2 = z1 + stab[r * PD + PD - 1];
+                float alpha;
+                if (O == 0) {
+                    alpha = 1.f * NO_HIT;
+                } else {
+                    alpha = sphere_raytrace(sobs, x1, y1, z1, x2, y2, z2);
+                    for (int o = 1; o < O; ++o)
+                        alpha = nanmin(alpha, sphere_raytrace(sobs + 4 * o, x1, y1, z1, x2, y2, z2));
+                    alpha = alpha * keep;
+                }
+                al[r] = alpha;
+            }
+            __syncwarp();
+            // R rounds of stable arg-min with removal == argsort(alpha)[:R]
+            for (int rank = 0; rank < R; ++rank) {
+                SortKey best;
+                best.flag = 3;
+                best.alpha = 0.f;
+                best.idx = 0x7fffffff;
+                for (int r = lane; r < d.n_rays; r += 32) {
+                    const float a = al[r];
+                    SortKey k;
+                    k.flag = (__float_as_uint(a) == 0xffc00001u) ? 3 : (isnan(a) ? 1 : 0);
+                    k.alpha = a;
+                    k.idx = r;
+                    if (key_less(k, best)) best = k;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    SortKey other;
+                    other.flag = __shfl_xor_sync(0xffffffffu, best.flag, o);
+                    other.alpha = __shfl_xor_sync(0xffffffffu, best.alpha, o);
+                    other.idx = __shfl_xor_sync(0xffffffffu, best.idx, o);
+                    if (key_less(other, best)) best = other;
+                }
+                if (lane == 0) {
+                    const int r = best.idx;
+                    const float a = best.alpha;
+                    const float x2 = x1 + stab[r * PD + 0], y2 = y1 + stab[r * PD + 1], z2 = z1 + stab[r * PD + PD - 1];
+                    my_hits[rank * PD + 0] = x1 + (x2 - x1) * a;
+                    my_hits[rank * PD + 1] = y1 + (y2 - y1) * a;
+                    my_hits[rank * PD + PD - 1] = z1 + (z2 - z1) * a;
+                    al[r] = __uint_as_float(0xffc00001u);  // tombstone (a NaN payload no alpha can have)
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+
+    // ---------------- active hit nodes: ||p - hit|| < comm_radius - 0.1 (double_integrator.py:254-257)
+    unsigned hit_bits = 0u;
+    {
+        bool act = false;
+        if (valid && lane < R) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < PD; ++c) {
+                const float dlt = p[c] - my_hits[lane * PD + c];
+                acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
+            }
+            act = sqrtf(acc) < d.lidar_radius;
+        }
+        hit_bits = __ballot_sync(0xffffffffu, act);
+    }
+    // ---------------- neighbour count: ||p_i - p_j|| < comm_radius, j != i (double_integrator.py:227-232)
+    int cnt = 0;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+        const int j = j0 + lane;
+        bool ok = false;
+        if (valid && j < N && j != i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < PD; ++c) {
+                const float dlt = p[c] - spos[j * PD + c];
+                acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
+            }
+            ok = sqrtf(acc) < d.comm_radius;
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    const int deg = valid ? (1 + cnt + __popc(hit_bits)) : 0;
+    if (lane == 0) s_off[warp + 1] = deg;
+    __syncthreads();
+    if (tid == 0) {
+        s_off[0] = 0;
+        for (int w = 0; w < GB_WARPS; ++w) s_off[w + 1] += s_off[w];
+        s_base = (s_off[GB_WARPS] > 0) ? atomicAdd(&counters[0], s_off[GB_WARPS]) : 0;
+    }
+    __syncthreads();
+    if (!valid) return;
+    const int base = s_base + s_off[warp];
+    const int a_id = (int)a_glob;
+    if (base + deg > d.edge_cap) {
+        if (lane == 0) {
+            atomicOr(&counters[1], 1);
+            row_start[a_id] = 0;
+            row_deg[a_id] = 0;
+        }
+        return;
+    }
+    if (lane == 0) {
+        row_start[a_id] = base;
+        row_deg[a_id] = deg;
+        edge_recv[base] = a_id;
+        edge_src[base] = -1;
+    }
+    int pos = base + 1;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+        const int j = j0 + lane;
+        bool ok = false;
+        if (j < N && j != i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < PD; ++c) {
+                const float dlt = p[c] - spos[j * PD + c];
+                acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
+            }
+            ok = sqrtf(acc) < d.comm_radius;
+        }
+        const unsigned bits = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const int e = pos + __popc(bits & lt);
+            edge_recv[e] = a_id;
+            edge_src[e] = g * N + j;
+        }
+        pos += __popc(bits);
+    }
+    if ((hit_bits >> lane) & 1u) {
+        const int e = pos + __popc(hit_bits & lt);
+        edge_recv[e] = a_id;
+        edge_src[e] = -2 - lane;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// u_ref (double_integrator.py:332-338; dubins_car.py:328-379)
+// ------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ void u_ref_dev(const gcbf_env_desc& d, const float* x, const float* gl, float* u) {
+    using T = EnvTraits<KIND>;
+    constexpr int SD = T::SD, NU = T::NU;
+    if (KIND == GCBF_ENV_DUBINS_CAR) {
+        const float PI_F = 3.14159265358979323846f;
+        const float TWO_PI = 6.283185307179586f;
+        const float pdx = x[0] - gl[0], pdy = x[1] - gl[1];
+        const float dist = sqrtf(pdx * pdx + pdy * pdy);
+        float theta_t = atan2f(-pdy, -pdx);
+        theta_t = theta_t - floorf(theta_t / TWO_PI) * TWO_PI;  // python-style mod
+        float theta = x[2] - floorf(x[2] / TWO_PI) * TWO_PI;
+        const float theta_diff = theta_t - theta;
+        const float dot = (-pdx) * cosf(theta) + (-pdy) * sinf(theta);
+        const float tb = acosf(fminf(fmaxf(dot / (dist + 0.0001f), -1.f), 1.f));
+        float omega = 0.f;
+        const bool c1 = (theta_diff < PI_F) && (theta_diff >= 0.f);
+        if (c1 && theta <= PI_F) omega = 1.0f * tb;
+        if (!c1 && theta <= PI_F) omega = -1.0f * tb;
+        const bool c2 = (theta_diff > -PI_F) && (theta_diff <= 0.f);
+        if (c2 && theta > PI_F) omega = -1.0f * tb;
+        if (!c2 && theta > PI_F) omega = 1.0f * tb;
+        omega = fminf(fmaxf(omega, -5.f), 5.f);
+        const float nrm = sqrtf(1e-6f + (pdx * pdx + pdy * pdy));
+        const float coef = (nrm > d.comm_radius) ? d.comm_radius / fmaxf(nrm, d.comm_radius) : 1.f;
+        const float qx = coef * pdx, qy = coef * pdy;
+        u[0] = omega;
+        u[1] = -2.5f * x[3] + 2.3f * sqrtf(qx * qx + qy * qy);
+        return;
+    }
+    float err[SD];
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < SD; ++c) {
+        err[c] = gl[c] - x[c];
+        acc = (c == 0) ? err[c] * err[c] : acc + err[c] * err[c];
+    }
+    const float nrm = sqrtf(acc);
+#pragma unroll
+    for (int c = 0; c < SD; ++c) {
+        const float emax = fabsf(err[c] / nrm * d.comm_radius);
+        // jnp.clip(x, lo, hi) = minimum(maximum(x, lo), hi), NaN-propagating
+        float e = err[c];
+        e = (isnan(e) || isnan(emax)) ? NAN : fminf(fmaxf(e, -emax), emax);
+        err[c] = e;
+    }
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < SD; ++c) s = (c == 0) ? err[c] * d.K[a * SD + c] : s + err[c] * d.K[a * SD + c];
+        u[a] = isnan(s) ? NAN : fminf(fmaxf(s, -d.u_lim), d.u_lim);
+    }
+}
+
+// agent_step_euler (double_integrator.py:128-143; SI :104-109; Dubins :104-122; LD :123-134)
+template <int KIND>
+__device__ __forceinline__ void euler_dev(const gcbf_env_desc& d, const float* x, const float* gl, const float* u,
+                                          float* xn) {
+    using T = EnvTraits<KIND>;
+    constexpr int SD = T::SD, NU = T::NU;
+    float xd[SD];
+    if (KIND == GCBF_ENV_SINGLE_INTEGRATOR) {
+        xd[0] = u[0];
+        xd[1] = u[1];
+    } else if (KIND == GCBF_ENV_DOUBLE_INTEGRATOR) {
+        xd[0] = x[2];
+        xd[1] = x[3];
+        xd[2] = u[0] / d.mass;
+        xd[3] = u[1] / d.mass;
+    } else if (KIND == GCBF_ENV_DUBINS_CAR) {
+        const float ddx = x[0] - gl[0], ddy = x[1] - gl[1];
+        const float stop = (sqrtf(ddx * ddx + ddy * ddy) < d.half_r) ? 1.f : 0.f;
+        const float keep = 1.f - stop;
+        xd[0] = (cosf(x[2]) * x[3]) * keep;
+        xd[1] = (sinf(x[2]) * x[3]) * keep;
+        xd[2] = (u[0] * 20.f) * keep;
+        xd[3] = u[1] * keep;
+    } else {
+#pragma unroll
+        for (int r = 0; r < SD; ++r) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < SD; ++c) s += x[c] * d.A[r * SD + c];
+            float t = 0.f;
+#pragma unroll
+            for (int c = 0; c < NU; ++c) t += u[c] * d.B[r * NU + c];
+            xd[r] = s + t;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < SD; ++c) {
+        float v = xd[c] * d.dt + x[c];
+        const bool limited = (KIND == GCBF_ENV_DOUBLE_INTEGRATOR && c >= 2) || (KIND == GCBF_ENV_DUBINS_CAR && c == 3) ||
+                             (KIND == GCBF_ENV_LINEAR_DRONE && c >= 3);
+        if (limited) v = isnan(v) ? v : fminf(fmaxf(v, -d.v_lim), d.v_lim);
+        xn[c] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// env step: one CTA per graph (deterministic reward / cost reductions).
+// ------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256)
+env_step_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const float* __restrict__ goal,
+                const float* __restrict__ obstacles, const float* __restrict__ pi,
+                const int32_t* __restrict__ row_start, const int32_t* __restrict__ row_deg,
+                const int32_t* __restrict__ edge_src, float* __restrict__ action, float* __restrict__ next_agent,
+                float* __restrict__ reward, float* __restrict__ cost, const int mode) {
+    using T = EnvTraits<KIND>;
+    constexpr int SD = T::SD, NU = T::NU, PD = T::PD;
+    constexpr int OBW = (PD == 2) ? 16 : 4;
+    extern __shared__ float smem[];
+    float* sobs = smem;  // [O, OBW]
+    __shared__ float red_r[256];
+    __shared__ float red_c[256];
+    __shared__ float red_o[256];
+    const int g = blockIdx.x, N = d.n_agents, O = d.n_obs;
+    if (O > 0) {
+        const float* ob = obstacles + (d.obs_per_graph ? (size_t)g * O * OBW : 0);
+        for (int i = threadIdx.x; i < O * OBW; i += blockDim.x) sobs[i] = ob[i];
+    }
+    __syncthreads();
+    float r_acc = 0.f, c_acc = 0.f, o_acc = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const size_t a = (size_t)g * N + i;
+        float x[SD], gl[SD], ur[NU], act[NU], u[NU], xn[SD];
+#pragma unroll
+        for (int c = 0; c < SD; ++c) {
+            x[c] = agent[a * SD + c];
+            gl[c] = goal[a * SD + c];
+        }
+        u_ref_dev<KIND>(d, x, gl, ur);
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) {
+            // mode 0: a = 2 pi + u_ref (gcbf_plus.py:182-186); 1: given action; 2: a = u_ref (test.py --u-ref)
+            act[c] = (mode == 0) ? (2.f * pi[a * NU + c] + ur[c]) : ((mode == 1) ? action[a * NU + c] : ur[c]);
+            u[c] = isnan(act[c]) ? act[c] : fminf(fmaxf(act[c], -d.u_lim), d.u_lim);  // clip_action
+            const float df = u[c] - ur[c];
+            sq = (c == 0) ? df * df : sq + df * df;
+            if (mode != 1) action[a * NU + c] = act[c];
+        }
+        euler_dev<KIND>(d, x, gl, u, xn);
+#pragma unroll
+        for (int c = 0; c < SD; ++c) next_agent[a * SD + c] = xn[c];
+        const float nr = sqrtf(sq);
+        r_acc += nr * nr;  // (jnp.linalg.norm(...) ** 2)
+        // get_cost (double_integrator.py:183-198): any_j (2r > dist_ij), via the neighbour list
+        bool col = false;
+        const int rs = row_start[a], rd = row_deg[a];
+        for (int e = rs + 1; e < rs + rd; ++e) {
+            const int s = edge_src[e];
+            if (s < 0) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < PD; ++c) {
+                const float dlt = x[c] - agent[(size_t)s * SD + c];
+                acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
+            }
+            col = col || (d.two_r > sqrtf(acc));
+        }
+        c_acc += col ? 1.f : 0.f;
+        o_acc += (O > 0 && inside_any<PD>(sobs, O, x, d.radius)) ? 1.f : 0.f;
+    }
+    red_r[threadIdx.x] = r_acc;
+    red_c[threadIdx.x] = c_acc;
+    red_o[threadIdx.x] = o_acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            red_r[threadIdx.x] += red_r[threadIdx.x + s];
+            red_c[threadIdx.x] += red_c[threadIdx.x + s];
+            red_o[threadIdx.x] += red_o[threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        reward[g] = -(red_r[0] / (float)N);
+        cost[g] = red_c[0] / (float)N + red_o[0] / (float)N;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// masks: warp per agent; brute force over the graph's agents + own hit nodes.
+// ------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(GB_WARPS * 32)
+masks_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const float* __restrict__ goal,
+             const float* __restrict__ hits, const float* __restrict__ obstacles, uint8_t* __restrict__ unsafe,
+             uint8_t* __restrict__ collision, uint8_t* __restrict__ finish, uint8_t* __restrict__ safe) {
+    using T = EnvTraits<KIND>;
+    constexpr int SD = T::SD, PD = T::PD;
+    constexpr int OBW = (PD == 2) ? 16 : 4;
+    extern __shared__ float smem[];
+    const int N = d.n_agents, O = d.n_obs, R = d.n_hits;
+    float* spos = smem;
+    float* sobs = spos + N * PD;
+    const int g = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < N; i += blockDim.x) {
+        const float* a = agent + ((size_t)g * N + i) * SD;
+#pragma unroll
+        for (int c = 0; c < PD; ++c) spos[i * PD + c] = a[c];
+    }
+    if (O > 0) {
+        const float* ob = obstacles + (d.obs_per_graph ? (size_t)g * O * OBW : 0);
+        for (int i = tid; i < O * OBW; i += blockDim.x) sobs[i] = ob[i];
+    }
+    __syncthreads();
+    const int i = blockIdx.x * GB_WARPS + warp;
+    if (i >= N) return;
+    const size_t a = (size_t)g * N + i;
+    float x[SD];
+#pragma unroll
+    for (int c = 0; c < SD; ++c) x[c] = agent[a * SD + c];
+    // heading for the "unsafe direction" test (double_integrator.py:393-415 / dubins_car.py:445-462)
+    float hx = 0.f, hy = 0.f;
+    if (KIND == GCBF_ENV_DOUBLE_INTEGRATOR) {
+        const float sp = sqrtf(x[2] * x[2] + x[3] * x[3]);
+        hx = x[2] / (sp + 0.0001f);
+        hy = x[3] / (sp + 0.0001f);
+    } else if (KIND == GCBF_ENV_DUBINS_CAR) {
+        hx = cosf(x[2]);
+        hy = sinf(x[2]);
+    }
+    bool any_unsafe_agent = false, any_col = false, all_safe = true, any_dir = false;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < N) {
+            // unsafe_mask uses pos[j] - pos[i]; collision/safe use pos[i] - pos[j]: same norm bitwise
+            float dl[PD];
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < PD; ++c) {
+                dl[c] = spos[j * PD + c] - x[c];
+                acc = (c == 0) ? dl[c] * dl[c] : acc + dl[c] * dl[c];
+            }
+            const float nrm = sqrtf(acc);
+            const float dist = nrm + ((j == i) ? d.two_r_p1 : 0.f);
+            any_unsafe_agent = any_unsafe_agent || (dist < d.unsafe_agent);
+            any_col = any_col || (dist < d.two_r);
+            all_safe = all_safe && (dist > d.safe_agent);
+            if (KIND == GCBF_ENV_DOUBLE_INTEGRATOR || KIND == GCBF_ENV_DUBINS_CAR) {
+                const bool warn = dist < d.warn_agent;
+                const float vx = dl[0] / (nrm + 0.0001f), vy = dl[1] / (nrm + 0.0001f);
+                const float inner = vx * hx + vy * hy;
+                const float th = atan2f(d.two_r, sqrtf(dist * dist - d.four_r_sq));
+                any_dir = any_dir || (warn && (inner > cosf(th)));
+            }
+        }
+    }
+    if ((KIND == GCBF_ENV_DOUBLE_INTEGRATOR || KIND == GCBF_ENV_DUBINS_CAR) && hits != nullptr && lane < R) {
+        const float* h = hits + (a * R + lane) * PD;
+        const float dx = h[0] - x[0], dy = h[1] - x[1];
+        const float dist = sqrtf(dx * dx + dy * dy);
+        const bool warn = dist < d.warn_obs;
+        const float vx = dx / (dist + 0.0001f), vy = dy / (dist + 0.0001f);
+        const float inner = vx * hx + vy * hy;
+        const float th = atan2f(d.radius, sqrtf(dist * dist - d.r_sq));
+        any_dir = any_dir || (warn && (inner > cosf(th)));
+    }
+    any_unsafe_agent = __any_sync(0xffffffffu, any_unsafe_agent);
+    any_col = __any_sync(0xffffffffu, any_col);
+    all_safe = __all_sync(0xffffffffu, all_safe);
+    any_dir = __any_sync(0xffffffffu, any_dir);
+    if (lane == 0) {
+        const bool in_unsafe = (O > 0) && inside_any<PD>(sobs, O, x, d.unsafe_obs);
+        const bool in_col = (O > 0) && inside_any<PD>(sobs, O, x, d.radius);
+        if (unsafe) unsafe[a] = (any_unsafe_agent || in_unsafe || any_dir) ? 1 : 0;
+        if (collision) collision[a] = (any_col || in_col) ? 1 : 0;
+        if (finish) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < PD; ++c) {
+                const float dlt = x[c] - goal[a * SD + c];
+                acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
+            }
+            finish[a] = (sqrtf(acc) < d.two_r) ? 1 : 0;
+        }
+        if (safe) {
+            const bool in_safe = (O > 0) && inside_any<PD>(sobs, O, x, d.safe_obs);
+            safe[a] = (all_safe && !in_safe) ? 1 : 0;
+        }
+    }
+}
+
+// action = (pi ? 2 pi : 0) + u_ref   (GCBFPlus.act, gcbf_plus.py:176-180; env.u_ref)
+template <int KIND>
+__global__ void act_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const float* __restrict__ goal,
+                           const float* __restrict__ pi, float* __restrict__ action) {
+    using T = EnvTraits<KIND>;
+    constexpr int SD = T::SD, NU = T::NU;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= d.n_graphs * d.n_agents) return;
+    float x[SD], gl[SD], ur[NU];
+#pragma unroll
+    for (int c = 0; c < SD; ++c) {
+        x[c] = agent[(size_t)a * SD + c];
+        gl[c] = goal[(size_t)a * SD + c];
+    }
+    u_ref_dev<KIND>(d, x, gl, ur);
+#pragma unroll
+    for (int c = 0; c < NU; ++c) action[(size_t)a * NU + c] = pi ? (2.f * pi[(size_t)a * NU + c] + ur[c]) : ur[c];
+}
+
+// GCBFPlus.safe_mask (gcbf_plus.py:160-174): safe[t] = !any(unsafe[t .. t+H]) ; safe[0] = 1.
+__global__ void safe_horizon_kernel(const uint8_t* __restrict__ unsafe, uint8_t* __restrict__ safe, int n_roll, int T,
+                                    int N, int H) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_roll * N) return;
+    const int b = idx / N, n = idx % N;
+    const uint8_t* u = unsafe + (size_t)b * T * N + n;
+    uint8_t* s = safe + (size_t)b * T * N + n;
+    // sliding count of unsafe flags in the window [t, min(t+H, T-1)]
+    int cnt = 0;
+    for (int t = 0; t <= min(H, T - 1); ++t) cnt += u[(size_t)t * N];
+    for (int t = 0; t < T; ++t) {
+        s[(size_t)t * N] = (t == 0) ? 1 : (cnt == 0 ? 1 : 0);
+        cnt -= u[(size_t)t * N];
+        if (t + H + 1 < T) cnt += u[(size_t)(t + H + 1) * N];
+    }
+}
+
+}  // namespace gcbf
+
+using namespace gcbf;
+
+static int32_t check_desc(const gcbf_env_desc* d) {
+    GCBF_REQUIRE(d != nullptr, "desc is NULL");
+    GCBF_REQUIRE(d->env_kind >= 0 && d->env_kind <= 3, "bad env_kind %d", d->env_kind);
+    GCBF_REQUIRE(d->n_graphs > 0 && d->n_agents > 0, "n_graphs/n_agents must be positive");
+    GCBF_REQUIRE(d->n_obs >= 0 && d->n_hits > 0 && d->n_hits <= 32, "n_obs >= 0 and 0 < n_hits <= 32 required");
+    GCBF_REQUIRE((int64_t)d->n_graphs * d->n_agents < (int64_t)1 << 30, "too many agents");
+    if (env_pd(d->env_kind) == 2)
+        GCBF_REQUIRE(d->n_rays >= 1 && d->n_rays <= 32 && d->n_hits == d->n_rays,
+                     "2-D envs need 1 <= n_rays <= 32 and n_hits == n_rays (got %d, %d)", d->n_rays, d->n_hits);
+    else
+        GCBF_REQUIRE(d->n_rays >= d->n_hits, "3-D env needs n_rays >= n_hits");
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_graph_build(const gcbf_env_desc* desc, const float* agent, const float* obstacles,
+                                    const float* ray_table, float* hits, int32_t* row_start, int32_t* row_deg,
+                                    int32_t* edge_recv, int32_t* edge_src, int32_t* counters, int32_t flags,
+                                    void* stream) {
+    if (int32_t rc = check_desc(desc)) return rc;
+    GCBF_REQUIRE(agent && hits && row_start && row_deg && edge_recv && edge_src && counters, "NULL pointer argument");
+    GCBF_REQUIRE(desc->n_obs == 0 || obstacles, "obstacles is NULL but n_obs > 0");
+    GCBF_REQUIRE(!(flags & 1) || ray_table, "ray_table is NULL");
+    GCBF_REQUIRE(desc->edge_cap > 0, "edge_cap must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int pd = env_pd(desc->env_kind);
+    const int obw = pd == 2 ? 16 : 4;
+    const size_t smem = sizeof(float) * ((size_t)desc->n_agents * pd + (size_t)desc->n_obs * obw +
+                                         (size_t)desc->n_rays * pd + (pd == 3 ? (size_t)GB_WARPS * desc->n_rays : 0));
+    GCBF_REQUIRE(smem <= 200 * 1024, "graph_build needs %zu B shared memory (> 200 KB): too many agents/obstacles", smem);
+    cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int32_t)e; }
+    dim3 grid((desc->n_agents + GB_WARPS - 1) / GB_WARPS, desc->n_graphs);
+    GCBF_DISPATCH_ENV(desc->env_kind, {
+        auto kern = graph_build_kernel<KIND>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, GB_WARPS * 32, smem, st>>>(*desc, agent, obstacles, ray_table, hits, row_start, row_deg,
+                                                edge_recv, edge_src, counters, flags & 1);
+    });
+    count_launch();
+    return check_launch("graph_build_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_env_step(const gcbf_env_desc* desc, const float* agent, const float* goal,
+                                 const float* obstacles, const float* pi, const int32_t* row_start,
+                                 const int32_t* row_deg, const int32_t* edge_src, float* action, float* next_agent,
+                                 float* reward, float* cost, int32_t mode, void* stream) {
+    if (int32_t rc = check_desc(desc)) return rc;
+    GCBF_REQUIRE(agent && goal && row_start && row_deg && edge_src && action && next_agent && reward && cost,
+                 "NULL pointer argument");
+    GCBF_REQUIRE(desc->n_obs == 0 || obstacles, "obstacles is NULL but n_obs > 0");
+    GCBF_REQUIRE(mode >= 0 && mode <= 2 && (mode != 0 || pi), "bad mode %d (mode 0 needs pi)", mode);
+    const int obw = env_pd(desc->env_kind) == 2 ? 16 : 4;
+    const size_t smem = sizeof(float) * (size_t)desc->n_obs * obw;
+    GCBF_REQUIRE(smem <= 40 * 1024, "too many obstacles for env_step");
+    cudaStream_t st = (cudaStream_t)stream;
+    GCBF_DISPATCH_ENV(desc->env_kind, {
+        env_step_kernel<KIND><<<desc->n_graphs, 256, smem, st>>>(*desc, agent, goal, obstacles, pi, row_start, row_deg,
+                                                                 edge_src, action, next_agent, reward, cost, mode);
+    });
+    count_launch();
+    return check_launch("env_step_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_act(const gcbf_env_desc* desc, const float* agent,
+                                                                   const float* goal, const float* pi, float* action,
+                                                                   void* stream) {
+    if (int32_t rc = check_desc(desc)) return rc;
+    GCBF_REQUIRE(agent && goal && action, "NULL pointer argument");
+    const int A = desc->n_graphs * desc->n_agents;
+    GCBF_DISPATCH_ENV(desc->env_kind, {
+        act_kernel<KIND><<<(A + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*desc, agent, goal, pi, action);
+    });
+    count_launch();
+    return check_launch("act_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_masks(const gcbf_env_desc* desc, const float* agent, const float* goal, const float* hits,
+                              const float* obstacles, uint8_t* unsafe, uint8_t* collision, uint8_t* finish,
+                              uint8_t* safe, void* stream) {
+    if (int32_t rc = check_desc(desc)) return rc;
+    GCBF_REQUIRE(agent && goal, "NULL pointer argument");
+    GCBF_REQUIRE(desc->n_obs == 0 || obstacles, "obstacles is NULL but n_obs > 0");
+    const int pd = env_pd(desc->env_kind);
+    const int obw = pd == 2 ? 16 : 4;
+    if (unsafe && (desc->env_kind == GCBF_ENV_DOUBLE_INTEGRATOR || desc->env_kind == GCBF_ENV_DUBINS_CAR))
+        GCBF_REQUIRE(hits, "unsafe_mask of DoubleIntegrator/DubinsCar needs the hit nodes");
+    const size_t smem = sizeof(float) * ((size_t)desc->n_agents * pd + (size_t)desc->n_obs * obw);
+    GCBF_REQUIRE(smem <= 200 * 1024, "masks: too many agents/obstacles for shared memory");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((desc->n_agents + GB_WARPS - 1) / GB_WARPS, desc->n_graphs);
+    GCBF_DISPATCH_ENV(desc->env_kind, {
+        auto kern = masks_kernel<KIND>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, GB_WARPS * 32, smem, st>>>(*desc, agent, goal, hits, obstacles, unsafe, collision, finish, safe);
+    });
+    count_launch();
+    return check_launch("masks_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_safe_horizon(const uint8_t* unsafe, uint8_t* safe, int32_t n_rollouts, int32_t T,
+                                     int32_t n_agents, int32_t horizon, void* stream) {
+    GCBF_REQUIRE(unsafe && safe && n_rollouts > 0 && T > 0 && n_agents > 0 && horizon >= 0, "bad argument");
+    const int n = n_rollouts * n_agents;
+    safe_horizon_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(unsafe, safe, n_rollouts, T, n_agents, horizon);
+    count_launch();
+    return check_launch("safe_horizon_kernel");
+}

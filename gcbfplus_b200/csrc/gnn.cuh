@@ -1,0 +1,204 @@
+// gnn.cuh -- non-GEMM kernels of the GNN (edge features + first message layer, attention
+// softmax + aggregation, output head) and the workspace layout shared by forward / backward.
+//
+// Replaces gcbfplus/nn/gnn.py:44-75 (GNNLayer message/aggregate/update), nn/mlp.py:6-30,
+// algo/module/cbf.py:12-21, algo/module/policy.py:63-73, and the edge-feature part of
+// env/double_integrator.py:223-264 / 275-286 (edge_blocks / add_edge_feats) and twins.
+#pragma once
+#include "common.cuh"
+
+namespace gcbf {
+
+constexpr int FEAT_LD = 8;  // per-edge feature row stride (ed <= 6)
+
+// Saved activations of one network forward (float offsets into the workspace).
+struct GnnWs {
+    int64_t feat, x1, x2, msg, g1, g2, att, ag, v1, v2, v3, h1, h2, total;
+};
+inline GnnWs make_ws(int64_t cap, int64_t A) {
+    GnnWs w;
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t r = o; o += (n + 3) & ~(int64_t)3; return r; };
+    w.feat = take(cap * FEAT_LD);
+    w.x1 = take(cap * 256);
+    w.x2 = take(cap * 256);
+    w.msg = take(cap * 128);
+    w.g1 = take(cap * 128);
+    w.g2 = take(cap * 128);
+    w.att = take(cap);
+    w.ag = take(A * 128);
+    w.v1 = take(A * 256);
+    w.v2 = take(A * 256);
+    w.v3 = take(A * 128);
+    w.h1 = take(A * 256);
+    w.h2 = take(A * 256);
+    w.total = o;
+    return w;
+}
+
+// edge_state (dubins_car.py:260-264: (x, y, v cos th, v sin th); identity otherwise)
+template <int KIND>
+__device__ __forceinline__ void edge_state_dev(const float* s, float* es) {
+    constexpr int SD = EnvTraits<KIND>::SD;
+    if (KIND == GCBF_ENV_DUBINS_CAR) {
+        es[0] = s[0];
+        es[1] = s[1];
+        es[2] = s[3] * cosf(s[2]);
+        es[3] = s[3] * sinf(s[2]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < SD; ++c) es[c] = s[c];
+    }
+}
+
+// Sender edge-state for an edge code (see gcbf_b200.h): agent / goal / hit node.
+template <int KIND>
+__device__ __forceinline__ void sender_state_dev(int code, int a, int R, const float* agent, const float* goal,
+                                                 const float* hits, float* es) {
+    using T = EnvTraits<KIND>;
+    constexpr int SD = T::SD, PD = T::PD, ED = T::ED;
+    if (code >= 0) {
+        edge_state_dev<KIND>(agent + (size_t)code * SD, es);
+    } else if (code == -1) {
+        edge_state_dev<KIND>(goal + (size_t)a * SD, es);
+    } else {
+        const int k = min(-2 - code, R - 1);
+        const float* h = hits + ((size_t)a * R + k) * PD;
+#pragma unroll
+        for (int c = 0; c < ED; ++c) es[c] = (c < PD) ? h[c] : 0.f;
+    }
+}
+
+// feat = es(recv) - es(send), position part norm-clipped when `clip`
+// (double_integrator.py:239-244 / 279-284).  Returns the clip coefficient and raw norm.
+template <int KIND>
+__device__ __forceinline__ void edge_feat_dev(const float* er, const float* es, bool clip, float rc, float* feat,
+                                              float* coef_out, float* nrm_out) {
+    using T = EnvTraits<KIND>;
+    constexpr int PD = T::PD, ED = T::ED;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < ED; ++c) {
+        feat[c] = er[c] - es[c];
+        if (c < PD) sq += feat[c] * feat[c];
+    }
+    float coef = 1.f;
+    const float nrm = sqrtf(1e-6f + sq);
+    if (clip && nrm > rc) coef = rc / fmaxf(nrm, rc);
+    if (clip) {
+#pragma unroll
+        for (int c = 0; c < PD; ++c) feat[c] *= coef;
+    }
+    *coef_out = coef;
+    *nrm_out = nrm;
+}
+
+// ---- edge features + message layer 1: X1 = relu(feat @ W1[:ed] + W1[ed + sender_type] + W1[ed+3+2] + b1)
+// one warp per edge (grid-stride); lane owns 8 output columns.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+edge_l1_kernel(const gcbf_env_desc d, const float* __restrict__ W1, const float* __restrict__ b1,
+               const float* __restrict__ agent, const float* __restrict__ goal, const float* __restrict__ hits,
+               const int32_t* __restrict__ edge_recv, const int32_t* __restrict__ edge_src,
+               const int32_t* __restrict__ counters, const int clip_all, float* __restrict__ feat_out,
+               float* __restrict__ X1) {
+    using T = EnvTraits<KIND>;
+    constexpr int ED = T::ED, SD = T::SD;
+    __shared__ __align__(16) float sW[ED][256];
+    __shared__ __align__(16) float sB[3][256];  // [hit, goal, agent] sender one-hot rows + receiver row + bias
+    for (int i = threadIdx.x; i < ED * 256; i += blockDim.x) sW[i / 256][i % 256] = W1[i];
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+        const int t = i / 256, c = i % 256;
+        sB[t][c] = W1[(ED + t) * 256 + c] + W1[(ED + 3 + 2) * 256 + c] + b1[c];
+    }
+    __syncthreads();
+    const int nE = min(counters[0], d.edge_cap);
+    const int A = d.n_graphs * d.n_agents;
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < nE; e += warps_total) {
+        const int a = min(max(edge_recv[e], 0), A - 1);
+        int code = edge_src[e];
+        code = min(code, A - 1);
+        float er[ED], es[ED], f[ED], coef, nrm;
+        edge_state_dev<KIND>(agent + (size_t)a * SD, er);
+        sender_state_dev<KIND>(code, a, d.n_hits, agent, goal, hits, es);
+        edge_feat_dev<KIND>(er, es, clip_all || code == -1, d.comm_radius, f, &coef, &nrm);
+        const int t = (code >= 0) ? 2 : ((code == -1) ? 1 : 0);
+        if (lane < ED) feat_out[(size_t)e * FEAT_LD + lane] = f[lane];
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = sB[t][lane * 8 + j];
+#pragma unroll
+        for (int c = 0; c < ED; ++c) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = fmaf(f[c], sW[c][lane * 8 + j], y[j]);
+        }
+        float4* dst = reinterpret_cast<float4*>(X1 + (size_t)e * 256 + lane * 8);
+        dst[0] = make_float4(fmaxf(y[0], 0.f), fmaxf(y[1], 0.f), fmaxf(y[2], 0.f), fmaxf(y[3], 0.f));
+        dst[1] = make_float4(fmaxf(y[4], 0.f), fmaxf(y[5], 0.f), fmaxf(y[6], 0.f), fmaxf(y[7], 0.f));
+    }
+}
+
+// ---- gate logit + segment softmax + weighted aggregation (gnn.py:64-72); warp per receiver.
+// gate = G2 @ a3 + ba3 ; att = softmax over the receiver's edges ; AG[a] = sum att * MSG.
+__global__ void __launch_bounds__(256)
+attn_aggregate_kernel(const int A, const int edge_cap, const float* __restrict__ G2, const float* __restrict__ MSG,
+                      const float* __restrict__ a3, const float* __restrict__ ba3,
+                      const int32_t* __restrict__ row_start, const int32_t* __restrict__ row_deg,
+                      float* __restrict__ ATT, float* __restrict__ AG) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    const float4 w = *reinterpret_cast<const float4*>(a3 + lane * 4);
+    const float bias = ba3[0];
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < A; a += warps_total) {
+        const int rs = row_start[a];
+        int rd = row_deg[a];
+        if (rs < 0 || rs + rd > edge_cap) rd = 0;
+        float mx = -INFINITY;
+        for (int e = rs; e < rs + rd; ++e) {
+            const float4 g = *reinterpret_cast<const float4*>(G2 + (size_t)e * 128 + lane * 4);
+            float s = g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
+            s = warp_sum(s) + bias;
+            if (lane == 0) ATT[e] = s;
+            mx = fmaxf(mx, s);
+        }
+        __syncwarp();
+        float den = 0.f;
+        for (int e = rs; e < rs + rd; ++e) den += expf(ATT[e] - mx);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = rs; e < rs + rd; ++e) {
+            const float att = expf(ATT[e] - mx) / den;
+            const float4 m = *reinterpret_cast<const float4*>(MSG + (size_t)e * 128 + lane * 4);
+            acc.x = fmaf(att, m.x, acc.x);
+            acc.y = fmaf(att, m.y, acc.y);
+            acc.z = fmaf(att, m.z, acc.z);
+            acc.w = fmaf(att, m.w, acc.w);
+            __syncwarp();
+            if (lane == 0) ATT[e] = att;
+        }
+        *reinterpret_cast<float4*>(AG + (size_t)a * 128 + lane * 4) = acc;
+    }
+}
+
+// ---- output head: out = tanh(H2 @ W[256, nout] + b); warp per agent.
+__global__ void __launch_bounds__(256)
+head_out_kernel(const int A, const int nout, const float* __restrict__ H2, const float* __restrict__ W,
+                const float* __restrict__ b, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < A; a += warps_total) {
+        const float4 h0 = *reinterpret_cast<const float4*>(H2 + (size_t)a * 256 + lane * 8);
+        const float4 h1 = *reinterpret_cast<const float4*>(H2 + (size_t)a * 256 + lane * 8 + 4);
+        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        for (int j = 0; j < nout; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = fmaf(hv[k], W[(lane * 8 + k) * nout + j], s);
+            s = warp_sum(s) + b[j];
+            if (lane == 0) out[(size_t)a * nout + j] = tanhf(s);
+        }
+    }
+}
+
+}  // namespace gcbf

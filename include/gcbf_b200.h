@@ -1,0 +1,160 @@
+/*
+ * gcbf_b200.h -- C ABI of libgcbf_b200.so: the sm_100a hot path of GCBF+
+ * (batched rollout step + GCBF+ train step) behind plain pointers and sizes.
+ *
+ * The reference (MIT-REALM/gcbfplus) has NO FFI / plugin / operator layer: its hot
+ * path is XLA code generated from Python.  Each entry point
+ * below therefore names the reference *Python* function(s) it replaces
+ * (paths relative to the reference root); INTEGRATION.md shows the ctypes
+ * binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns all memory (inputs, outputs, workspace); the library never
+ *     allocates, frees or retains device memory across calls;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     re-entrant, and CUDA-graph capturable (no host sync, no allocation);
+ *   - return value: 0 = ok; < 0 = argument / configuration error, nothing was
+ *     enqueued; > 0 = cudaError_t of a failed launch.  gcbf_last_error_string()
+ *     describes the last non-zero return of the calling thread;
+ *   - fp32 everywhere, int32 indices, uint8 masks.
+ *
+ * Batch layout ("swarm batch"): G graphs x N agents, A = G*N.
+ *   agent  [G,N,sd]   goal [G,N,sd]   hits [G,N,R,pd]  (pd = 2 or 3)
+ *   obstacles: Rectangle [G,O,16] = cx,cy,w/2,h/2,cos,sin,p0x,p0y,...,p3x,p3y,0,0
+ *              Sphere    [G,O,4]  = cx,cy,cz,radius
+ *   edges (receiver-grouped lists, replaces utils/graph.py:35-44,209-244):
+ *     row_start[A], row_deg[A]; edge_recv[e] = global agent id of the receiver;
+ *     edge_src[e]  >= 0  : global agent id of the sending agent
+ *                  == -1 : the receiver's own goal node
+ *                  <= -2 : the receiver's hit node k = -2 - edge_src[e]
+ *     per receiver the order is [goal | agents ascending j | active hits ascending k].
+ */
+#ifndef GCBF_B200_H
+#define GCBF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCBF_ENV_SINGLE_INTEGRATOR 0
+#define GCBF_ENV_DOUBLE_INTEGRATOR 1
+#define GCBF_ENV_DUBINS_CAR 2
+#define GCBF_ENV_LINEAR_DRONE 3
+
+#define GCBF_NET_CBF 0
+#define GCBF_NET_ACTOR 1
+
+#define GCBF_MSG_HID 256
+#define GCBF_MSG_DIM 128
+
+/* Environment / batch descriptor.  Python-float constants of the reference are
+ * rounded to fp32 by the HOST exactly where JAX's weak typing rounds them (e.g.
+ * lidar_radius = float32(comm_radius - 1e-1)). */
+typedef struct gcbf_env_desc {
+    int32_t env_kind;       /* GCBF_ENV_* */
+    int32_t n_graphs;       /* G */
+    int32_t n_agents;       /* N */
+    int32_t n_obs;          /* O obstacles per graph (0 allowed) */
+    int32_t n_rays;         /* rays cast per agent (2-D: n_rays <= 32; 3-D: (n/2)*n+2) */
+    int32_t n_hits;         /* R hit nodes kept per agent */
+    int32_t edge_cap;       /* capacity of edge_recv / edge_src and of per-edge workspaces */
+    int32_t obs_per_graph;  /* 1: obstacles [G,O,..]; 0: one obstacle set shared by all graphs */
+    float comm_radius;      /* params["comm_radius"] */
+    float comm_radius_p1;   /* comm_radius + 1 (self-edge removal, double_integrator.py:230) */
+    float lidar_radius;     /* comm_radius - 1e-1 (double_integrator.py:257) */
+    float dt;               /* env/__init__.py:44 */
+    float mass;             /* DoubleIntegrator params["m"] */
+    float radius;           /* car_radius / drone_radius */
+    float two_r;            /* radius * 2 */
+    float two_r_p1;         /* radius * 2 + 1 */
+    float half_r;           /* radius * 0.5 (Dubins stop mask) */
+    float unsafe_agent;     /* agent-agent unsafe distance (2r; LinearDrone 2.5r) */
+    float unsafe_obs;       /* obstacle inflation in unsafe_mask (r; Dubins/LD 1.5r) */
+    float warn_agent;       /* 3r */
+    float warn_obs;         /* 2r */
+    float four_r_sq;        /* 4 * r**2 */
+    float r_sq;             /* r**2 */
+    float safe_agent;       /* safe_mask distance (4r; SI 2.5r) */
+    float safe_obs;         /* safe_mask inflation (2r; SI 1.5r) */
+    float v_lim;            /* state_lim on velocity components (inf if none) */
+    float u_lim;            /* action_lim */
+    float K[18];            /* LQR gain [nu, sd] row-major (u_ref), fp32 */
+    float A[36];            /* LinearDrone A [sd,sd] row-major (continuous), fp32 */
+    float B[18];            /* LinearDrone B [sd,nu] row-major, fp32 */
+} gcbf_env_desc;
+
+/* ---------------------------------------------------------------- misc */
+const char* gcbf_last_error_string(void);
+int32_t gcbf_version(void);
+/* number of thread-block launches of this library's kernels since process start
+ * (host-side counter; used by bench.py for "gpu_launches"). */
+int64_t gcbf_launch_count(void);
+/* size in floats of one network's flat parameter buffer and the offset table
+ * (24 entries: W,b of the 12 Dense layers in forward order). */
+int32_t gcbf_param_count(int32_t edge_dim, int32_t out_dim);
+int32_t gcbf_param_offsets(int32_t edge_dim, int32_t out_dim, int32_t* offsets24_host);
+
+/* ---------------------------------------------------------------- graph build (a1,a2,a3)
+ * Replaces env.get_graph: get_lidar/raytracing/inside_obstacles
+ * (gcbfplus/env/utils.py:49-131, env/obstacle.py:53-96,234-270) and edge_blocks +
+ * GetGraph.to_padded (env/double_integrator.py:223-264,288-320;
+ * utils/graph.py:35-44,209-244) for G graphs at once.
+ * flags bit0: 1 = cast rays and write `hits`; 0 = `hits` is an input (topology only).
+ * counters[0] <- number of edges; counters[1] |= 1 on edge_cap overflow (sticky). */
+int32_t gcbf_graph_build(const gcbf_env_desc* desc, const float* agent, const float* obstacles,
+                         const float* ray_table, float* hits, int32_t* row_start, int32_t* row_deg,
+                         int32_t* edge_recv, int32_t* edge_src, int32_t* counters, int32_t flags,
+                         void* stream);
+
+/* ---------------------------------------------------------------- GNN forward (a4,a5)
+ * Replaces CBF.get_cbf / DeterministicPolicy.get_action: GNNLayer + head MLP + tanh
+ * (gcbfplus/nn/gnn.py:44-104, nn/mlp.py:6-30, algo/module/cbf.py:12-53,
+ * algo/module/policy.py:63-128), including env.add_edge_feats when clip_all = 1
+ * (env/double_integrator.py:275-286).
+ * params: flat fp32 buffer (gcbf_param_offsets).  out: [A, out_dim] (tanh applied).
+ * workspace: gcbf_gnn_workspace_floats() floats; holds the saved activations
+ * the backward pass reads. */
+int64_t gcbf_gnn_workspace_floats(const gcbf_env_desc* desc, int32_t out_dim);
+int32_t gcbf_gnn_forward(const gcbf_env_desc* desc, int32_t net_kind, int32_t out_dim,
+                         const float* params, const float* agent, const float* goal, const float* hits,
+                         const int32_t* row_start, const int32_t* row_deg, const int32_t* edge_recv,
+                         const int32_t* edge_src, const int32_t* counters, int32_t clip_all, float* out,
+                         float* workspace, int64_t workspace_floats, void* stream);
+
+/* ---------------------------------------------------------------- env step (a6,a7)
+ * Replaces GCBFPlus.act/step (algo/gcbf_plus.py:176-186: a = 2 pi + u_ref) and
+ * env.step minus get_graph (env/double_integrator.py:145-198: clip_action,
+ * agent_step_euler, reward, get_cost).
+ * mode 0: action <- 2*pi + u_ref (output);  mode 1: `action` is an INPUT (env.step(graph, action));
+ * mode 2: action <- u_ref (test.py --u-ref).
+ * Outputs: action [A,nu] (unclipped a, what the rollout records), next_agent [A,sd],
+ * reward [G], cost [G]. */
+int32_t gcbf_env_step(const gcbf_env_desc* desc, const float* agent, const float* goal,
+                      const float* obstacles, const float* pi, const int32_t* row_start,
+                      const int32_t* row_deg, const int32_t* edge_src, float* action,
+                      float* next_agent, float* reward, float* cost, int32_t mode, void* stream);
+/* action [A,nu] <- (pi ? 2*pi : 0) + u_ref(agent, goal): GCBFPlus.act (algo/gcbf_plus.py:176-180)
+ * and env.u_ref (env/double_integrator.py:332-338, env/dubins_car.py:328-379). */
+int32_t gcbf_act(const gcbf_env_desc* desc, const float* agent, const float* goal, const float* pi,
+                 float* action, void* stream);
+
+/* ---------------------------------------------------------------- labels / masks (a9)
+ * Replaces env.unsafe_mask / collision_mask / finish_mask / safe_mask
+ * (env/double_integrator.py:356-440 and twins).  Any output pointer may be NULL.
+ * Outputs uint8 [A]. */
+int32_t gcbf_masks(const gcbf_env_desc* desc, const float* agent, const float* goal,
+                   const float* hits, const float* obstacles, uint8_t* unsafe, uint8_t* collision,
+                   uint8_t* finish, uint8_t* safe, void* stream);
+/* GCBFPlus.safe_mask horizon labelling (algo/gcbf_plus.py:160-174).
+ * unsafe/safe: uint8 [n_rollouts, T, N]. */
+int32_t gcbf_safe_horizon(const uint8_t* unsafe, uint8_t* safe, int32_t n_rollouts, int32_t T,
+                          int32_t n_agents, int32_t horizon, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCBF_B200_H */

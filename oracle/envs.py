@@ -136,6 +136,19 @@ class OracleEnv:
             acc = acc + x[..., k] * x[..., k]
         return torch.sqrt(acc)
 
+    @staticmethod
+    def _matvec(x: torch.Tensor, M: torch.Tensor, zero_init: bool = False) -> torch.Tensor:
+        """x @ M.T with an explicit left-to-right sum of separately rounded products
+        (the reference's XLA dot has no specified order; this is the order the CUDA path uses)."""
+        cols = []
+        for r in range(M.shape[0]):
+            acc = torch.zeros_like(x[:, 0]) if zero_init else None
+            for c in range(M.shape[1]):
+                t = x[:, c] * M[r, c]
+                acc = t if acc is None else acc + t
+            cols.append(acc)
+        return torch.stack(cols, dim=-1)
+
     def state_lim(self):
         inf = float("inf")
         lim = {"SingleIntegrator": [inf, inf], "DoubleIntegrator": [inf, inf, 0.5, 0.5],
@@ -277,7 +290,7 @@ class OracleEnv:
         error_max = torch.abs(error / nrm * self._c(self.comm_radius))
         error = torch.minimum(torch.maximum(error, -error_max), error_max)
         K = torch.tensor(np.asarray(self.K), dtype=self.dtype)
-        return self.clip_action(error @ K.T)
+        return self.clip_action(self._matvec(error, K))
 
     def _u_ref_dubins(self, agent, goal):
         """dubins_car.py:328-379."""
@@ -319,7 +332,7 @@ class OracleEnv:
                                 action[:, 0] * 20.0, action[:, 1]], dim=1)
         A = torch.tensor(self._A, dtype=self.dtype)              # linear_drone.py:130-134
         B = torch.tensor(self._B, dtype=self.dtype)
-        return agent @ A.T + action @ B.T
+        return self._matvec(agent, A, zero_init=True) + self._matvec(action, B, zero_init=True)
 
     def agent_step_euler(self, agent, action, goal=None):
         """double_integrator.py:128-135; Dubins :104-110 (with stop mask)."""
