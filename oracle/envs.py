@@ -21,7 +21,7 @@ import numpy as np
 import scipy.linalg
 import torch
 
-from .geometry import (Rectangle, Sphere, get_lidar_all, inside_obstacles, ray_table_2d,
+from .geometry import (Rectangle, Sphere, exact_sqrt, get_lidar_all, inside_obstacles, ray_table_2d,
                        ray_table_3d)
 
 AGENT, GOAL, OBS = 0, 1, 2
@@ -134,7 +134,7 @@ class OracleEnv:
         acc = x[..., 0] * x[..., 0]
         for k in range(1, x.shape[-1]):
             acc = acc + x[..., k] * x[..., k]
-        return torch.sqrt(acc)
+        return exact_sqrt(acc)
 
     @staticmethod
     def _matvec(x: torch.Tensor, M: torch.Tensor, zero_init: bool = False) -> torch.Tensor:
@@ -182,7 +182,7 @@ class OracleEnv:
         sq = feats[:, 0] * feats[:, 0]
         for k in range(1, pd):
             sq = sq + feats[:, k] * feats[:, k]
-        feats_norm = torch.sqrt(1e-6 + sq)[:, None]
+        feats_norm = exact_sqrt(1e-6 + sq)[:, None]
         cr = self._c(self.comm_radius)
         safe = torch.maximum(feats_norm, cr)
         coef = torch.where(feats_norm > cr, cr / safe, torch.ones_like(feats_norm))
@@ -311,7 +311,7 @@ class OracleEnv:
         omega = torch.where(c2 & (theta > pi), -k_omega * theta_between, omega)
         omega = torch.where((~c2) & (theta > pi), k_omega * theta_between, omega)
         omega = torch.clamp(omega, -5.0, 5.0)
-        nrm = torch.sqrt(1e-6 + (pos_diff[:, 0] * pos_diff[:, 0] + pos_diff[:, 1] * pos_diff[:, 1]))[:, None]
+        nrm = exact_sqrt(1e-6 + (pos_diff[:, 0] * pos_diff[:, 0] + pos_diff[:, 1] * pos_diff[:, 1]))[:, None]
         cr = self._c(self.comm_radius)
         coef = torch.where(nrm > cr, cr / torch.maximum(nrm, cr), torch.ones_like(nrm))
         pd2 = coef * pos_diff
@@ -427,8 +427,8 @@ class OracleEnv:
         else:
             heading = torch.stack([torch.cos(g.agent[:, 2]), torch.sin(g.agent[:, 2])], dim=1)[:, None, :]
         inner = (pos_vec * heading)[..., 0] + (pos_vec * heading)[..., 1]
-        th_a = torch.atan2(self._c(r * 2).expand_as(agent_dist), torch.sqrt(agent_dist ** 2 - 4 * r ** 2))
-        th_o = torch.atan2(self._c(r).expand_as(obs_dist), torch.sqrt(obs_dist ** 2 - r ** 2))
+        th_a = torch.atan2(self._c(r * 2).expand_as(agent_dist), exact_sqrt(agent_dist ** 2 - 4 * r ** 2))
+        th_o = torch.atan2(self._c(r).expand_as(obs_dist), exact_sqrt(obs_dist ** 2 - r ** 2))
         theta = torch.cat([th_a, th_o], dim=1)
         lidar_mask = torch.block_diag(*[torch.ones(1, R)] * N).bool()
         valid = torch.cat([torch.ones(N, N, dtype=torch.bool), lidar_mask], dim=-1)

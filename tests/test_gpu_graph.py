@@ -25,6 +25,7 @@ CASES = [  # env, N, G, area, n_obs, n_rays
 def _build(env_id, N, G, area, n_obs, n_rays, seed):
     agent, goal, obs = random_scene(env_id, N, G, area, n_obs, seed)
     env = product_env(env_id, N, area, n_obs, n_rays)
+    env.edge_cap_per_agent = 64
     pobs = product_obstacles(env_id, obs)
     graph = env.get_graph(torch.from_numpy(agent).cuda(), torch.from_numpy(goal).cuda(), pobs)
     torch.cuda.synchronize()

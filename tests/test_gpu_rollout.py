@@ -1,0 +1,70 @@
+"""GPU parity: closed-loop rollout (CUDA-graph engine) vs the oracle's rollout from identical
+initial conditions with the reference's pretrained weights.  Bar: trajectories
+within a tolerance that grows with t (chaotic closed loop, fp32 summation order), safe / finish /
+success rates (test.py:184-198) identical."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (oracle_env, oracle_obstacles, oracle_params, product_algo, product_env, random_scene)
+
+pytestmark = pytest.mark.gpu
+
+
+def _reset_scene(env_id, N, E, area, n_obs, seed):
+    env = product_env(env_id, N, area, n_obs)
+    graph = env.reset(seed, n_envs=E)
+    return env, graph
+
+
+@pytest.mark.parametrize("env_id,N,E,area,n_obs,T", [("DoubleIntegrator", 8, 3, 2.0, 4, 96),
+                                                      ("SingleIntegrator", 8, 2, 2.0, 4, 64),
+                                                      ("DubinsCar", 8, 2, 2.5, 4, 64),
+                                                      ("LinearDrone", 8, 2, 1.2, 3, 48)])
+def test_rollout_matches_oracle(env_id, N, E, area, n_obs, T):
+    from gcbfplus_b200.trainer.rollout import RolloutEngine
+    from oracle.algo import rates, rollout
+    env, g0 = _reset_scene(env_id, N, E, area, n_obs, seed=11)
+    algo = product_algo(env, env_id)
+    eng = RolloutEngine(env, E, T=T, n_obs=n_obs)
+    eng.set_params(algo.actor_params)
+    eng.set_initial(g0.agent, g0.goal, g0.obstacle)
+    eng.run()
+    torch.cuda.synchronize()
+    first = {k: getattr(eng, k).clone() for k in ("agent", "hits", "actions", "rewards", "costs")}
+    eng.run()                                   # CUDA-graph replay must be bit-reproducible
+    torch.cuda.synchronize()
+    for k, v in first.items():
+        assert torch.equal(v, getattr(eng, k)) or (torch.isnan(v) == torch.isnan(getattr(eng, k))).all(), k
+    # eager (no graph) engine gives the same bits
+    eng2 = RolloutEngine(env, E, T=T, n_obs=n_obs, use_cuda_graph=False)
+    eng2.set_params(algo.actor_params)
+    eng2.set_initial(g0.agent, g0.goal, g0.obstacle)
+    eng2.run()
+    torch.cuda.synchronize()
+    assert torch.equal(eng2.agent, eng.agent)
+    res = eng.result()
+    col, fin = env.rollout_masks(_as_rollout_result(res))
+    oenv = oracle_env(env_id, N, area, n_obs)
+    ap, _ = oracle_params(env_id)
+    packed = g0.obstacle.packed.cpu().numpy()
+    for e in range(E):
+        ref = rollout(oenv, ap, g0.agent[e].cpu(), g0.goal[e].cpu(), oracle_obstacles(packed[e]), T=T)
+        got = res.agent[e].cpu().numpy()
+        want = ref["states"].numpy()
+        err = np.abs(got - want).reshape(T + 1, -1).max(axis=1)
+        assert err[1] <= 2e-6, err[:4]
+        assert err[: T // 4].max() <= 1e-4, err[: T // 4].max()
+        assert err.max() <= 5e-3, err.max()
+        np.testing.assert_allclose(res.rewards[e].cpu().numpy(), ref["rewards"].numpy(), atol=5e-3)
+        got_rates = rates(col[:, e].cpu().numpy(), fin[:, e].cpu().numpy())
+        want_rates = rates(ref["collision"].numpy(), ref["finish"].numpy())
+        assert got_rates == want_rates, (got_rates, want_rates)
+
+
+def _as_rollout_result(res):
+    from gcbfplus_b200.env.base import RolloutResult
+    g = {"agent": res.agent.transpose(0, 1).contiguous(), "goal": res.goal, "hits": res.hits.transpose(0, 1).contiguous(),
+         "obstacle": res.obstacle}
+    return RolloutResult(g, res.actions.transpose(0, 1), res.rewards.transpose(0, 1), res.costs.transpose(0, 1),
+                         res.dones.transpose(0, 1), {})
