@@ -54,6 +54,9 @@ _SIGNATURES = {
     "gcbf_act": (C.c_int32, [C.POINTER(EnvDesc)] + [_P] * 5),
     "gcbf_masks": (C.c_int32, [C.POINTER(EnvDesc)] + [_P] * 9),
     "gcbf_safe_horizon": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "gcbf_gemm_nn": (C.c_int32, [C.c_int32, C.c_int32] + [_P] * 7 + [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "gcbf_gemm_tn": (C.c_int32, [_P, C.c_int32] + [_P] * 5 + [C.c_int32] * 5 + [_P]),
+    "gcbf_colsum": (C.c_int32, [_P] * 5 + [C.c_int32] * 4 + [_P]),
     "gcbf_train_workspace_floats": (C.c_int64, [C.POINTER(EnvDesc)]),
     "gcbf_train_step": (C.c_int32, [C.POINTER(EnvDesc), C.POINTER(C.c_float)] + [_P] * 18 + [C.c_int64, _P]),
     "gcbf_grad_sqnorm": (C.c_int32, [_P, C.c_int32, _P, _P]),

@@ -86,3 +86,36 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_gnn_forward(const
     return gnn_forward_impl(desc, out_dim, params, agent, goal, hits, row_start, row_deg, edge_recv, edge_src, counters,
                             clip_all, out, workspace, (cudaStream_t)stream);
 }
+
+// ---- building blocks exported for unit tests and for bench.py's isolated kernel timing ----
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_gemm_nn(int32_t epi, int32_t accum, const float* A,
+                                                                       const float* B, const float* bias,
+                                                                       const float* bias2, float* C, const float* aux,
+                                                                       const int32_t* m_ptr, int32_t m_fixed,
+                                                                       int32_t m_cap, int32_t K, int32_t N,
+                                                                       void* stream) {
+    GCBF_REQUIRE(A && B && C, "gcbf_gemm_nn: NULL pointer");
+    GCBF_REQUIRE((epi != EPI_BIAS && epi != EPI_BIAS_RELU) || bias, "gcbf_gemm_nn: bias required");
+    GCBF_REQUIRE(epi != EPI_RELU_MASK || aux, "gcbf_gemm_nn: aux required");
+    return launch_gemm_nn(epi, accum != 0, A, B, bias, bias2, C, aux, RowCount{m_ptr, m_fixed, m_cap}, K, N,
+                          (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_gemm_tn(const float* X, int32_t ldx, const float* dY,
+                                                                       float* C, const float* roww,
+                                                                       const int32_t* row2agent, const int32_t* m_ptr,
+                                                                       int32_t m_fixed, int32_t m_cap, int32_t K1,
+                                                                       int32_t N, int32_t n_agents_total, void* stream) {
+    GCBF_REQUIRE(X && dY && C, "gcbf_gemm_tn: NULL pointer");
+    return launch_gemm_tn(X, ldx, dY, C, roww, row2agent, RowCount{m_ptr, m_fixed, m_cap}, K1, N, n_agents_total,
+                          (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_colsum(const float* dY, float* db, const float* roww,
+                                                                      const int32_t* row2agent, const int32_t* m_ptr,
+                                                                      int32_t m_fixed, int32_t m_cap, int32_t N,
+                                                                      int32_t n_agents_total, void* stream) {
+    GCBF_REQUIRE(dY && db, "gcbf_colsum: NULL pointer");
+    return launch_colsum(dY, db, roww, row2agent, RowCount{m_ptr, m_fixed, m_cap}, N, n_agents_total,
+                         (cudaStream_t)stream);
+}

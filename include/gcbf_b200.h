@@ -154,6 +154,26 @@ int32_t gcbf_masks(const gcbf_env_desc* desc, const float* agent, const float* g
 int32_t gcbf_safe_horizon(const uint8_t* unsafe, uint8_t* safe, int32_t n_rollouts, int32_t T,
                           int32_t n_agents, int32_t horizon, void* stream);
 
+/* ---------------------------------------------------------------- dense-layer building blocks
+ * The fp32 GEMM family the MLPs are made of (flax nn.Dense, gcbfplus/nn/mlp.py:19-21, and its
+ * autodiff transposes).  Exported so the kernels can be unit-tested against a plain fp32
+ * reference and timed in isolation by bench.py; row-major contiguous operands.
+ * gemm_nn: C[M,N] = epi(A[M,K] @ B[K,N]);  epi 0: +bias(+bias2), 1: relu(+bias(+bias2)),
+ *          2: none, 3: aux > 0 ? acc : 0;  accum != 0: C += (epi 2/3 only).
+ *          M = *m_ptr (device) if m_ptr else m_fixed, clamped to m_cap.  K % 16 == 0, N % 128 == 0.
+ * gemm_tn: C[K1,N] += sum_m w(m) X[m, :K1] dY[m, :N]  (ldx = row stride of X; w optional:
+ *          roww[row2agent ? row2agent[m] : m]).  K1, N multiples of 128.
+ * colsum : db[N] += sum_m w(m) dY[m, :N], N <= 256. */
+int32_t gcbf_gemm_nn(int32_t epi, int32_t accum, const float* A, const float* B, const float* bias,
+                     const float* bias2, float* C, const float* aux, const int32_t* m_ptr,
+                     int32_t m_fixed, int32_t m_cap, int32_t K, int32_t N, void* stream);
+int32_t gcbf_gemm_tn(const float* X, int32_t ldx, const float* dY, float* C, const float* roww,
+                     const int32_t* row2agent, const int32_t* m_ptr, int32_t m_fixed, int32_t m_cap,
+                     int32_t K1, int32_t N, int32_t n_agents_total, void* stream);
+int32_t gcbf_colsum(const float* dY, float* db, const float* roww, const int32_t* row2agent,
+                    const int32_t* m_ptr, int32_t m_fixed, int32_t m_cap, int32_t N,
+                    int32_t n_agents_total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,197 @@
+"""CPU: pins the oracle against everything the reference offers for this path:
+LQR gains, parameter trees of the pretrained pickles, closed-form geometry, the
+dense (reference layout) == sparse equivalence, label semantics, optimizer restatement."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, ENVS, oracle_env, oracle_obstacles, oracle_params, random_scene
+from oracle.algo import (AdamW, act, compute_norm_and_clip, gcbf_plus_loss, get_cbf, polyak, rates, rollout,
+                         safe_mask_horizon, train_step)
+from oracle.envs import OracleEnv
+from oracle.geometry import Rectangle, Sphere, get_lidar, ray_table_2d, ray_table_3d
+
+
+def test_lqr_gains_known_answers():
+    """SURVEY 8a6 (recomputed there with scipy 1.18 from the reference's A, B, Q, R)."""
+    K = OracleEnv("DoubleIntegrator", 2, 4.0).K
+    np.testing.assert_allclose(K, [[1.5850302, 0, 1.70600375, 0], [0, 1.5850302, 0, 1.70600375]], atol=1e-7)
+    K = OracleEnv("SingleIntegrator", 2, 4.0).K
+    np.testing.assert_allclose(K, 1.38453172 * np.eye(2), atol=1e-7)
+    K = OracleEnv("LinearDrone", 2, 2.0).K
+    np.testing.assert_allclose(np.diag(K[:, :3]), [0.63123451, 0.63123451, 0.6365321], atol=1e-7)
+    np.testing.assert_allclose(np.diag(K[:, 3:]), [0.11461079, 0.11461079, 0.10032613], atol=1e-7)
+
+
+@pytest.mark.parametrize("env_id,n_actor,n_cbf", [("SingleIntegrator", 365955, 365698), ("DoubleIntegrator", 366467, 366210),
+                                                 ("DubinsCar", 366467, 366210), ("LinearDrone", 367236, 366722)])
+def test_pretrained_fixture_counts(env_id, n_actor, n_cbf):
+    z = np.load(os.path.join(GOLDEN, f"params_{env_id}.npz"))
+    assert sum(z[k].size for k in z.files if k.startswith("actor:")) == n_actor
+    assert sum(z[k].size for k in z.files if k.startswith("cbf:")) == n_cbf
+    ed = {"SingleIntegrator": 2, "DoubleIntegrator": 4, "DubinsCar": 4, "LinearDrone": 6}[env_id]
+    assert z["cbf:params/GNN_0/GNNLayer_0/msg/Dense_0/kernel"].shape == (ed + 6, 256)
+    assert z["cbf:params/GNN_0/GNNLayer_0/update/Dense_0/kernel"].shape == (131, 256)
+
+
+def test_fixture_equals_reference_pickle_when_reference_is_mounted():
+    ref = "/root/reference/pretrained/DoubleIntegrator/gcbf+/models/1000/cbf.pkl"
+    if not os.path.exists(ref):
+        pytest.skip("reference not mounted (GPU box)")
+    from oracle.nn import flatten_params, load_ref_pickle
+    flat = flatten_params(load_ref_pickle(ref))
+    z = np.load(os.path.join(GOLDEN, "params_DoubleIntegrator.npz"))
+    for k, v in flat.items():
+        np.testing.assert_array_equal(z["cbf:" + k], v)
+
+
+def test_rectangle_raycast_closed_form():
+    """Axis-aligned unit square at (2,0): ray from origin along +x hits at x = 1.5."""
+    rect = Rectangle.create([[2.0, 0.0]], [1.0], [1.0], [0.0])
+    tab = ray_table_2d(32, 2.0)                       # ray 16 is theta = 0, rays 15/17 are -/+ 11.25 deg
+    hits = get_lidar(torch.tensor([0.0, 0.0]), rect, tab, 32)
+    t = 1.5 * np.tan(np.pi / 16)
+    got = sorted(hits[:2].tolist(), key=lambda p: p[1])
+    np.testing.assert_allclose(got, [[1.5, -t], [1.5, t]], atol=1e-6)
+    # reference quirk kept: the exactly horizontal ray is parallel to two edges of an axis-aligned
+    # rectangle -> det == 0 -> sign(0) * clip = 0 -> alpha = x/0 -> NaN through jnp.min; NaNs sort last
+    assert torch.isnan(hits[-1]).any()
+    # rays that miss land 1e6 ranges away (obstacle.py:94)
+    assert hits[-2].abs().max() > 1e5
+    # inside the obstacle: every alpha is 0 -> all hit points equal the start (env/utils.py:124)
+    hits_in = get_lidar(torch.tensor([2.0, 0.1]), rect, tab, 32)
+    assert torch.equal(hits_in[:31], torch.tensor([2.0, 0.1]).expand(31, 2))      # (NaN * 0 = NaN: the quirk ray)
+    assert rect.inside(torch.tensor([[2.0, 0.0], [2.55, 0.0], [2.6, 0.6]]), 0.1).squeeze(-1).tolist() == [True, True, False]
+
+
+def test_sphere_raycast_closed_form_and_topk():
+    sph = Sphere.create([[0.0, 0.0, 1.0]], [0.25])
+    tab = ray_table_3d(32, 2.0)
+    assert tab.shape == (514, 3)
+    hits = get_lidar(torch.tensor([0.0, 0.0, 0.0]), sph, tab, 16)
+    assert hits.shape == (16, 3)
+    # closest return is the +z pole ray: hit at z = 0.75
+    np.testing.assert_allclose(hits[0].numpy(), [0, 0, 0.75], atol=1e-6)
+    assert (hits.norm(dim=-1)[1:] >= hits.norm(dim=-1)[:-1] - 1e-6).all()     # sorted by alpha
+
+
+def test_zero_obstacles_all_rays_miss():
+    hits = get_lidar(torch.tensor([1.0, 1.0]), None, ray_table_2d(32, 0.5), 32)
+    assert (hits.abs().max(dim=-1).values > 1e4).all()
+
+
+@pytest.mark.parametrize("env_id", ENVS)
+def test_dense_reference_layout_equals_sparse(env_id):
+    N, area, n_obs = 8, 1.6, 4
+    agent, goal, obs = random_scene(env_id, N, 1, area, n_obs, seed=4)
+    oenv = oracle_env(env_id, N, area, n_obs)
+    from helpers import product_obstacles
+    pobs = product_obstacles(env_id, obs, device="cpu")
+    oobs = oracle_obstacles(pobs.packed.numpy()[0])
+    dense = oenv.get_graph(torch.from_numpy(agent[0]), torch.from_numpy(goal[0]), oobs)
+    sparse = oenv.sparsify(dense)
+    R = oenv.n_hits
+    assert dense.edges.shape[0] == (2 * N * N + N * R if env_id != "DubinsCar" else N * N + N + N * R)
+    assert dense.nodes.shape[0] == 2 * N + N * R + 1
+    ap, cp = oracle_params(env_id)
+    with torch.no_grad():
+        np.testing.assert_allclose(get_cbf(cp, dense).numpy(), get_cbf(cp, sparse).numpy(), atol=2e-6)
+        a_d, a_s = act(oenv, ap, dense), act(oenv, ap, sparse)
+        np.testing.assert_allclose(a_d.numpy(), a_s.numpy(), atol=2e-6)
+        fd, fs = oenv.forward_graph(dense, a_d), oenv.forward_graph(sparse, a_d)
+        np.testing.assert_allclose(get_cbf(cp, fd).numpy(), get_cbf(cp, fs).numpy(), atol=2e-6)
+
+
+def test_cbf_sign_flips_at_collision_distance():
+    """SURVEY 4 smoke check: two agents head-on, h < 0 inside 2r = 0.1, h > 0 well outside."""
+    _, cp = oracle_params("DoubleIntegrator")
+    env = OracleEnv("DoubleIntegrator", 2, 4.0, params={"n_obs": 0})
+    hs = {}
+    for d in (0.05, 0.10, 0.20, 0.60):
+        agent = torch.tensor([[1.0, 1.0, 0.3, 0.0], [1.0 + d, 1.0, -0.3, 0.0]])
+        goal = torch.tensor([[3.0, 1.0, 0, 0], [0.0, 1.0, 0, 0]])
+        with torch.no_grad():
+            hs[d] = get_cbf(cp, env.sparsify(env.get_graph(agent, goal, None))).squeeze(-1)
+    assert (hs[0.05] < 0).all() and (hs[0.10] < 0).all() and (hs[0.20] > 0).all() and (hs[0.60] > 0).all()
+
+
+def test_safe_mask_horizon_semantics():
+    u = np.zeros((10, 2), dtype=bool)
+    u[6, 0] = True
+    s = safe_mask_horizon(u, 3)
+    assert s[:, 1].all()
+    assert s[:, 0].tolist() == [True, True, True, False, False, False, False, True, True, True]
+    u[0, 1] = True
+    assert safe_mask_horizon(u, 3)[0, 1]            # initial state always safe (gcbf_plus.py:170)
+
+
+def test_adamw_clip_polyak_restatement():
+    torch.manual_seed(0)
+    p = {"w": torch.randn(5, 3), "b": torch.randn(3)}
+    g = {"w": torch.randn(5, 3) * 10, "b": torch.randn(3) * 10}
+    gc, n = compute_norm_and_clip(g, 2.0)
+    assert abs(torch.sqrt(sum((v * v).sum() for v in gc.values())).item() - 2.0) < 1e-5
+    small = {k: v * 1e-3 for k, v in g.items()}
+    gs, _ = compute_norm_and_clip(small, 2.0)
+    torch.testing.assert_close(gs["w"], small["w"])                        # below max_norm: unchanged
+    opt, ref = AdamW(p, lr=1e-2), torch.optim.AdamW([torch.nn.Parameter(v.clone()) for v in p.values()], lr=1e-2,
+                                                   weight_decay=1e-3, eps=1e-8)
+    q = dict(p)
+    for _ in range(3):
+        q = opt.step(q, gc)
+        for prm, k in zip(ref.param_groups[0]["params"], p):
+            prm.grad = gc[k].clone()
+        ref.step()
+    # optax adamw decays with lr*wd*p inside the same update (equivalent to torch's decoupled form to O(lr^2 wd))
+    for prm, k in zip(ref.param_groups[0]["params"], p):
+        torch.testing.assert_close(q[k], prm.data, atol=1e-5, rtol=1e-4)
+    bad = {"w": gc["w"].clone(), "b": gc["b"].clone()}
+    bad["b"][0] = float("nan")
+    t_before = opt.t
+    assert opt.step(q, bad) is q and opt.t == t_before                     # apply_if_finite skips
+    pk = polyak({"w": torch.ones(2)}, {"w": torch.zeros(2)}, 0.5)
+    assert pk["w"].tolist() == [0.5, 0.5]
+
+
+def test_loss_gradient_routing_float64():
+    """update_inner semantics (gcbf_plus.py:399-407): for unlabelled agents the CBF parameters get
+    no gradient through h(g') / h_dot, but the actor still does."""
+    env_id, N, area = "DoubleIntegrator", 4, 1.2
+    agent, goal, obs = random_scene(env_id, N, 2, area, 2, seed=8)
+    from helpers import product_obstacles
+    pobs = product_obstacles(env_id, obs, device="cpu")
+    oenv = oracle_env(env_id, N, area, 2, dtype=torch.float64)
+    ap, cp = oracle_params(env_id, dtype=torch.float64)
+    cp = {k: v.clone().requires_grad_(True) for k, v in cp.items()}
+    ap = {k: v.clone().requires_grad_(True) for k, v in ap.items()}
+    graphs = [oenv.sparsify(oenv.get_graph(torch.from_numpy(agent[g]).double(), torch.from_numpy(goal[g]).double(),
+                                           oracle_obstacles(pobs.packed.numpy()[g], torch.float64))) for g in range(2)]
+    none = torch.zeros(2, N, dtype=torch.bool)
+    u_qp = torch.zeros(2, N, 2, dtype=torch.float64)
+    kw = dict(coef_action=0.0, coef_unsafe=0.0, coef_safe=0.0, coef_h_dot=1.0, eps=10.0)  # eps large: relu active
+    total, _ = gcbf_plus_loss(oenv, cp, ap, graphs, none, none, u_qp, **kw)
+    gc = torch.autograd.grad(total, list(cp.values()), retain_graph=True, allow_unused=True)
+    ga = torch.autograd.grad(total, list(ap.values()), allow_unused=True)
+    assert any(g is not None and g.abs().max() > 0 for g in ga)
+    # unlabelled: d/dcbf of relu(-h_dot_ng - alpha h + eps) = -alpha dh/dcbf only
+    h_only = sum(-1.0 * get_cbf(cp, g).sum() for g in graphs) / (2 * N)
+    gh = torch.autograd.grad(h_only, list(cp.values()), allow_unused=True)
+    for a, b in zip(gc, gh):
+        if a is not None:
+            torch.testing.assert_close(a, b, atol=1e-10, rtol=1e-8)
+
+
+def test_rollout_and_rates_smoke():
+    env_id, N, area = "DoubleIntegrator", 4, 2.0
+    agent, goal, obs = random_scene(env_id, N, 1, area, 2, seed=3, vel_scale=0.0)
+    from helpers import product_obstacles
+    pobs = product_obstacles(env_id, obs, device="cpu")
+    oenv = oracle_env(env_id, N, area, 2)
+    ap, _ = oracle_params(env_id)
+    out = rollout(oenv, ap, torch.from_numpy(agent[0]), torch.from_numpy(goal[0]),
+                  oracle_obstacles(pobs.packed.numpy()[0]), T=8)
+    assert out["states"].shape == (9, N, 4) and out["actions"].shape == (8, N, 2)
+    s, f, ok = rates(out["collision"].numpy(), out["finish"].numpy())
+    assert 0.0 <= s <= 1.0 and 0.0 <= f <= 1.0 and ok <= min(s, f) + 1e-9
