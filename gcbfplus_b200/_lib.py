@@ -58,6 +58,7 @@ _SIGNATURES = {
     "gcbf_gemm_tn": (C.c_int32, [_P, C.c_int32] + [_P] * 5 + [C.c_int32] * 5 + [_P]),
     "gcbf_colsum": (C.c_int32, [_P] * 5 + [C.c_int32] * 4 + [_P]),
     "gcbf_train_workspace_floats": (C.c_int64, [C.POINTER(EnvDesc)]),
+    "gcbf_mask_counts": (C.c_int32, [_P, _P, C.c_int32, _P, _P]),
     "gcbf_train_step": (C.c_int32, [C.POINTER(EnvDesc), C.POINTER(C.c_float)] + [_P] * 18 + [C.c_int64, _P]),
     "gcbf_grad_sqnorm": (C.c_int32, [_P, C.c_int32, _P, _P]),
     "gcbf_clip_adamw": (C.c_int32, [_P, _P, _P, _P, C.c_int32, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -1,0 +1,230 @@
+"""GCBF+ update -- host orchestration of gcbfplus/algo/gcbf_plus.py:198-297,354-447
+(update, sample_batch, update_nets, update_inner) on top of libgcbf_b200's train-step kernels.
+
+Per minibatch: gcbf_mask_counts -> [all-reduce counts] -> gcbf_train_step -> [ONE all-reduce of
+(grad_cbf | grad_actor | stats)] -> gcbf_grad_sqnorm + gcbf_clip_adamw per network.  No host
+synchronisation inside the minibatch loop; the info dict of the LAST minibatch is read back
+once per epoch loop (the reference returns the last minibatch's info, gcbf_plus.py:445-446).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..trainer.buffer import MaskedReplayBuffer
+from ..trainer.data import Rollout
+from ..utils.graph import SwarmGraph
+
+
+class TrainState:
+    """Optimizer state + packed gradient buffer for both networks (flax TrainState analogue)."""
+
+    def __init__(self, algo):
+        dev = algo._env.device
+        self.n_cbf = algo.cbf_params.count
+        self.n_act = algo.actor_net_params.count
+        f32 = torch.float32
+        # one contiguous buffer so that a sharded run needs ONE all-reduce per optimizer step
+        self.packed = torch.zeros(self.n_cbf + self.n_act + 16, dtype=f32, device=dev)
+        self.grad_cbf = self.packed[: self.n_cbf]
+        self.grad_act = self.packed[self.n_cbf: self.n_cbf + self.n_act]
+        self.stats = self.packed[self.n_cbf + self.n_act:]
+        self.m_cbf = torch.zeros(self.n_cbf, dtype=f32, device=dev)
+        self.v_cbf = torch.zeros(self.n_cbf, dtype=f32, device=dev)
+        self.m_act = torch.zeros(self.n_act, dtype=f32, device=dev)
+        self.v_act = torch.zeros(self.n_act, dtype=f32, device=dev)
+        self.step_cbf = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.step_act = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.norm_cbf = torch.zeros(2, dtype=f32, device=dev)
+        self.norm_act = torch.zeros(2, dtype=f32, device=dev)
+        self.denoms = torch.zeros(4, dtype=f32, device=dev)
+        self.ws: Optional[torch.Tensor] = None
+        self.ws_key = None
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def train_minibatch(algo, graph: SwarmGraph, safe_mask: torch.Tensor, unsafe_mask: torch.Tensor,
+                    u_qp: torch.Tensor, apply: bool = True) -> TrainState:
+    """One `update_fn` (gcbf_plus.py:356-441) on the (local shard of the) minibatch `graph`.
+    safe/unsafe_mask uint8 [B, N]; u_qp [B, N, nu].  Enqueues only (no host sync)."""
+    env = algo._env
+    lib = env.lib
+    if algo._trainer_state is None:
+        algo._trainer_state = TrainState(algo)
+    ts: TrainState = algo._trainer_state
+    B, N = graph.n_graphs, env.num_agents
+    d = env.desc(B, 0, edge_cap=graph.edge_recv.numel())
+    key = (B, d.edge_cap)
+    if ts.ws_key != key:
+        n = lib.gcbf_train_workspace_floats(C.byref(d))
+        if n <= 0:
+            raise RuntimeError("gcbf_train_workspace_floats failed")
+        ts.ws = None
+        ts.ws = torch.empty(int(n), dtype=torch.float32, device=env.device)
+        ts.ws_key = key
+    st = env._stream()
+    safe_mask = safe_mask.reshape(B * N).to(torch.uint8).contiguous()
+    unsafe_mask = unsafe_mask.reshape(B * N).to(torch.uint8).contiguous()
+    u_qp = u_qp.reshape(B * N, env.action_dim).float().contiguous()
+    _lib.check(lib.gcbf_mask_counts(_lib.ptr(safe_mask), _lib.ptr(unsafe_mask), B * N, _lib.ptr(ts.denoms), st),
+               "gcbf_mask_counts")
+    dist = _dist()
+    if dist is not None:
+        dist.all_reduce(ts.denoms)                      # global ratio-of-sums denominators
+    hp = (C.c_float * 6)(algo.alpha, algo.eps, algo.loss_action_coef, algo.loss_unsafe_coef, algo.loss_safe_coef,
+                         algo.loss_h_dot_coef)
+    rc = lib.gcbf_train_step(C.byref(d), hp, _lib.ptr(algo.cbf_params.flat), _lib.ptr(algo.actor_net_params.flat),
+                             _lib.ptr(graph.agent), _lib.ptr(graph.goal), _lib.ptr(graph.hits),
+                             _lib.ptr(graph.row_start), _lib.ptr(graph.row_deg), _lib.ptr(graph.edge_recv),
+                             _lib.ptr(graph.edge_src), _lib.ptr(graph.counters), _lib.ptr(safe_mask),
+                             _lib.ptr(unsafe_mask), _lib.ptr(u_qp), _lib.ptr(ts.denoms), _lib.ptr(ts.grad_cbf),
+                             _lib.ptr(ts.grad_act), _lib.ptr(ts.stats), _lib.ptr(ts.ws), ts.ws.numel(), st)
+    _lib.check(rc, "gcbf_train_step")
+    if dist is not None:
+        dist.all_reduce(ts.packed)                      # the single gradient all-reduce per optimizer step
+    if apply:
+        apply_gradients(algo, ts)
+    return ts
+
+
+def apply_gradients(algo, ts: TrainState) -> None:
+    """compute_norm_and_clip + TrainState.apply_gradients for both nets (gcbf_plus.py:435-438)."""
+    lib = algo._env.lib
+    st = algo._env._stream()
+    for grad, norm, p, m, v, step, lr, n in (
+            (ts.grad_cbf, ts.norm_cbf, algo.cbf_params.flat, ts.m_cbf, ts.v_cbf, ts.step_cbf, algo.lr_cbf, ts.n_cbf),
+            (ts.grad_act, ts.norm_act, algo.actor_net_params.flat, ts.m_act, ts.v_act, ts.step_act, algo.lr_actor,
+             ts.n_act)):
+        _lib.check(lib.gcbf_grad_sqnorm(_lib.ptr(grad), n, _lib.ptr(norm), st), "gcbf_grad_sqnorm")
+        _lib.check(lib.gcbf_clip_adamw(_lib.ptr(p), _lib.ptr(grad), _lib.ptr(m), _lib.ptr(v), n, _lib.ptr(norm),
+                                       _lib.ptr(step), lr, 0.9, 0.999, 1e-8, 1e-3, algo.max_grad_norm, st),
+                   "gcbf_clip_adamw")
+
+
+def read_info(algo) -> Dict[str, float]:
+    """Info dict of the last minibatch with the reference's keys (gcbf_plus.py:423-440). Syncs."""
+    ts: TrainState = algo._trainer_state
+    s = ts.stats.cpu().numpy().astype(np.float64)
+    den = ts.denoms.cpu().numpy().astype(np.float64)
+    n_unsafe, n_safe, n_tot = den[0], den[1], den[2]
+    loss_unsafe = s[0] / (n_unsafe + 1e-6)
+    loss_safe = s[1] / (n_safe + 1e-6)
+    loss_h_dot = s[2] / n_tot
+    loss_action = s[3] / n_tot
+    total = (algo.loss_action_coef * loss_action + algo.loss_unsafe_coef * loss_unsafe +
+             algo.loss_safe_coef * loss_safe + algo.loss_h_dot_coef * loss_h_dot)
+    return {
+        "grad_norm/cbf": float(np.sqrt(ts.norm_cbf[0].item())), "grad_norm/actor": float(np.sqrt(ts.norm_act[0].item())),
+        "loss/action": loss_action, "loss/unsafe": loss_unsafe, "loss/safe": loss_safe, "loss/h_dot": loss_h_dot,
+        "loss/total": total, "acc/unsafe": (s[4] + 1e-6) / (n_unsafe + 1e-6), "acc/safe": (s[5] + 1e-6) / (n_safe + 1e-6),
+        "acc/h_dot": s[6] / n_tot, "acc/unsafe_data_ratio": n_unsafe / n_tot,
+    }
+
+
+def update_tgt(algo, tau: float = 0.5) -> None:
+    """gcbf_plus.py:188-191,228."""
+    env = algo._env
+    _lib.check(env.lib.gcbf_polyak(_lib.ptr(algo.cbf_tgt_params.flat), _lib.ptr(algo.cbf_params.flat),
+                                   algo.cbf_params.count, tau, env._stream()), "gcbf_polyak")
+
+
+# ------------------------------------------------------------------------------------ labels
+def label_rollout(algo, rollout: Rollout):
+    """gcbf_plus.py:285-287: unsafe_mask of every stored graph (b, T) and the horizon safe mask.
+    Returns uint8 tensors [b, T, N]."""
+    env = algo._env
+    lib = env.lib
+    b, T, N = rollout.length, rollout.time_horizon, env.num_agents
+    agent = rollout.agent[:, :T].reshape(b * T, N, env.state_dim).contiguous()
+    hits = rollout.hits[:, :T].reshape(b * T, N, env.n_hits, env.pos_dim).contiguous()
+    goal = rollout.goal[:, None].expand(b, T, N, env.state_dim).reshape(b * T, N, env.state_dim).contiguous()
+    obs = rollout.obstacle
+    O = obs.n_obs if obs is not None else 0
+    packed = obs.packed[:, None].expand(b, T, *obs.packed.shape[1:]).reshape(b * T, *obs.packed.shape[1:]).contiguous() \
+        if O > 0 else None
+    d = env.desc(b * T, O, edge_cap=1)
+    unsafe = torch.empty(b * T * N, dtype=torch.uint8, device=agent.device)
+    _lib.check(lib.gcbf_masks(C.byref(d), _lib.ptr(agent), _lib.ptr(goal), _lib.ptr(hits), _lib.ptr(packed),
+                              _lib.ptr(unsafe), None, None, None, env._stream()), "gcbf_masks")
+    unsafe = unsafe.reshape(b, T, N)
+    safe = torch.empty_like(unsafe)
+    _lib.check(lib.gcbf_safe_horizon(_lib.ptr(unsafe), _lib.ptr(safe), b, T, N, algo.horizon, env._stream()),
+               "gcbf_safe_horizon")
+    return safe, unsafe
+
+
+# ------------------------------------------------------------------------------------ update (gcbf_plus.py:282-297)
+def _flatten_bt(rollout: Rollout, safe: torch.Tensor, unsafe: torch.Tensor):
+    """(b, T, ...) -> dict of per-graph arrays [(b*T), ...]: the `merge01` of gcbf_plus.py:263-266."""
+    b, T = rollout.length, rollout.time_horizon
+    N = rollout.num_agents
+    return {
+        "agent": rollout.agent[:, :T].reshape(b * T, N, -1),
+        "hits": rollout.hits[:, :T].reshape(b * T, N, *rollout.hits.shape[3:]),
+        "goal": rollout.goal[:, None].expand(b, T, *rollout.goal.shape[1:]).reshape(b * T, N, -1),
+        "safe": safe.reshape(b * T, N), "unsafe": unsafe.reshape(b * T, N),
+    }
+
+
+def _cat(parts):
+    return {k: torch.cat([p[k] for p in parts], dim=0) for k in parts[0]}
+
+
+def update(algo, rollout: Rollout, step: int) -> dict:
+    """GCBFPlus.update (gcbf_plus.py:282-297) + sample_batch (:232-280) + update_nets (:198-230),
+    with the replay kept on the device.  QP action labels (get_qp_action, :299-352) are
+    a "next" row: until the batched QP solver lands, u_qp := u_ref(graph), the QP's
+    unconstrained minimiser."""
+    env = algo._env
+    if algo._trainer_state is None:
+        algo._trainer_state = TrainState(algo)
+    if not hasattr(algo, "buffer"):
+        algo.buffer = MaskedReplayBuffer(size=algo.buffer_size)
+        algo.unsafe_buffer = MaskedReplayBuffer(size=algo.buffer_size // 2)
+    safe, unsafe = label_rollout(algo, rollout)
+    new = _flatten_bt(rollout, safe, unsafe)
+    b, T = rollout.length, rollout.time_horizon
+    if algo.buffer.length > algo.batch_size:
+        memory = algo.buffer.sample_rollouts(b)                       # b stored rollouts -> b*T graphs
+        unsafe_memory = algo.unsafe_buffer.sample_graphs(b * T) if algo.unsafe_buffer.length > 0 else memory
+        algo.buffer.append_rollouts(new, b, T)
+        algo.unsafe_buffer.append_graphs(new, new["unsafe"].any(dim=-1))
+        batch = _cat([unsafe_memory, memory, new])
+    else:
+        algo.buffer.append_rollouts(new, b, T)
+        algo.unsafe_buffer.append_graphs(new, new["unsafe"].any(dim=-1))
+        batch = new
+    n = batch["agent"].shape[0]
+    # u_qp labels (see docstring)
+    u_qp = batch_u_ref(algo, batch)
+    n_mb = max(n // algo.batch_size, 1)
+    info = {}
+    for _ in range(algo.inner_epoch):
+        idx = torch.from_numpy(algo.rng.permutation(n)).to(env.device)
+        for mb in np.array_split(np.arange(n), n_mb):
+            sel = idx[torch.from_numpy(mb).to(env.device)]
+            g = env.get_graph(batch["agent"][sel], batch["goal"][sel], None, hits=batch["hits"][sel].contiguous())
+            train_minibatch(algo, g, batch["safe"][sel], batch["unsafe"][sel], u_qp[sel])
+    info = read_info(algo)
+    update_tgt(algo, 0.5)
+    return info
+
+
+def batch_u_ref(algo, batch) -> torch.Tensor:
+    env = algo._env
+    n = batch["agent"].shape[0]
+    out = torch.empty(n, env.num_agents, env.action_dim, dtype=torch.float32, device=env.device)
+    d = env.desc(n, 0, edge_cap=1)
+    _lib.check(env.lib.gcbf_act(C.byref(d), _lib.ptr(batch["agent"].contiguous()), _lib.ptr(batch["goal"].contiguous()),
+                                None, _lib.ptr(out), env._stream()), "gcbf_act")
+    return out

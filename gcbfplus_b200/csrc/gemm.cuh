@@ -135,7 +135,7 @@ gemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, const f
 // backward-weight: C[K1,N] += sum_m w(m) X[m, K1] dY[m, N]; K1, N multiples of 128.
 // grid = (K1/128 * N/128) * splits ; each CTA walks m-chunks {split, split+S, ...}.
 // `roww`: optional per-agent weights; `row2agent`: optional row -> agent map (edges -> receiver).
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+static __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_tn_kernel(const float* __restrict__ X, const int ldx, const float* __restrict__ dY, float* __restrict__ C,
                const float* __restrict__ roww, const int32_t* __restrict__ row2agent,
                const int32_t* __restrict__ m_ptr, const int m_fixed, const int m_cap, const int K1, const int N,
@@ -220,7 +220,7 @@ gemm_tn_kernel(const float* __restrict__ X, const int ldx, const float* __restri
 }
 
 // db[n] += sum_m w(m) dY[m, n]; N <= 256; each CTA takes a strided set of 32-row chunks.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ dY, float* __restrict__ db, const float* __restrict__ roww,
               const int32_t* __restrict__ row2agent, const int32_t* __restrict__ m_ptr, const int m_fixed,
               const int m_cap, const int N, const int n_agents_total) {

@@ -142,7 +142,7 @@ edge_l1_kernel(const gcbf_env_desc d, const float* __restrict__ W1, const float*
 
 // ---- gate logit + segment softmax + weighted aggregation (gnn.py:64-72); warp per receiver.
 // gate = G2 @ a3 + ba3 ; att = softmax over the receiver's edges ; AG[a] = sum att * MSG.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 attn_aggregate_kernel(const int A, const int edge_cap, const float* __restrict__ G2, const float* __restrict__ MSG,
                       const float* __restrict__ a3, const float* __restrict__ ba3,
                       const int32_t* __restrict__ row_start, const int32_t* __restrict__ row_deg,
@@ -182,7 +182,7 @@ attn_aggregate_kernel(const int A, const int edge_cap, const float* __restrict__
 }
 
 // ---- output head: out = tanh(H2 @ W[256, nout] + b); warp per agent.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 head_out_kernel(const int A, const int nout, const float* __restrict__ H2, const float* __restrict__ W,
                 const float* __restrict__ b, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;

@@ -1,0 +1,903 @@
+// train.cu -- the GCBF+ train step: three GNN forwards with saved activations, the four
+// losses, hand-written backward (dW via split-M GEMMs, dX through the edge features, the Euler
+// step and the action clip back into the actor), global-norm clip + AdamW + apply_if_finite,
+// and the target-network polyak update.
+//
+// Replaces gcbfplus/algo/gcbf_plus.py:354-447 (update_inner / get_loss / value_and_grad),
+// trainer/utils.py:62-75 (compute_norm_and_clip), optax.adamw + optax.apply_if_finite
+// (gcbf_plus.py:109-110,127-128) and gcbf_plus.py:188-191 (update_tgt).
+#include "gemm.cuh"
+#include "gnn.cuh"
+
+namespace gcbf {
+
+int32_t gnn_forward_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* agent, const float* goal,
+                         const float* hits, const int32_t* row_start, const int32_t* row_deg,
+                         const int32_t* edge_recv, const int32_t* edge_src, const int32_t* counters, int clip_all,
+                         float* out, float* ws, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------ small helpers
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = in[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+static int32_t launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    transpose_kernel<<<grid, block, 0, st>>>(in, out, rows, cols);
+    count_launch();
+    return check_launch("transpose_kernel");
+}
+
+// Transposed copies of the GEMM weights of one network (backward-data operands).
+struct TransLayout {
+    int w[12];
+    int total;
+};
+static TransLayout make_trans_layout(const ParamLayout& L) {
+    TransLayout T;
+    int off = 0;
+    for (int i = 0; i < 12; ++i) {
+        T.w[i] = off;
+        int rows = L.in[i];
+        if (i == L_UPD0) rows = 128;  // only the aggregated-message rows 3..130
+        if (i == L_MSG0 || i == L_GATE || i == L_OUT) { T.w[i] = -1; continue; }
+        off += rows * L.out[i];
+    }
+    T.total = off;
+    return T;
+}
+static int32_t build_transposes(const ParamLayout& L, const TransLayout& T, const float* P, float* PT, cudaStream_t st) {
+    for (int i = 0; i < 12; ++i) {
+        if (T.w[i] < 0) continue;
+        const float* src = P + L.w[i] + (i == L_UPD0 ? 3 * 256 : 0);
+        const int rows = (i == L_UPD0) ? 128 : L.in[i];
+        if (int32_t rc = launch_transpose(src, PT + T.w[i], rows, L.out[i], st)) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ act + dynamics (forward)
+// a = 2 pi + u_ref ; u = clip_action(a) ; x' = agent_step_euler(x, u)   (gcbf_plus.py:386-391)
+// u_ref / Euler are restated here (default FMA contraction; the geometry TU keeps the strict copies).
+template <int KIND>
+__device__ __forceinline__ void u_ref_train(const gcbf_env_desc& d, const float* x, const float* gl, float* u) {
+    using T = EnvTraits<KIND>;
+    constexpr int SD = T::SD, NU = T::NU;
+    if (KIND == GCBF_ENV_DUBINS_CAR) {
+        const float PI_F = 3.14159265358979323846f, TWO_PI = 6.283185307179586f;
+        const float pdx = x[0] - gl[0], pdy = x[1] - gl[1];
+        const float dist = sqrtf(pdx * pdx + pdy * pdy);
+        float theta_t = atan2f(-pdy, -pdx);
+        theta_t = theta_t - floorf(theta_t / TWO_PI) * TWO_PI;
+        const float theta = x[2] - floorf(x[2] / TWO_PI) * TWO_PI;
+        const float theta_diff = theta_t - theta;
+        const float dot = (-pdx) * cosf(theta) + (-pdy) * sinf(theta);
+        const float tb = acosf(fminf(fmaxf(dot / (dist + 0.0001f), -1.f), 1.f));
+        float omega = 0.f;
+        const bool c1 = (theta_diff < PI_F) && (theta_diff >= 0.f);
+        if (c1 && theta <= PI_F) omega = tb;
+        if (!c1 && theta <= PI_F) omega = -tb;
+        const bool c2 = (theta_diff > -PI_F) && (theta_diff <= 0.f);
+        if (c2 && theta > PI_F) omega = -tb;
+        if (!c2 && theta > PI_F) omega = tb;
+        omega = fminf(fmaxf(omega, -5.f), 5.f);
+        const float nrm = sqrtf(1e-6f + (pdx * pdx + pdy * pdy));
+        const float coef = (nrm > d.comm_radius) ? d.comm_radius / fmaxf(nrm, d.comm_radius) : 1.f;
+        const float qx = coef * pdx, qy = coef * pdy;
+        u[0] = omega;
+        u[1] = -2.5f * x[3] + 2.3f * sqrtf(qx * qx + qy * qy);
+        return;
+    }
+    float err[SD], acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < SD; ++c) {
+        err[c] = gl[c] - x[c];
+        acc += err[c] * err[c];
+    }
+    const float nrm = sqrtf(acc);
+#pragma unroll
+    for (int c = 0; c < SD; ++c) {
+        const float emax = fabsf(err[c] / nrm * d.comm_radius);
+        err[c] = (isnan(err[c]) || isnan(emax)) ? NAN : fminf(fmaxf(err[c], -emax), emax);
+    }
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < SD; ++c) s += err[c] * d.K[a * SD + c];
+        u[a] = isnan(s) ? NAN : fminf(fmaxf(s, -d.u_lim), d.u_lim);
+    }
+}
+
+template <int KIND>
+__global__ void act_dyn_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const float* __restrict__ goal,
+                               const float* __restrict__ pi, float* __restrict__ action, float* __restrict__ xnext) {
+    using T = EnvTraits<KIND>;
+    constexpr int SD = T::SD, NU = T::NU;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= d.n_graphs * d.n_agents) return;
+    float x[SD], gl[SD], ur[NU], u[NU], xd[SD];
+#pragma unroll
+    for (int c = 0; c < SD; ++c) {
+        x[c] = agent[(size_t)a * SD + c];
+        gl[c] = goal[(size_t)a * SD + c];
+    }
+    u_ref_train<KIND>(d, x, gl, ur);
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+        const float act = 2.f * pi[(size_t)a * NU + c] + ur[c];
+        action[(size_t)a * NU + c] = act;
+        u[c] = isnan(act) ? act : fminf(fmaxf(act, -d.u_lim), d.u_lim);
+    }
+    if (KIND == GCBF_ENV_SINGLE_INTEGRATOR) {
+        xd[0] = u[0];
+        xd[1] = u[1];
+    } else if (KIND == GCBF_ENV_DOUBLE_INTEGRATOR) {
+        xd[0] = x[2];
+        xd[1] = x[3];
+        xd[2] = u[0] / d.mass;
+        xd[3] = u[1] / d.mass;
+    } else if (KIND == GCBF_ENV_DUBINS_CAR) {
+        const float ddx = x[0] - gl[0], ddy = x[1] - gl[1];
+        const float keep = (sqrtf(ddx * ddx + ddy * ddy) < d.half_r) ? 0.f : 1.f;
+        xd[0] = cosf(x[2]) * x[3] * keep;
+        xd[1] = sinf(x[2]) * x[3] * keep;
+        xd[2] = u[0] * 20.f * keep;
+        xd[3] = u[1] * keep;
+    } else {
+#pragma unroll
+        for (int r = 0; r < SD; ++r) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < SD; ++c) s += x[c] * d.A[r * SD + c];
+#pragma unroll
+            for (int c = 0; c < NU; ++c) s += u[c] * d.B[r * NU + c];
+            xd[r] = s;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < SD; ++c) {
+        float v = xd[c] * d.dt + x[c];
+        const bool limited = (KIND == GCBF_ENV_DOUBLE_INTEGRATOR && c >= 2) || (KIND == GCBF_ENV_DUBINS_CAR && c == 3) ||
+                             (KIND == GCBF_ENV_LINEAR_DRONE && c >= 3);
+        if (limited) v = isnan(v) ? v : fminf(fmaxf(v, -d.v_lim), d.v_lim);
+        xnext[(size_t)a * SD + c] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------ losses (gcbf_plus.py:362-431)
+// stats (local numerators): 0 sum relu(h+eps)[unsafe]  1 sum relu(-h+eps)[safe]  2 sum max_val_h_dot
+// 3 sum ||a-u_qp||^2  4 #(h<0 & unsafe)  5 #(h>0 & safe)  6 #(h_dot + alpha h > 0)  7 n_unsafe  8 n_safe  9 n_agents
+// denoms (global): 0 n_unsafe  1 n_safe  2 n_agents
+struct TrainHP {
+    float alpha, eps, c_action, c_unsafe, c_safe, c_hdot, dt_inv;
+};
+
+template <int NU>
+__global__ void __launch_bounds__(256)
+loss_kernel(const int A, const TrainHP hp, const float* __restrict__ h, const float* __restrict__ h_next,
+            const uint8_t* __restrict__ safe_m, const uint8_t* __restrict__ unsafe_m, const float* __restrict__ action,
+            const float* __restrict__ u_qp, const float* __restrict__ denoms, float* __restrict__ dh,
+            float* __restrict__ dh_next, float* __restrict__ da, float* __restrict__ labelled,
+            float* __restrict__ stats) {
+    __shared__ float red[10][8];
+    float loc[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) loc[i] = 0.f;
+    const float inv_unsafe = 1.f / (denoms[0] + 1e-6f);
+    const float inv_safe = 1.f / (denoms[1] + 1e-6f);
+    const float inv_n = 1.f / denoms[2];
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < A; a += gridDim.x * blockDim.x) {
+        const float hv = h[a], hn = h_next[a];
+        const bool us = unsafe_m[a] != 0, sf = safe_m[a] != 0;
+        const bool lab = us || sf;
+        float g = 0.f;
+        if (us) {
+            const float v = hv + hp.eps;
+            if (v > 0.f) { loc[0] += v; g += hp.c_unsafe * inv_unsafe; }
+            if (hv < 0.f) loc[4] += 1.f;
+            loc[7] += 1.f;
+        }
+        if (sf) {
+            const float v = -hv + hp.eps;
+            if (v > 0.f) { loc[1] += v; g -= hp.c_safe * inv_safe; }
+            if (hv > 0.f) loc[5] += 1.f;
+            loc[8] += 1.f;
+        }
+        const float h_dot = (hn - hv) * hp.dt_inv;
+        const float v = -h_dot - hp.alpha * hv + hp.eps;
+        float gn = 0.f;
+        if (v > 0.f) {
+            loc[2] += v;
+            const float w = hp.c_hdot * inv_n;
+            gn = -hp.dt_inv * w;                                  // d/dh'
+            g += (lab ? (hp.dt_inv - hp.alpha) : (-hp.alpha)) * w;  // d/dh (h inside h_dot detached if unlabelled)
+        }
+        if (h_dot + hp.alpha * hv > 0.f) loc[6] += 1.f;
+        loc[9] += 1.f;
+        dh[a] = g;
+        dh_next[a] = gn;
+        labelled[a] = lab ? 1.f : 0.f;
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) {
+            const float df = action[(size_t)a * NU + c] - u_qp[(size_t)a * NU + c];
+            sq += df * df;
+            da[(size_t)a * NU + c] = hp.c_action * 2.f * df * inv_n;
+        }
+        loc[3] += sq;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const float s = warp_sum(loc[i]);
+        if (lane == 0) red[i][warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+        atomicAdd(stats + threadIdx.x, s);
+    }
+}
+
+// counts of the label masks (denominators; all-reduced across ranks by the host)
+__global__ void mask_count_kernel(const int A, const uint8_t* __restrict__ safe_m, const uint8_t* __restrict__ unsafe_m,
+                                  float* __restrict__ denoms) {
+    float us = 0.f, sf = 0.f;
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < A; a += gridDim.x * blockDim.x) {
+        us += unsafe_m[a] ? 1.f : 0.f;
+        sf += safe_m[a] ? 1.f : 0.f;
+    }
+    us = warp_sum(us);
+    sf = warp_sum(sf);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(denoms + 0, us);
+        atomicAdd(denoms + 1, sf);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(denoms + 2, (float)A);
+}
+
+// ------------------------------------------------------------------------------------ backward: output head
+// out = tanh(z), z = H2 @ W + b.  dz = d_out (1 - out^2); dW += H2^T (w dz); db += sum w dz; dH2 = dz W^T.
+__global__ void __launch_bounds__(256)
+head_out_bwd_kernel(const int A, const int nout, const float* __restrict__ H2, const float* __restrict__ W,
+                    const float* __restrict__ out, const float* __restrict__ d_out, const float* __restrict__ roww,
+                    float* __restrict__ dH2, float* __restrict__ dW, float* __restrict__ db) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    float wacc[8][4], bacc[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wacc[k][j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bacc[j] = 0.f;
+    float wl[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wl[k][j] = (j < nout) ? W[(lane * 8 + k) * nout + j] : 0.f;
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < A; a += warps_total) {
+        const float4 h0 = *reinterpret_cast<const float4*>(H2 + (size_t)a * 256 + lane * 8);
+        const float4 h1 = *reinterpret_cast<const float4*>(H2 + (size_t)a * 256 + lane * 8 + 4);
+        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const float rw = roww ? roww[a] : 1.f;
+        float dz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < nout) {
+                const float o = out[(size_t)a * nout + j];
+                dz[j] = d_out[(size_t)a * nout + j] * (1.f - o * o);
+            } else {
+                dz[j] = 0.f;
+            }
+        }
+        float dh[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s = fmaf(dz[j], wl[k][j], s);
+                wacc[k][j] = fmaf(hv[k], rw * dz[j], wacc[k][j]);
+            }
+            dh[k] = s;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bacc[j] += rw * dz[j];
+        float4* dst = reinterpret_cast<float4*>(dH2 + (size_t)a * 256 + lane * 8);
+        dst[0] = make_float4(dh[0], dh[1], dh[2], dh[3]);
+        dst[1] = make_float4(dh[4], dh[5], dh[6], dh[7]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        for (int j = 0; j < nout; ++j) atomicAdd(dW + (lane * 8 + k) * nout + j, wacc[k][j]);
+    if (lane == 0)
+        for (int j = 0; j < nout; ++j) atomicAdd(db + j, bacc[j]);
+}
+
+// ------------------------------------------------------------------------------------ backward: attention + aggregation
+// AG[a] = sum_e att_e MSG_e, att = softmax(gate), gate_e = G2_e . a3 + ba3.
+// dMSG_e = att_e dAG ; datt_e = dAG . MSG_e ; dgate_e = att_e (datt_e - sum att datt) ;
+// dG2_e = dgate_e a3 ; da3 += w sum dgate_e G2_e ; dba3 += w sum dgate_e.
+__global__ void __launch_bounds__(256)
+attn_aggregate_bwd_kernel(const int A, const int edge_cap, const float* __restrict__ dAG, const float* __restrict__ MSG,
+                          const float* __restrict__ G2, const float* __restrict__ ATT, const float* __restrict__ a3,
+                          const int32_t* __restrict__ row_start, const int32_t* __restrict__ row_deg,
+                          const float* __restrict__ roww, float* __restrict__ dMSG, float* __restrict__ dG2,
+                          float* __restrict__ da3, float* __restrict__ dba3) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    const float4 w3 = *reinterpret_cast<const float4*>(a3 + lane * 4);
+    float4 acc3 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float accb = 0.f;
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < A; a += warps_total) {
+        const int rs = row_start[a];
+        int rd = row_deg[a];
+        if (rs < 0 || rs + rd > edge_cap) rd = 0;
+        const float4 dag = *reinterpret_cast<const float4*>(dAG + (size_t)a * 128 + lane * 4);
+        const float rw = roww ? roww[a] : 1.f;
+        float dot_sum = 0.f;
+        for (int e = rs; e < rs + rd; ++e) {
+            const float4 m = *reinterpret_cast<const float4*>(MSG + (size_t)e * 128 + lane * 4);
+            const float datt = warp_sum(dag.x * m.x + dag.y * m.y + dag.z * m.z + dag.w * m.w);
+            dot_sum = fmaf(ATT[e], datt, dot_sum);
+        }
+        for (int e = rs; e < rs + rd; ++e) {
+            const float att = ATT[e];
+            const float4 m = *reinterpret_cast<const float4*>(MSG + (size_t)e * 128 + lane * 4);
+            const float datt = warp_sum(dag.x * m.x + dag.y * m.y + dag.z * m.z + dag.w * m.w);
+            const float dgate = att * (datt - dot_sum);
+            *reinterpret_cast<float4*>(dMSG + (size_t)e * 128 + lane * 4) =
+                make_float4(att * dag.x, att * dag.y, att * dag.z, att * dag.w);
+            *reinterpret_cast<float4*>(dG2 + (size_t)e * 128 + lane * 4) =
+                make_float4(dgate * w3.x, dgate * w3.y, dgate * w3.z, dgate * w3.w);
+            const float4 g = *reinterpret_cast<const float4*>(G2 + (size_t)e * 128 + lane * 4);
+            const float wd = rw * dgate;
+            acc3.x = fmaf(wd, g.x, acc3.x);
+            acc3.y = fmaf(wd, g.y, acc3.y);
+            acc3.z = fmaf(wd, g.z, acc3.z);
+            acc3.w = fmaf(wd, g.w, acc3.w);
+            accb += wd;
+        }
+    }
+    atomicAdd(da3 + lane * 4 + 0, acc3.x);
+    atomicAdd(da3 + lane * 4 + 1, acc3.y);
+    atomicAdd(da3 + lane * 4 + 2, acc3.z);
+    atomicAdd(da3 + lane * 4 + 3, acc3.w);
+    if (lane == 0) atomicAdd(dba3, accb);
+}
+
+// ------------------------------------------------------------------------------------ backward: edge layer 1
+// dY = dX1pre [nE,256] (already masked by X1 > 0).  dW1[:ed] += feat^T (w dY); dW1[ed+t] += sum_{type t} w dY;
+// dW1[ed+5] += sum w dY; db1 += sum w dY.  Thread = output column; CTA = strided chunk of edges.
+template <int ED>
+__global__ void __launch_bounds__(256)
+edge_l1_bwd_w_kernel(const int edge_cap, const int n_agents_total, const int32_t* __restrict__ counters,
+                     const float* __restrict__ dY, const float* __restrict__ feat,
+                     const int32_t* __restrict__ edge_src, const int32_t* __restrict__ edge_recv,
+                     const float* __restrict__ roww, float* __restrict__ dW1, float* __restrict__ db1) {
+    const int nE = min(counters[0], edge_cap);
+    const int c = threadIdx.x;
+    float accw[ED], acct[3], accall = 0.f;
+#pragma unroll
+    for (int i = 0; i < ED; ++i) accw[i] = 0.f;
+    acct[0] = acct[1] = acct[2] = 0.f;
+    for (int e = blockIdx.x; e < nE; e += gridDim.x) {
+        float w = 1.f;
+        if (roww) w = roww[min(max(edge_recv[e], 0), n_agents_total - 1)];
+        const float g = w * dY[(size_t)e * 256 + c];
+        const int code = edge_src[e];
+        const int t = (code >= 0) ? 2 : ((code == -1) ? 1 : 0);
+#pragma unroll
+        for (int i = 0; i < ED; ++i) accw[i] = fmaf(feat[(size_t)e * FEAT_LD + i], g, accw[i]);
+        acct[0] += (t == 0) ? g : 0.f;
+        acct[1] += (t == 1) ? g : 0.f;
+        acct[2] += (t == 2) ? g : 0.f;
+        accall += g;
+    }
+#pragma unroll
+    for (int i = 0; i < ED; ++i) atomicAdd(dW1 + i * 256 + c, accw[i]);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) atomicAdd(dW1 + (ED + t) * 256 + c, acct[t]);
+    atomicAdd(dW1 + (ED + 3 + 2) * 256 + c, accall);
+    atomicAdd(db1 + c, accall);
+}
+
+// dfeat = dY @ W1[:ed]^T, through the norm-clip, scattered to d_es[recv] (+) and d_es[sender agent] (-).
+// d_es is in edge-state space ([A, ED]); one warp per edge.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+edge_l1_bwd_x_kernel(const gcbf_env_desc d, const float* __restrict__ W1, const float* __restrict__ dY,
+                     const float* __restrict__ agent, const float* __restrict__ goal, const float* __restrict__ hits,
+                     const int32_t* __restrict__ edge_recv, const int32_t* __restrict__ edge_src,
+                     const int32_t* __restrict__ counters, const int clip_all, float* __restrict__ d_es) {
+    using T = EnvTraits<KIND>;
+    constexpr int ED = T::ED, SD = T::SD, PD = T::PD;
+    __shared__ __align__(16) float sW[ED][256];
+    for (int i = threadIdx.x; i < ED * 256; i += blockDim.x) sW[i / 256][i % 256] = W1[i];
+    __syncthreads();
+    const int nE = min(counters[0], d.edge_cap);
+    const int A = d.n_graphs * d.n_agents;
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < nE; e += warps_total) {
+        const float4 g0 = *reinterpret_cast<const float4*>(dY + (size_t)e * 256 + lane * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(dY + (size_t)e * 256 + lane * 8 + 4);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float df[ED];
+#pragma unroll
+        for (int c = 0; c < ED; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = fmaf(gv[j], sW[c][lane * 8 + j], s);
+            df[c] = warp_sum(s);
+        }
+        if (lane == 0) {
+            const int a = min(max(edge_recv[e], 0), A - 1);
+            int code = min(edge_src[e], A - 1);
+            float er[ED], es[ED], f[ED], coef, nrm;
+            edge_state_dev<KIND>(agent + (size_t)a * SD, er);
+            sender_state_dev<KIND>(code, a, d.n_hits, agent, goal, hits, es);
+            const bool clip = clip_all || code == -1;
+            edge_feat_dev<KIND>(er, es, clip, d.comm_radius, f, &coef, &nrm);
+            if (clip && coef != 1.f) {
+                // feat_p = coef * dlt_p, coef = rc / n: d dlt_q = coef (df_q - dlt_q (sum_p df_p dlt_p) / n^2)
+                float dotp = 0.f;
+#pragma unroll
+                for (int p = 0; p < PD; ++p) dotp += df[p] * (er[p] - es[p]);
+                const float inv_n2 = 1.f / (nrm * nrm);
+#pragma unroll
+                for (int p = 0; p < PD; ++p) df[p] = coef * (df[p] - (er[p] - es[p]) * dotp * inv_n2);
+            }
+#pragma unroll
+            for (int c = 0; c < ED; ++c) {
+                atomicAdd(d_es + (size_t)a * ED + c, df[c]);
+                if (code >= 0) atomicAdd(d_es + (size_t)code * ED + c, -df[c]);
+            }
+        }
+    }
+}
+
+// d_es (edge-state grads of x') -> d pi.   x' = clip_state(x + xdot(x, u) dt), u = clip_action(a),
+// a = 2 pi + u_ref  (gcbf_plus.py:386-391; double_integrator.py:128-143,340-354 and twins).
+// d_pi = 2 (da_dyn + da_direct).
+template <int KIND>
+__global__ void dyn_bwd_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const float* __restrict__ goal,
+                               const float* __restrict__ action, const float* __restrict__ xnext,
+                               const float* __restrict__ d_es, const float* __restrict__ da_direct,
+                               float* __restrict__ d_pi) {
+    using T = EnvTraits<KIND>;
+    constexpr int SD = T::SD, NU = T::NU, ED = T::ED;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= d.n_graphs * d.n_agents) return;
+    float dx[SD], xn[SD], de[ED];
+#pragma unroll
+    for (int c = 0; c < ED; ++c) de[c] = d_es[(size_t)a * ED + c];
+#pragma unroll
+    for (int c = 0; c < SD; ++c) xn[c] = xnext[(size_t)a * SD + c];
+    if (KIND == GCBF_ENV_DUBINS_CAR) {  // es = (x, y, v cos th, v sin th)
+        const float th = xn[2], v = xn[3];
+        dx[0] = de[0];
+        dx[1] = de[1];
+        dx[2] = de[2] * (-v * sinf(th)) + de[3] * (v * cosf(th));
+        dx[3] = de[2] * cosf(th) + de[3] * sinf(th);
+    } else {
+#pragma unroll
+        for (int c = 0; c < SD; ++c) dx[c] = de[c];
+    }
+    // clip_state: zero gradient on clipped velocity components
+#pragma unroll
+    for (int c = 0; c < SD; ++c) {
+        const bool limited = (KIND == GCBF_ENV_DOUBLE_INTEGRATOR && c >= 2) || (KIND == GCBF_ENV_DUBINS_CAR && c == 3) ||
+                             (KIND == GCBF_ENV_LINEAR_DRONE && c >= 3);
+        if (limited && !(xn[c] > -d.v_lim && xn[c] < d.v_lim)) dx[c] = 0.f;
+    }
+    float du[NU];
+    if (KIND == GCBF_ENV_SINGLE_INTEGRATOR) {
+        du[0] = dx[0] * d.dt;
+        du[1] = dx[1] * d.dt;
+    } else if (KIND == GCBF_ENV_DOUBLE_INTEGRATOR) {
+        du[0] = dx[2] * d.dt / d.mass;
+        du[1] = dx[3] * d.dt / d.mass;
+    } else if (KIND == GCBF_ENV_DUBINS_CAR) {
+        const float ddx = agent[(size_t)a * SD + 0] - goal[(size_t)a * SD + 0];
+        const float ddy = agent[(size_t)a * SD + 1] - goal[(size_t)a * SD + 1];
+        const float keep = (sqrtf(ddx * ddx + ddy * ddy) < d.half_r) ? 0.f : 1.f;
+        du[0] = dx[2] * 20.f * d.dt * keep;
+        du[1] = dx[3] * d.dt * keep;
+    } else {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < SD; ++r) s += dx[r] * d.B[r * NU + c];
+            du[c] = s * d.dt;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+        const float act = action[(size_t)a * NU + c];
+        const float g = (act > -d.u_lim && act < d.u_lim) ? du[c] : 0.f;  // clip_action
+        d_pi[(size_t)a * NU + c] = 2.f * (g + da_direct[(size_t)a * NU + c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------ one network backward
+struct BwdArgs {
+    const gcbf_env_desc* d;
+    int out_dim;
+    const float* P;        // parameters
+    const float* PT;       // transposed GEMM weights (make_trans_layout)
+    const float* fw;       // forward workspace (saved activations)
+    float* gw;             // gradient workspace (same layout)
+    const float* out;      // network output (tanh applied) [A, out_dim]
+    const float* d_out;    // upstream gradient wrt the output [A, out_dim]
+    const float* roww;     // optional per-agent weights applied to every dW / db contribution
+    float* G;              // parameter gradient (accumulated)
+    const float *agent, *goal, *hits;
+    const int32_t *row_start, *row_deg, *edge_recv, *edge_src, *counters;
+    int clip_all;
+    float* d_es;           // optional [A, ED] (accumulated) : gradient wrt the agents' edge states
+};
+
+static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
+    const gcbf_env_desc* d = b.d;
+    const int ed = env_ed(d->env_kind);
+    const ParamLayout L = make_layout(ed, b.out_dim);
+    const TransLayout TL = make_trans_layout(L);
+    const int A = d->n_graphs * d->n_agents, cap = d->edge_cap;
+    const GnnWs W = make_ws(cap, A);
+    const RowCount re{b.counters, 0, cap};
+    const RowCount ra{nullptr, A, A};
+    const int nsm = sm_count();
+    const float* fw = b.fw;
+    float* gw = b.gw;
+    int32_t rc;
+#define RC(x) do { if ((rc = (x))) return rc; } while (0)
+    // ---- output layer
+    {
+        const int grid = min((A + 7) / 8, 2 * nsm);
+        head_out_bwd_kernel<<<grid, 256, 0, st>>>(A, b.out_dim, fw + W.h2, b.P + L.w[L_OUT], b.out, b.d_out, b.roww,
+                                                  gw + W.h2, b.G + L.w[L_OUT], b.G + L.b[L_OUT]);
+        count_launch();
+        RC(check_launch("head_out_bwd_kernel"));
+    }
+    // ---- head MLP
+    RC(launch_gemm_tn(fw + W.h1, 256, gw + W.h2, b.G + L.w[L_HEAD1], b.roww, nullptr, ra, 256, 256, A, st));
+    RC(launch_colsum(gw + W.h2, b.G + L.b[L_HEAD1], b.roww, nullptr, ra, 256, A, st));
+    RC(launch_gemm_nn(EPI_RELU_MASK, false, gw + W.h2, b.PT + TL.w[L_HEAD1], nullptr, nullptr, gw + W.h1, fw + W.h1, ra, 256, 256, st));
+    RC(launch_gemm_tn(fw + W.v3, 128, gw + W.h1, b.G + L.w[L_HEAD0], b.roww, nullptr, ra, 128, 256, A, st));
+    RC(launch_colsum(gw + W.h1, b.G + L.b[L_HEAD0], b.roww, nullptr, ra, 256, A, st));
+    RC(launch_gemm_nn(EPI_NONE, false, gw + W.h1, b.PT + TL.w[L_HEAD0], nullptr, nullptr, gw + W.v3, nullptr, ra, 256, 128, st));
+    // ---- update MLP
+    RC(launch_gemm_tn(fw + W.v2, 256, gw + W.v3, b.G + L.w[L_UPDOUT], b.roww, nullptr, ra, 256, 128, A, st));
+    RC(launch_colsum(gw + W.v3, b.G + L.b[L_UPDOUT], b.roww, nullptr, ra, 128, A, st));
+    RC(launch_gemm_nn(EPI_NONE, false, gw + W.v3, b.PT + TL.w[L_UPDOUT], nullptr, nullptr, gw + W.v2, nullptr, ra, 128, 256, st));
+    RC(launch_gemm_tn(fw + W.v1, 256, gw + W.v2, b.G + L.w[L_UPD1], b.roww, nullptr, ra, 256, 256, A, st));
+    RC(launch_colsum(gw + W.v2, b.G + L.b[L_UPD1], b.roww, nullptr, ra, 256, A, st));
+    RC(launch_gemm_nn(EPI_RELU_MASK, false, gw + W.v2, b.PT + TL.w[L_UPD1], nullptr, nullptr, gw + W.v1, fw + W.v1, ra, 256, 256, st));
+    RC(launch_gemm_tn(fw + W.ag, 128, gw + W.v1, b.G + L.w[L_UPD0] + 3 * 256, b.roww, nullptr, ra, 128, 256, A, st));
+    RC(launch_colsum(gw + W.v1, b.G + L.b[L_UPD0], b.roww, nullptr, ra, 256, A, st));
+    RC(launch_colsum(gw + W.v1, b.G + L.w[L_UPD0] + 2 * 256, b.roww, nullptr, ra, 256, A, st));  // agent one-hot row
+    RC(launch_gemm_nn(EPI_NONE, false, gw + W.v1, b.PT + TL.w[L_UPD0], nullptr, nullptr, gw + W.ag, nullptr, ra, 256, 128, st));
+    // ---- attention + aggregation
+    {
+        const int grid = min((A + 7) / 8, 2 * nsm);
+        attn_aggregate_bwd_kernel<<<grid, 256, 0, st>>>(A, cap, gw + W.ag, fw + W.msg, fw + W.g2, fw + W.att,
+                                                        b.P + L.w[L_GATE], b.row_start, b.row_deg, b.roww, gw + W.msg,
+                                                        gw + W.g2, b.G + L.w[L_GATE], b.G + L.b[L_GATE]);
+        count_launch();
+        RC(check_launch("attn_aggregate_bwd_kernel"));
+    }
+    // ---- gate MLP (edge rows; dW weighted by the receiver's weight)
+    RC(launch_gemm_tn(fw + W.g1, 128, gw + W.g2, b.G + L.w[L_ATT1], b.roww, b.edge_recv, re, 128, 128, A, st));
+    RC(launch_colsum(gw + W.g2, b.G + L.b[L_ATT1], b.roww, b.edge_recv, re, 128, A, st));
+    RC(launch_gemm_nn(EPI_RELU_MASK, false, gw + W.g2, b.PT + TL.w[L_ATT1], nullptr, nullptr, gw + W.g1, fw + W.g1, re, 128, 128, st));
+    RC(launch_gemm_tn(fw + W.msg, 128, gw + W.g1, b.G + L.w[L_ATT0], b.roww, b.edge_recv, re, 128, 128, A, st));
+    RC(launch_colsum(gw + W.g1, b.G + L.b[L_ATT0], b.roww, b.edge_recv, re, 128, A, st));
+    RC(launch_gemm_nn(EPI_NONE, true, gw + W.g1, b.PT + TL.w[L_ATT0], nullptr, nullptr, gw + W.msg, nullptr, re, 128, 128, st));
+    // ---- message MLP
+    RC(launch_gemm_tn(fw + W.x2, 256, gw + W.msg, b.G + L.w[L_MSGOUT], b.roww, b.edge_recv, re, 256, 128, A, st));
+    RC(launch_colsum(gw + W.msg, b.G + L.b[L_MSGOUT], b.roww, b.edge_recv, re, 128, A, st));
+    RC(launch_gemm_nn(EPI_NONE, false, gw + W.msg, b.PT + TL.w[L_MSGOUT], nullptr, nullptr, gw + W.x2, nullptr, re, 128, 256, st));
+    RC(launch_gemm_tn(fw + W.x1, 256, gw + W.x2, b.G + L.w[L_MSG1], b.roww, b.edge_recv, re, 256, 256, A, st));
+    RC(launch_colsum(gw + W.x2, b.G + L.b[L_MSG1], b.roww, b.edge_recv, re, 256, A, st));
+    RC(launch_gemm_nn(EPI_RELU_MASK, false, gw + W.x2, b.PT + TL.w[L_MSG1], nullptr, nullptr, gw + W.x1, fw + W.x1, re, 256, 256, st));
+    // ---- edge layer 1
+    {
+        const int grid = min(max(cap / 64, 1), 4 * nsm);
+        switch (ed) {
+            case 2: edge_l1_bwd_w_kernel<2><<<grid, 256, 0, st>>>(cap, A, b.counters, gw + W.x1, fw + W.feat, b.edge_src, b.edge_recv, b.roww, b.G + L.w[L_MSG0], b.G + L.b[L_MSG0]); break;
+            case 4: edge_l1_bwd_w_kernel<4><<<grid, 256, 0, st>>>(cap, A, b.counters, gw + W.x1, fw + W.feat, b.edge_src, b.edge_recv, b.roww, b.G + L.w[L_MSG0], b.G + L.b[L_MSG0]); break;
+            default: edge_l1_bwd_w_kernel<6><<<grid, 256, 0, st>>>(cap, A, b.counters, gw + W.x1, fw + W.feat, b.edge_src, b.edge_recv, b.roww, b.G + L.w[L_MSG0], b.G + L.b[L_MSG0]); break;
+        }
+        count_launch();
+        RC(check_launch("edge_l1_bwd_w_kernel"));
+    }
+    if (b.d_es) {
+        const int grid = min((cap + 7) / 8, 4 * nsm);
+        GCBF_DISPATCH_ENV(d->env_kind, {
+            edge_l1_bwd_x_kernel<KIND><<<grid, 256, 0, st>>>(*d, b.P + L.w[L_MSG0], gw + W.x1, b.agent, b.goal, b.hits,
+                                                             b.edge_recv, b.edge_src, b.counters, b.clip_all, b.d_es);
+        });
+        count_launch();
+        RC(check_launch("edge_l1_bwd_x_kernel"));
+    }
+#undef RC
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ optimizer kernels
+__global__ void __launch_bounds__(256)
+sqnorm_kernel(const float* __restrict__ g, const int n, float* __restrict__ out) {
+    float s = 0.f, bad = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float v = g[i];
+        s = fmaf(v, v, s);
+        bad += isfinite(v) ? 0.f : 1.f;
+    }
+    s = warp_sum(s);
+    bad = warp_sum(bad);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out + 0, s);
+        if (bad > 0.f) atomicAdd(out + 1, bad);
+    }
+}
+
+// compute_norm_and_clip (trainer/utils.py:66-75) + optax.adamw + apply_if_finite.
+// norm_info[0] = sum g^2, norm_info[1] = #non-finite; step[0] = optimizer step count (advanced by thread 0).
+__global__ void __launch_bounds__(256)
+clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  const int n, const float* __restrict__ norm_info, int32_t* __restrict__ step, const float lr,
+                  const float b1, const float b2, const float eps, const float wd, const float max_norm) {
+    if (norm_info[1] > 0.f || !isfinite(norm_info[0])) return;  // apply_if_finite: skip, state not advanced
+    const int t = step[0] + 1;
+    const float gnorm = sqrtf(norm_info[0]);
+    const float denom = fmaxf(max_norm, gnorm);
+    const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float gi = (g[i] / denom) * max_norm;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float mhat = mi / bc1, vhat = vi / bc2;
+        p[i] = p[i] - lr * (mhat / (sqrtf(vhat) + eps) + wd * p[i]);
+    }
+}
+__global__ void adamw_advance_kernel(const float* __restrict__ norm_info, int32_t* __restrict__ step) {
+    if (!(norm_info[1] > 0.f || !isfinite(norm_info[0]))) step[0] += 1;
+}
+
+__global__ void polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, const int n, const float tau) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        tgt[i] = tau * src[i] + (1.f - tau) * tgt[i];
+}
+
+// ------------------------------------------------------------------------------------ train workspace layout
+struct TrainWs {
+    int64_t ws0, ws1, ws2, gws, pt_cbf, pt_act, h, hn, pi, act, xn, d_es, dh, dhn, da, dpi, lab, total;
+};
+static TrainWs make_train_ws(const gcbf_env_desc* d) {
+    const int ed = env_ed(d->env_kind), nu = env_nu(d->env_kind), sd = env_sd(d->env_kind);
+    const int64_t A = (int64_t)d->n_graphs * d->n_agents;
+    const GnnWs W = make_ws(d->edge_cap, A);
+    const TransLayout Tc = make_trans_layout(make_layout(ed, 1)), Ta = make_trans_layout(make_layout(ed, nu));
+    TrainWs t;
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t r = o; o += (n + 3) & ~(int64_t)3; return r; };
+    t.ws0 = take(W.total);
+    t.ws1 = take(W.total);
+    t.ws2 = take(W.total);
+    t.gws = take(W.total);
+    t.pt_cbf = take(Tc.total);
+    t.pt_act = take(Ta.total);
+    t.h = take(A);
+    t.hn = take(A);
+    t.pi = take(A * nu);
+    t.act = take(A * nu);
+    t.xn = take(A * sd);
+    t.d_es = take(A * ed);
+    t.dh = take(A);
+    t.dhn = take(A);
+    t.da = take(A * nu);
+    t.dpi = take(A * nu);
+    t.lab = take(A);
+    t.total = o;
+    return t;
+}
+
+}  // namespace gcbf
+
+using namespace gcbf;
+
+extern "C" __attribute__((visibility("default"))) int64_t gcbf_train_workspace_floats(const gcbf_env_desc* desc) {
+    if (!desc || desc->edge_cap <= 0 || desc->n_graphs <= 0 || desc->n_agents <= 0 || desc->env_kind < 0 ||
+        desc->env_kind > 3)
+        return -1;
+    return make_train_ws(desc).total;
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_mask_counts(const uint8_t* safe_mask,
+                                                                           const uint8_t* unsafe_mask,
+                                                                           int32_t n_agents_total, float* denoms,
+                                                                           void* stream) {
+    GCBF_REQUIRE(safe_mask && unsafe_mask && denoms && n_agents_total > 0, "gcbf_mask_counts: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(denoms, 0, 4 * sizeof(float), st);
+    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int32_t)e; }
+    mask_count_kernel<<<min((n_agents_total + 255) / 256, 2 * sm_count()), 256, 0, st>>>(n_agents_total, safe_mask,
+                                                                                         unsafe_mask, denoms);
+    count_launch();
+    return check_launch("mask_count_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
+    const gcbf_env_desc* desc, const float* hp_host, const float* cbf_params, const float* actor_params,
+    const float* agent, const float* goal, const float* hits, const int32_t* row_start, const int32_t* row_deg,
+    const int32_t* edge_recv, const int32_t* edge_src, const int32_t* counters, const uint8_t* safe_mask,
+    const uint8_t* unsafe_mask, const float* u_qp, const float* denoms, float* grad_cbf, float* grad_actor,
+    float* stats, float* workspace, int64_t workspace_floats, void* stream) {
+    GCBF_REQUIRE(desc && hp_host && cbf_params && actor_params && agent && goal && hits && row_start && row_deg &&
+                     edge_recv && edge_src && counters && safe_mask && unsafe_mask && u_qp && denoms && grad_cbf &&
+                     grad_actor && stats && workspace, "gcbf_train_step: NULL pointer argument");
+    GCBF_REQUIRE(desc->env_kind >= 0 && desc->env_kind <= 3 && desc->edge_cap > 0 && desc->n_graphs > 0 &&
+                     desc->n_agents > 0, "gcbf_train_step: bad descriptor");
+    const TrainWs TW = make_train_ws(desc);
+    GCBF_REQUIRE(workspace_floats >= TW.total, "train workspace too small: %lld < %lld floats",
+                 (long long)workspace_floats, (long long)TW.total);
+    GCBF_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)cbf_params & 15) == 0 &&
+                     ((uintptr_t)actor_params & 15) == 0 && ((uintptr_t)grad_cbf & 15) == 0 &&
+                     ((uintptr_t)grad_actor & 15) == 0, "buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const gcbf_env_desc* d = desc;
+    const int ed = env_ed(d->env_kind), nu = env_nu(d->env_kind);
+    const int A = d->n_graphs * d->n_agents;
+    const ParamLayout Lc = make_layout(ed, 1), La = make_layout(ed, nu);
+    float* ws = workspace;
+    TrainHP hp;
+    hp.alpha = hp_host[0];
+    hp.eps = hp_host[1];
+    hp.c_action = hp_host[2];
+    hp.c_unsafe = hp_host[3];
+    hp.c_safe = hp_host[4];
+    hp.c_hdot = hp_host[5];
+    hp.dt_inv = 1.f / d->dt;
+    int32_t rc;
+#define RC(x) do { if ((rc = (x))) return rc; } while (0)
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(grad_cbf, 0, sizeof(float) * Lc.total, st)) != cudaSuccess ||
+        (e = cudaMemsetAsync(grad_actor, 0, sizeof(float) * La.total, st)) != cudaSuccess ||
+        (e = cudaMemsetAsync(stats, 0, sizeof(float) * 16, st)) != cudaSuccess ||
+        (e = cudaMemsetAsync(ws + TW.d_es, 0, sizeof(float) * (size_t)A * ed, st)) != cudaSuccess) {
+        set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+        return (int32_t)e;
+    }
+    RC(build_transposes(Lc, make_trans_layout(Lc), cbf_params, ws + TW.pt_cbf, st));
+    RC(build_transposes(La, make_trans_layout(La), actor_params, ws + TW.pt_act, st));
+    // ---- forward: h = cbf(g), pi = actor(g), x' = f(x, clip(2 pi + u_ref)), h' = cbf(g')
+    RC(gnn_forward_impl(d, 1, cbf_params, agent, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 0,
+                        ws + TW.h, ws + TW.ws0, st));
+    RC(gnn_forward_impl(d, nu, actor_params, agent, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 0,
+                        ws + TW.pi, ws + TW.ws1, st));
+    GCBF_DISPATCH_ENV(d->env_kind, {
+        act_dyn_kernel<KIND><<<(A + 127) / 128, 128, 0, st>>>(*d, agent, goal, ws + TW.pi, ws + TW.act, ws + TW.xn);
+    });
+    count_launch();
+    RC(check_launch("act_dyn_kernel"));
+    RC(gnn_forward_impl(d, 1, cbf_params, ws + TW.xn, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 1,
+                        ws + TW.hn, ws + TW.ws2, st));
+    // ---- losses and their derivatives wrt h, h', a
+    {
+        const int grid = min((A + 255) / 256, 2 * sm_count());
+        if (nu == 2)
+            loss_kernel<2><<<grid, 256, 0, st>>>(A, hp, ws + TW.h, ws + TW.hn, safe_mask, unsafe_mask, ws + TW.act, u_qp,
+                                                 denoms, ws + TW.dh, ws + TW.dhn, ws + TW.da, ws + TW.lab, stats);
+        else
+            loss_kernel<3><<<grid, 256, 0, st>>>(A, hp, ws + TW.h, ws + TW.hn, safe_mask, unsafe_mask, ws + TW.act, u_qp,
+                                                 denoms, ws + TW.dh, ws + TW.dhn, ws + TW.da, ws + TW.lab, stats);
+        count_launch();
+        RC(check_launch("loss_kernel"));
+    }
+    // ---- backward 1: cbf on g' (dW only from labelled receivers; dX from all) -> d_es
+    BwdArgs b;
+    b.d = d;
+    b.agent = ws + TW.xn;
+    b.goal = goal;
+    b.hits = hits;
+    b.row_start = row_start;
+    b.row_deg = row_deg;
+    b.edge_recv = edge_recv;
+    b.edge_src = edge_src;
+    b.counters = counters;
+    b.gw = ws + TW.gws;
+    b.out_dim = 1;
+    b.P = cbf_params;
+    b.PT = ws + TW.pt_cbf;
+    b.fw = ws + TW.ws2;
+    b.out = ws + TW.hn;
+    b.d_out = ws + TW.dhn;
+    b.roww = ws + TW.lab;
+    b.G = grad_cbf;
+    b.clip_all = 1;
+    b.d_es = ws + TW.d_es;
+    RC(gnn_backward_impl(b, st));
+    // ---- through the Euler step / clips into the policy output
+    GCBF_DISPATCH_ENV(d->env_kind, {
+        dyn_bwd_kernel<KIND><<<(A + 127) / 128, 128, 0, st>>>(*d, agent, goal, ws + TW.act, ws + TW.xn, ws + TW.d_es,
+                                                              ws + TW.da, ws + TW.dpi);
+    });
+    count_launch();
+    RC(check_launch("dyn_bwd_kernel"));
+    // ---- backward 2: actor on g
+    b.agent = agent;
+    b.out_dim = nu;
+    b.P = actor_params;
+    b.PT = ws + TW.pt_act;
+    b.fw = ws + TW.ws1;
+    b.out = ws + TW.pi;
+    b.d_out = ws + TW.dpi;
+    b.roww = nullptr;
+    b.G = grad_actor;
+    b.clip_all = 0;
+    b.d_es = nullptr;
+    RC(gnn_backward_impl(b, st));
+    // ---- backward 3: cbf on g
+    b.out_dim = 1;
+    b.P = cbf_params;
+    b.PT = ws + TW.pt_cbf;
+    b.fw = ws + TW.ws0;
+    b.out = ws + TW.h;
+    b.d_out = ws + TW.dh;
+    b.G = grad_cbf;
+    RC(gnn_backward_impl(b, st));
+#undef RC
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_grad_sqnorm(const float* grad, int32_t n, float* out2,
+                                                                           void* stream) {
+    GCBF_REQUIRE(grad && out2 && n > 0, "gcbf_grad_sqnorm: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(float), st);
+    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int32_t)e; }
+    sqnorm_kernel<<<min((n + 1023) / 1024, 2 * sm_count()), 256, 0, st>>>(grad, n, out2);
+    count_launch();
+    return check_launch("sqnorm_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_clip_adamw(float* params, const float* grad, float* m,
+                                                                          float* v, int32_t n,
+                                                                          const float* norm_info, int32_t* step,
+                                                                          float lr, float b1, float b2, float eps,
+                                                                          float wd, float max_norm, void* stream) {
+    GCBF_REQUIRE(params && grad && m && v && norm_info && step && n > 0, "gcbf_clip_adamw: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    clip_adamw_kernel<<<min((n + 1023) / 1024, 2 * sm_count()), 256, 0, st>>>(params, grad, m, v, n, norm_info, step, lr,
+                                                                             b1, b2, eps, wd, max_norm);
+    count_launch();
+    if (int32_t rc = check_launch("clip_adamw_kernel")) return rc;
+    adamw_advance_kernel<<<1, 1, 0, st>>>(norm_info, step);
+    count_launch();
+    return check_launch("adamw_advance_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_polyak(float* tgt, const float* src, int32_t n,
+                                                                      float tau, void* stream) {
+    GCBF_REQUIRE(tgt && src && n > 0, "gcbf_polyak: bad argument");
+    polyak_kernel<<<min((n + 1023) / 1024, 2 * sm_count()), 256, 0, (cudaStream_t)stream>>>(tgt, src, n, tau);
+    count_launch();
+    return check_launch("polyak_kernel");
+}

@@ -154,6 +154,43 @@ int32_t gcbf_masks(const gcbf_env_desc* desc, const float* agent, const float* g
 int32_t gcbf_safe_horizon(const uint8_t* unsafe, uint8_t* safe, int32_t n_rollouts, int32_t T,
                           int32_t n_agents, int32_t horizon, void* stream);
 
+/* ---------------------------------------------------------------- train step (a10, a11)
+ * gcbf_train_step replaces one `update_fn` of GCBFPlus.update_inner up to (not including) the
+ * optimizer (gcbfplus/algo/gcbf_plus.py:356-434): h = cbf(g); a = 2 pi(g) + u_ref; g' =
+ * env.forward_graph(g, a); h' = cbf(g'); loss = c_a mean||a - u_qp||^2 + c_u unsafe + c_s safe +
+ * c_h mean relu(-h_dot - alpha h + eps) with the reference's stop-gradient routing for
+ * unlabelled agents (:399-407); jax.value_and_grad wrt (cbf_params, actor_params).
+ *   hp_host[6] (HOST): alpha, eps, loss_action_coef, loss_unsafe_coef, loss_safe_coef, loss_h_dot_coef
+ *   denoms[4] (device): GLOBAL n_unsafe, n_safe, n_agents of the minibatch (gcbf_mask_counts, then
+ *     summed over ranks by the host when the minibatch is sharded)
+ *   grad_cbf / grad_actor: flat gradients in the parameter layout (overwritten)
+ *   stats[16] (device, overwritten): LOCAL numerators 0 sum relu(h+eps)[unsafe], 1 sum relu(-h+eps)[safe],
+ *     2 sum relu(-h_dot-alpha h+eps), 3 sum ||a-u_qp||^2, 4 #(h<0 & unsafe), 5 #(h>0 & safe),
+ *     6 #(h_dot+alpha h>0), 7 n_unsafe, 8 n_safe, 9 n_agents
+ *   workspace: gcbf_train_workspace_floats(desc) floats.
+ * Sharded training: ranks call this on their shard with the global denoms, then sum
+ * [grad_cbf | grad_actor | stats] with ONE all-reduce before gcbf_clip_adamw. */
+int64_t gcbf_train_workspace_floats(const gcbf_env_desc* desc);
+int32_t gcbf_mask_counts(const uint8_t* safe_mask, const uint8_t* unsafe_mask, int32_t n_agents_total,
+                         float* denoms, void* stream);
+int32_t gcbf_train_step(const gcbf_env_desc* desc, const float* hp_host, const float* cbf_params,
+                        const float* actor_params, const float* agent, const float* goal,
+                        const float* hits, const int32_t* row_start, const int32_t* row_deg,
+                        const int32_t* edge_recv, const int32_t* edge_src, const int32_t* counters,
+                        const uint8_t* safe_mask, const uint8_t* unsafe_mask, const float* u_qp,
+                        const float* denoms, float* grad_cbf, float* grad_actor, float* stats,
+                        float* workspace, int64_t workspace_floats, void* stream);
+/* out2[0] = sum g^2, out2[1] = number of non-finite entries (trainer/utils.py:62-64 compute_norm). */
+int32_t gcbf_grad_sqnorm(const float* grad, int32_t n, float* out2, void* stream);
+/* compute_norm_and_clip (trainer/utils.py:66-75) + optax.adamw(lr, b1, b2, eps, weight_decay) wrapped in
+ * optax.apply_if_finite (gcbf_plus.py:109-110,127-128): g <- g / max(max_norm, ||g||) * max_norm; if any
+ * gradient entry is non-finite nothing is changed; step[0] (device int32) counts applied updates. */
+int32_t gcbf_clip_adamw(float* params, const float* grad, float* m, float* v, int32_t n,
+                        const float* norm_info, int32_t* step, float lr, float b1, float b2, float eps,
+                        float weight_decay, float max_norm, void* stream);
+/* tgt <- tau * src + (1 - tau) * tgt  (GCBFPlus.update_tgt, gcbf_plus.py:188-191). */
+int32_t gcbf_polyak(float* tgt, const float* src, int32_t n, float tau, void* stream);
+
 /* ---------------------------------------------------------------- dense-layer building blocks
  * The fp32 GEMM family the MLPs are made of (flax nn.Dense, gcbfplus/nn/mlp.py:19-21, and its
  * autodiff transposes).  Exported so the kernels can be unit-tested against a plain fp32

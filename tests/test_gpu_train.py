@@ -1,0 +1,170 @@
+"""GPU parity: the GCBF+ train step (losses, hand-written backward, clip + AdamW) vs the
+oracle's torch-autograd restatement of gcbf_plus.py:354-447 in float64.
+Tolerance: gradients within 2e-4 of the float64 reference relative to the gradient's max
+magnitude per tensor (fp32 accumulation over edges/agents, atomics order); losses 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (oracle_env, oracle_obstacles, oracle_params, product_algo, product_env, product_obstacles,
+                     random_scene)
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("DoubleIntegrator", 6, 4, 1.4, 3), ("SingleIntegrator", 6, 3, 1.4, 3), ("DubinsCar", 6, 3, 1.6, 3),
+         ("LinearDrone", 6, 3, 1.0, 2)]
+
+
+def _setup(env_id, N, B, area, n_obs, seed=21, pretrained=True):
+    agent, goal, obs = random_scene(env_id, N, B, area, n_obs, seed, vel_scale=0.45)
+    env = product_env(env_id, N, area, n_obs)
+    env.edge_cap_per_agent = 64
+    algo = product_algo(env, env_id if pretrained else None, seed=3)
+    pobs = product_obstacles(env_id, obs)
+    graph = env.get_graph(torch.from_numpy(agent).cuda(), torch.from_numpy(goal).cuda(), pobs)
+    rng = np.random.default_rng(seed)
+    unsafe = env.unsafe_mask(graph)
+    safe = (~unsafe) & torch.from_numpy(rng.uniform(size=(B, N)) < 0.6).cuda()      # some agents unlabelled
+    u_qp = env.u_ref(graph) + torch.from_numpy(rng.normal(0, 0.1, size=(B, N, env.action_dim)).astype(np.float32)).cuda()
+    return env, algo, graph, pobs, agent, goal, safe, unsafe, u_qp
+
+
+@pytest.mark.parametrize("env_id,N,B,area,n_obs", CASES)
+@pytest.mark.parametrize("pretrained", [True, False])
+def test_gradients_match_oracle_autograd(env_id, N, B, area, n_obs, pretrained):
+    from gcbfplus_b200.algo.train import read_info, train_minibatch
+    from oracle.algo import gcbf_plus_loss
+    from oracle.nn import to_torch
+    env, algo, graph, pobs, agent, goal, safe, unsafe, u_qp = _setup(env_id, N, B, area, n_obs, pretrained=pretrained)
+    # exercise every loss term with comparable weights
+    algo.loss_action_coef, algo.loss_h_dot_coef, algo.eps = 0.05, 0.3, 0.02
+    ts = train_minibatch(algo, graph, safe, unsafe, u_qp, apply=False)
+    torch.cuda.synchronize()
+    graph.check_overflow()
+    info = read_info(algo)
+    # ---- oracle (float64)
+    oenv = oracle_env(env_id, N, area, n_obs, dtype=torch.float64)
+    cp = to_torch(algo.cbf_params.to_tree(), torch.float64, requires_grad=True)
+    ap = to_torch(algo.actor_net_params.to_tree(), torch.float64, requires_grad=True)
+    packed = pobs.packed.cpu().numpy()
+    graphs = [oenv.sparsify(oenv.get_graph(torch.from_numpy(agent[g]).double(), torch.from_numpy(goal[g]).double(),
+                                           oracle_obstacles(packed[g], torch.float64))) for g in range(B)]
+    total, oinfo = gcbf_plus_loss(oenv, cp, ap, graphs, safe.cpu(), unsafe.cpu(), u_qp.cpu().double(), alpha=algo.alpha,
+                                  eps=algo.eps, coef_action=algo.loss_action_coef, coef_unsafe=algo.loss_unsafe_coef,
+                                  coef_safe=algo.loss_safe_coef, coef_h_dot=algo.loss_h_dot_coef)
+    for k in ("loss/action", "loss/unsafe", "loss/safe", "loss/h_dot", "loss/total", "acc/unsafe", "acc/safe",
+              "acc/h_dot", "acc/unsafe_data_ratio"):
+        assert abs(info[k] - float(oinfo[k])) <= 2e-5 * max(1.0, abs(float(oinfo[k]))), (k, info[k], float(oinfo[k]))
+    names_c, names_a = list(cp), list(ap)
+    gs = torch.autograd.grad(total, [cp[k] for k in names_c] + [ap[k] for k in names_a], allow_unused=True)
+    from gcbfplus_b200.algo.params import NetParams
+    any_nonzero = False
+    for net, names, grads, flat in (("cbf", names_c, gs[:len(names_c)], ts.grad_cbf),
+                                    ("actor", names_a, gs[len(names_c):], ts.grad_act)):
+        proto = algo.cbf_params if net == "cbf" else algo.actor_net_params
+        tmp = NetParams(proto.edge_dim, proto.out_dim, proto.kind, device="cuda")
+        tmp.flat.copy_(flat)
+        got = to_torch(tmp.to_tree(), torch.float64)
+        gmax = max(float(g.abs().max()) for g in grads if g is not None)
+        any_nonzero = any_nonzero or gmax > 0      # a converged pretrained CBF can have exactly zero loss terms
+        for k, g in zip(names, grads):
+            want = g if g is not None else torch.zeros_like(got[k])
+            err = float((got[k] - want).abs().max())
+            scale = max(float(want.abs().max()), 1e-3 * gmax)
+            assert err <= 2e-4 * scale + 1e-9, (net, k, err, scale)
+    assert any_nonzero
+
+
+def test_clip_adamw_and_polyak_match_oracle():
+    """Optimizer kernels in isolation: the oracle's float64 clip + AdamW is fed the SAME gradients
+    (Adam's m/sqrt(v) is sign-like for near-zero entries, so end-to-end comparison through
+    independently rounded gradients is ill-conditioned there)."""
+    from gcbfplus_b200.algo.params import NetParams
+    from gcbfplus_b200.algo.train import apply_gradients, read_info, train_minibatch, update_tgt
+    from oracle.algo import AdamW, compute_norm_and_clip
+    from oracle.nn import to_torch
+    env_id, N, B, area, n_obs = "DoubleIntegrator", 6, 4, 1.4, 3
+    env, algo, graph, pobs, agent, goal, safe, unsafe, u_qp = _setup(env_id, N, B, area, n_obs)
+    algo.loss_action_coef, algo.loss_h_dot_coef = 0.05, 0.3
+    algo.lr_cbf = algo.lr_actor = 1e-3
+    cp = to_torch(algo.cbf_params.to_tree(), torch.float64)
+    ap = to_torch(algo.actor_net_params.to_tree(), torch.float64)
+    tgt0 = algo.cbf_tgt_params.flat.clone()
+    oc, oa = AdamW(cp, lr=1e-3), AdamW(ap, lr=1e-3)
+
+    def tree_of(flat, proto):
+        tmp = NetParams(proto.edge_dim, proto.out_dim, proto.kind, device="cuda")
+        tmp.flat.copy_(flat)
+        return to_torch(tmp.to_tree(), torch.float64)
+
+    for it in range(3):                                            # 3 optimizer steps: bias correction, moments
+        ts = train_minibatch(algo, graph, safe, unsafe, u_qp, apply=False)
+        gc, ga = tree_of(ts.grad_cbf, algo.cbf_params), tree_of(ts.grad_act, algo.actor_net_params)
+        apply_gradients(algo, ts)
+        gcc, nc = compute_norm_and_clip(gc, algo.max_grad_norm)
+        gac, na = compute_norm_and_clip(ga, algo.max_grad_norm)
+        cp, ap = oc.step(cp, gcc), oa.step(ap, gac)
+        info = read_info(algo)
+        assert abs(info["grad_norm/cbf"] - float(nc)) <= 1e-5 * float(nc)
+        assert abs(info["grad_norm/actor"] - float(na)) <= 1e-5 * float(na)
+        got_c = to_torch(algo.cbf_params.to_tree(), torch.float64)
+        got_a = to_torch(algo.actor_net_params.to_tree(), torch.float64)
+        for got, want in ((got_c, cp), (got_a, ap)):
+            for k in want:
+                assert float((got[k] - want[k]).abs().max()) <= 2e-6, (it, k)   # updates are O(1e-3)
+        cp = {k: v.float().double() for k, v in got_c.items()}      # keep the two in lock-step (fp32 storage)
+        ap = {k: v.float().double() for k, v in got_a.items()}
+    assert int(algo._trainer_state.step_cbf.item()) == 3
+    update_tgt(algo, 0.5)
+    torch.testing.assert_close(algo.cbf_tgt_params.flat, 0.5 * algo.cbf_params.flat + 0.5 * tgt0)
+
+
+def test_apply_if_finite_skips_update():
+    from gcbfplus_b200.algo.train import apply_gradients, train_minibatch
+    env, algo, graph, pobs, agent, goal, safe, unsafe, u_qp = _setup("DoubleIntegrator", 6, 2, 1.4, 2)
+    ts = train_minibatch(algo, graph, safe, unsafe, u_qp, apply=False)
+    before = algo.cbf_params.flat.clone()
+    ts.grad_cbf[5] = float("nan")
+    apply_gradients(algo, ts)
+    torch.cuda.synchronize()
+    assert torch.equal(before, algo.cbf_params.flat) and int(ts.step_cbf.item()) == 0
+    assert int(ts.step_act.item()) == 1
+
+
+def test_gemm_kernels_match_torch_fp32():
+    """Numerics of the GEMM building blocks vs plain PyTorch fp32 (allow_tf32 off)."""
+    import ctypes as C
+    from gcbfplus_b200 import _lib
+    lib = _lib.load()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (M, K, N) in [(1, 128, 128), (300, 256, 256), (1000, 128, 256), (4097, 256, 128)]:
+        A = torch.randn(M, K, device="cuda", generator=g)
+        W = torch.randn(K, N, device="cuda", generator=g) * 0.1
+        b = torch.randn(N, device="cuda", generator=g)
+        b2 = torch.randn(N, device="cuda", generator=g)
+        out = torch.empty(M, N, device="cuda")
+        mcount = torch.tensor([M], dtype=torch.int32, device="cuda")
+        _lib.check(lib.gcbf_gemm_nn(1, 0, A.data_ptr(), W.data_ptr(), b.data_ptr(), b2.data_ptr(), out.data_ptr(), None,
+                                    mcount.data_ptr(), 0, M, K, N, st))
+        torch.testing.assert_close(out, torch.relu(A @ W + b + b2), atol=2e-4, rtol=1e-5)
+        aux = torch.randn(M, N, device="cuda", generator=g)
+        acc = torch.randn(M, N, device="cuda", generator=g)
+        want = acc + (A @ W) * (aux > 0)
+        _lib.check(lib.gcbf_gemm_nn(3, 1, A.data_ptr(), W.data_ptr(), None, None, acc.data_ptr(), aux.data_ptr(), None,
+                                    M, M, K, N, st))
+        torch.testing.assert_close(acc, want, atol=2e-4, rtol=1e-5)
+    for (M, K1, N) in [(5, 128, 128), (777, 256, 128), (20000, 128, 256)]:
+        X = torch.randn(M, K1, device="cuda", generator=g)
+        dY = torch.randn(M, N, device="cuda", generator=g)
+        w = (torch.rand(64, device="cuda", generator=g) > 0.3).float()
+        r2a = torch.randint(0, 64, (M,), device="cuda", generator=g, dtype=torch.int32)
+        Cw = torch.zeros(K1, N, device="cuda")
+        db = torch.zeros(N, device="cuda")
+        _lib.check(lib.gcbf_gemm_tn(X.data_ptr(), K1, dY.data_ptr(), Cw.data_ptr(), w.data_ptr(), r2a.data_ptr(), None, M,
+                                    M, K1, N, 64, st))
+        _lib.check(lib.gcbf_colsum(dY.data_ptr(), db.data_ptr(), w.data_ptr(), r2a.data_ptr(), None, M, M, N, 64, st))
+        wd = dY * w[r2a.long()][:, None]
+        torch.testing.assert_close(Cw, X.T @ wd, atol=1e-3 * (M ** 0.5) / 10 + 1e-4, rtol=1e-4)
+        torch.testing.assert_close(db, wd.sum(0), atol=1e-3 * (M ** 0.5) / 10 + 1e-4, rtol=1e-4)
