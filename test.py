@@ -1,0 +1,109 @@
+"""test.py -- evaluation CLI with the reference's flags (test.py:239-266): rollouts with a trained
+(or --u-ref nominal) controller and safe / finish / success rates (test.py:184-198).
+Video rendering / CBF contour plots are out of scope -> --no-video is implied."""
+import argparse
+import os
+
+import numpy as np
+import yaml
+
+from gcbfplus_b200.algo import make_algo
+from gcbfplus_b200.env import make_env
+from gcbfplus_b200.trainer.rollout import RolloutEngine
+from gcbfplus_b200.trainer.utils import test_rates
+
+
+def test(args):
+    print(f"> Running test.py {args}")
+    if args.cpu:
+        raise SystemExit("--cpu: gcbfplus_b200 is the sm_100a CUDA path only (no CPU fallback by design)")
+    np.random.seed(args.seed)
+    config = None
+    if not args.u_ref and args.path is not None:
+        with open(os.path.join(args.path, "config.yaml"), "r") as f:
+            config = yaml.load(f, Loader=yaml.UnsafeLoader)
+    num_agents = config.num_agents if args.num_agents is None else args.num_agents
+    env = make_env(env_id=config.env if args.env is None else args.env, num_agents=num_agents, num_obs=args.obs,
+                   area_size=args.area_size, max_step=args.max_step, max_travel=args.max_travel)
+    policy = "u_ref"
+    algo = None
+    if not args.u_ref:
+        assert args.path is not None, "--path or --u-ref required"
+        model_path = os.path.join(args.path, "models")
+        step = max(int(m) for m in os.listdir(model_path) if m.isdigit()) if args.step is None else args.step
+        print("step: ", step)
+        algo = make_algo(
+            algo=config.algo, env=env, node_dim=env.node_dim, edge_dim=env.edge_dim, state_dim=env.state_dim,
+            action_dim=env.action_dim, n_agents=env.num_agents, gnn_layers=config.gnn_layers,
+            batch_size=config.batch_size, buffer_size=config.buffer_size, horizon=config.horizon,
+            lr_actor=config.lr_actor, lr_cbf=config.lr_cbf, alpha=config.alpha, eps=0.02, inner_epoch=8,
+            loss_action_coef=config.loss_action_coef, loss_unsafe_coef=config.loss_unsafe_coef,
+            loss_safe_coef=config.loss_safe_coef, loss_h_dot_coef=config.loss_h_dot_coef, max_grad_norm=2.0,
+            seed=config.seed)
+        algo.load(model_path, step)
+        policy = "actor"
+        path = args.path
+    else:
+        assert args.env is not None
+        path = os.path.join(f"./logs/{args.env}/nominal")
+        os.makedirs(path, exist_ok=True)
+    n_epi = args.epi - args.offset
+    eng = RolloutEngine(env, n_epi, T=env.max_episode_steps, policy=policy)
+    if algo is not None:
+        eng.set_params(algo.actor_params)
+    g0 = env.reset(args.seed + args.offset, n_envs=n_epi)       # all episodes run as one batch
+    eng.set_initial(g0.agent, g0.goal, g0.obstacle)
+    eng.run()
+    ro = eng.result()
+    rates, is_unsafe, is_finish = test_rates(env, ro)
+    rewards = ro.rewards.sum(dim=1).cpu().numpy()
+    costs = ro.costs.sum(dim=1).cpu().numpy()
+    for i in range(n_epi):
+        print(f"epi: {i}, reward: {rewards[i]:.3f}, cost: {costs[i]:.3f}, safe rate: {rates[i, 0] * 100:.3f}%,"
+              f"finish rate: {rates[i, 1] * 100:.3f}%, success rate: {rates[i, 2] * 100:.3f}%")
+    safe_mean, safe_std = (1 - is_unsafe).mean(), (1 - is_unsafe).std()
+    finish_mean, finish_std = is_finish.mean(), is_finish.std()
+    succ = (1 - is_unsafe) * is_finish
+    print(f"reward: {np.mean(rewards):.3f}, min/max reward: {np.min(rewards):.3f}/{np.max(rewards):.3f}, "
+          f"cost: {np.mean(costs):.3f}, min/max cost: {np.min(costs):.3f}/{np.max(costs):.3f}, "
+          f"safe_rate: {safe_mean * 100:.3f}%, finish_rate: {finish_mean * 100:.3f}%, "
+          f"success_rate: {succ.mean() * 100:.3f}%")
+    if args.log:
+        with open(os.path.join(path, "test_log.csv"), "a") as f:
+            f.write(f"{env.num_agents},{args.epi},{env.max_episode_steps},{env.area_size},{env.params['n_obs']},"
+                    f"{safe_mean * 100:.3f},{safe_std * 100:.3f},{finish_mean * 100:.3f},{finish_std * 100:.3f},"
+                    f"{succ.mean() * 100:.3f},{succ.std() * 100:.3f}\n")
+    if not args.no_video:
+        print("video rendering is out of scope of the B200 hot path (SURVEY.md section 2, row 17); skipped")
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("-n", "--num-agents", type=int, default=None)
+    parser.add_argument("--obs", type=int, default=0)
+    parser.add_argument("--area-size", type=float, required=True)
+    parser.add_argument("--max-step", type=int, default=None)
+    parser.add_argument("--path", type=str, default=None)
+    parser.add_argument("--n-rays", type=int, default=32)
+    parser.add_argument("--alpha", type=float, default=1.0)
+    parser.add_argument("--max-travel", type=float, default=None)
+    parser.add_argument("--cbf", type=int, default=None)
+    parser.add_argument("--seed", type=int, default=1234)
+    parser.add_argument("--debug", action="store_true", default=False)
+    parser.add_argument("--cpu", action="store_true", default=False)
+    parser.add_argument("--u-ref", action="store_true", default=False)
+    parser.add_argument("--env", type=str, default=None)
+    parser.add_argument("--algo", type=str, default=None)
+    parser.add_argument("--step", type=int, default=None)
+    parser.add_argument("--epi", type=int, default=5)
+    parser.add_argument("--offset", type=int, default=0)
+    parser.add_argument("--no-video", action="store_true", default=False)
+    parser.add_argument("--nojit-rollout", action="store_true", default=False)
+    parser.add_argument("--log", action="store_true", default=False)
+    parser.add_argument("--dpi", type=int, default=100)
+    args = parser.parse_args()
+    test(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,69 @@
+"""GPU integration: Trainer.train() for 2 iterations (rollout engine -> labels -> replay -> CUDA
+train steps -> polyak -> save), checkpoint round trip in the reference's pickle layout, test.py metrics."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, product_algo, product_env
+
+pytestmark = pytest.mark.gpu
+
+
+def test_trainer_two_iterations_and_checkpoint(tmp_path):
+    from gcbfplus_b200.trainer.trainer import Trainer
+    env = product_env("DoubleIntegrator", 8, 4.0, 4)
+    env_test = product_env("DoubleIntegrator", 8, 4.0, 4)
+    algo = product_algo(env, None, seed=0)
+    algo.batch_size = 64
+    algo.inner_epoch = 2
+    env._max_step = env_test._max_step = 32
+    before = algo.cbf_params.flat.clone()
+    tr = Trainer(env, env_test, algo, n_env_train=4, n_env_test=4, log_dir=str(tmp_path / "log"), seed=0,
+                 params={"run_name": "t", "training_steps": 1, "eval_interval": 1, "eval_epi": 1, "save_interval": 1})
+    tr.train()
+    torch.cuda.synchronize()
+    assert not torch.equal(before, algo.cbf_params.flat)
+    assert torch.isfinite(algo.cbf_params.flat).all() and torch.isfinite(algo.actor_params.flat).all()
+    keys = set().union(*[set(h) for h in tr.history])
+    for k in ("eval/reward", "eval/cost", "eval/unsafe_frac", "eval/finish", "loss/total", "loss/h_dot", "acc/safe",
+              "grad_norm/cbf", "grad_norm/actor"):
+        assert k in keys, k
+    # second iteration uses the replay path (buffer.length > batch_size)
+    assert algo.buffer.length == 2 * 4 * 32
+    ck = tmp_path / "log" / "models" / "1"
+    tree = pickle.load(open(ck / "cbf.pkl", "rb"))
+    assert tree["params"]["GNN_0"]["GNNLayer_0"]["msg"]["Dense_0"]["kernel"].shape == (10, 256)
+    algo2 = product_algo(env, None, seed=5)
+    algo2.load(str(tmp_path / "log" / "models"), 1)
+    # (the checkpoint of step 1 is written BEFORE update 1, trainer.py:130-139, like the reference)
+    np.testing.assert_array_equal(algo2.cbf_params.to_tree()["params"]["Dense_0"]["kernel"],
+                                  tree["params"]["Dense_0"]["kernel"])
+    assert not torch.equal(algo2.cbf_params.flat, before)
+
+
+def test_reference_pickle_layout_roundtrip(tmp_path):
+    env = product_env("DoubleIntegrator", 8, 4.0, 4)
+    algo = product_algo(env, "DoubleIntegrator")
+    algo.save(str(tmp_path), 1000)
+    z = np.load(os.path.join(GOLDEN, "params_DoubleIntegrator.npz"))
+    tree = pickle.load(open(tmp_path / "1000" / "actor.pkl", "rb"))
+    np.testing.assert_array_equal(tree["params"]["OutputDense"]["kernel"], z["actor:params/OutputDense/kernel"])
+
+
+def test_eval_rates_pretrained_policy_is_safe():
+    """Sanity on the metric path (test.py:184-198): the pretrained DoubleIntegrator policy at the
+    training density keeps the swarm collision-free and mostly reaches the goals."""
+    from gcbfplus_b200.trainer.rollout import RolloutEngine
+    from gcbfplus_b200.trainer.utils import test_rates
+    env = product_env("DoubleIntegrator", 8, 4.0, 0)
+    algo = product_algo(env, "DoubleIntegrator")
+    eng = RolloutEngine(env, 8, T=256, n_obs=0)
+    eng.set_params(algo.actor_params)
+    g0 = env.reset(7, n_envs=8)
+    eng.set_initial(g0.agent, g0.goal, g0.obstacle)
+    eng.run()
+    rates, is_unsafe, is_finish = test_rates(env, eng.result())
+    assert rates[:, 0].mean() >= 0.95 and rates[:, 1].mean() >= 0.6, rates
