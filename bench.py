@@ -182,6 +182,11 @@ def run_ours(args):
     h2d = (h_agent.numel() + h_goal.numel() + h_obs.numel()) * 4
     d2h = (h_rew.numel() + h_cost.numel() + h_final.numel()) * 4
 
+    # ---- train step (update_inner, reported separately per SURVEY 8d): minibatch of 256 graphs of the
+    # recorded rollout, sharded over ranks, incl. the denominator + packed-gradient all-reduces
+    train = None if args.no_train else train_step_bench(torch, dist if world > 1 else None, env, algo, eng, rank, world,
+                                                        args, max_over_ranks, barrier)
+
     # ---- roofline of the dominant kernel (fp32 GEMM 256x256 over the edge rows), timed alone
     roof = gemm_roofline(torch, _lib, dev, int(n_edges), E * N) if rank == 0 else None
     cpu = cpu_baseline(args, steps=1) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
@@ -208,11 +213,59 @@ def run_ours(args):
                 "fp32_fma_tflops": value / (N * E * world) * flop_step / 1e12 / world,
                 "note": "whole rollout vs HBM (312 B/agent-step) and achieved fp32 TFLOP/s per GPU; the path is "
                         "FLOP/latency-bound, not HBM-bound (SURVEY 8d)"},
+            "train_step": train,
             "cpu_baseline": cpu,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_bench(torch, dist, env, algo, eng, rank, world, args, max_over_ranks, barrier):
+    """GCBF+ update_inner throughput: global minibatch of 256 graphs (N=512) drawn from the recorded
+    rollout, B/world graphs per rank, u_qp := u_ref + 0.1 (QP labels are an input)."""
+    from gcbfplus_b200.algo import train as T
+    B_glob = 256
+    B = max(B_glob // world, 1)
+    ro = eng.result()
+    tsel = torch.arange(B, device=env.device) % eng.T
+    esel = torch.arange(B, device=env.device) % eng.E
+    agent = eng.agent[tsel, esel].contiguous()
+    hits = eng.hits[tsel, esel].contiguous()
+    goal = eng.goal[esel].contiguous()
+    old = env.edge_cap_per_agent
+    env.edge_cap_per_agent = 4
+    g = env.get_graph(agent, goal, None, hits=hits)
+    env.edge_cap_per_agent = old
+    obs_rep = ro.obstacle.select(esel.cpu().numpy()) if hasattr(ro.obstacle, "select") else None
+    gm = g._replace(obstacle=obs_rep)
+    unsafe = env.unsafe_mask(gm)
+    safe = ~unsafe
+    u_qp = env.u_ref(g) + 0.1
+    algo._trainer_state = None
+    for _ in range(2):
+        T.train_minibatch(algo, g, safe, unsafe, u_qp, apply=True)
+    torch.cuda.synchronize()
+    g.check_overflow()
+    n_it = 5
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = env.lib.gcbf_launch_count()
+    barrier()
+    ev0.record()
+    for _ in range(n_it):
+        T.train_minibatch(algo, g, safe, unsafe, u_qp, apply=True)
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1)) / n_it
+    launches = (env.lib.gcbf_launch_count() - n0) // n_it
+    n_edges = g.n_edge
+    N = env.num_agents
+    flops = 9.0 * (n_edges * F_EDGE + B * N * F_NODE) * world       # 3 passes x (fwd + ~2x bwd), SURVEY 8d
+    return {"ms_per_minibatch": ms, "graphs_per_s": B * world / (ms * 1e-3),
+            "agent_samples_per_s": B * world * N / (ms * 1e-3), "global_batch_graphs": B * world,
+            "graphs_per_rank": B, "edges_per_rank": n_edges, "launches_per_step": int(launches),
+            "approx_tflops_per_gpu": flops / world / (ms * 1e-3) / 1e12,
+            "allreduce_bytes_per_step": 4 * (algo._trainer_state.packed.numel() + 4) if world > 1 else 0}
 
 
 def gemm_roofline(torch, _lib, dev, n_edges: int, n_agents: int):
@@ -320,6 +373,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--T", type=int, default=T_STEPS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -39,8 +39,8 @@ class TrainState:
         self.v_act = torch.zeros(self.n_act, dtype=f32, device=dev)
         self.step_cbf = torch.zeros(1, dtype=torch.int32, device=dev)
         self.step_act = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.norm_cbf = torch.zeros(2, dtype=f32, device=dev)
-        self.norm_act = torch.zeros(2, dtype=f32, device=dev)
+        self.norm_cbf = torch.zeros(2 + 512, dtype=f32, device=dev)
+        self.norm_act = torch.zeros(2 + 512, dtype=f32, device=dev)
         self.denoms = torch.zeros(4, dtype=f32, device=dev)
         self.ws: Optional[torch.Tensor] = None
         self.ws_key = None

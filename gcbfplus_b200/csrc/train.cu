@@ -640,19 +640,49 @@ static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------ optimizer kernels
+// deterministic two-stage sum of squares (every rank must derive the SAME clip scale from the
+// all-reduced gradient, so no float atomics here): SQN_BLOCKS partials, then an ordered tree.
+constexpr int SQN_BLOCKS = 256;
 __global__ void __launch_bounds__(256)
-sqnorm_kernel(const float* __restrict__ g, const int n, float* __restrict__ out) {
+sqnorm_partial_kernel(const float* __restrict__ g, const int n, float* __restrict__ partial) {
+    __shared__ float sh[2][256];
     float s = 0.f, bad = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float v = g[i];
         s = fmaf(v, v, s);
         bad += isfinite(v) ? 0.f : 1.f;
     }
-    s = warp_sum(s);
-    bad = warp_sum(bad);
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(out + 0, s);
-        if (bad > 0.f) atomicAdd(out + 1, bad);
+    sh[0][threadIdx.x] = s;
+    sh[1][threadIdx.x] = bad;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = sh[0][0];
+        partial[SQN_BLOCKS + blockIdx.x] = sh[1][0];
+    }
+}
+__global__ void __launch_bounds__(SQN_BLOCKS)
+sqnorm_final_kernel(const float* __restrict__ partial, float* __restrict__ out) {
+    __shared__ float sh[2][SQN_BLOCKS];
+    sh[0][threadIdx.x] = partial[threadIdx.x];
+    sh[1][threadIdx.x] = partial[SQN_BLOCKS + threadIdx.x];
+    __syncthreads();
+    for (int o = SQN_BLOCKS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = sh[0][0];
+        out[1] = sh[1][0];
     }
 }
 
@@ -867,15 +897,16 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
     return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int32_t gcbf_grad_sqnorm(const float* grad, int32_t n, float* out2,
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_grad_sqnorm(const float* grad, int32_t n, float* out,
                                                                            void* stream) {
-    GCBF_REQUIRE(grad && out2 && n > 0, "gcbf_grad_sqnorm: bad argument");
+    GCBF_REQUIRE(grad && out && n > 0, "gcbf_grad_sqnorm: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(float), st);
-    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int32_t)e; }
-    sqnorm_kernel<<<min((n + 1023) / 1024, 2 * sm_count()), 256, 0, st>>>(grad, n, out2);
+    sqnorm_partial_kernel<<<SQN_BLOCKS, 256, 0, st>>>(grad, n, out + 2);
     count_launch();
-    return check_launch("sqnorm_kernel");
+    if (int32_t rc = check_launch("sqnorm_partial_kernel")) return rc;
+    sqnorm_final_kernel<<<1, SQN_BLOCKS, 0, st>>>(out + 2, out);
+    count_launch();
+    return check_launch("sqnorm_final_kernel");
 }
 
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_clip_adamw(float* params, const float* grad, float* m,

@@ -180,8 +180,10 @@ int32_t gcbf_train_step(const gcbf_env_desc* desc, const float* hp_host, const f
                         const uint8_t* safe_mask, const uint8_t* unsafe_mask, const float* u_qp,
                         const float* denoms, float* grad_cbf, float* grad_actor, float* stats,
                         float* workspace, int64_t workspace_floats, void* stream);
-/* out2[0] = sum g^2, out2[1] = number of non-finite entries (trainer/utils.py:62-64 compute_norm). */
-int32_t gcbf_grad_sqnorm(const float* grad, int32_t n, float* out2, void* stream);
+/* out[0] = sum g^2, out[1] = number of non-finite entries (trainer/utils.py:62-64 compute_norm);
+ * out must hold 2 + 512 floats (out[2..] = scratch partials).  Deterministic (no float atomics) so
+ * that every rank derives the same clip scale from the all-reduced gradient. */
+int32_t gcbf_grad_sqnorm(const float* grad, int32_t n, float* out, void* stream);
 /* compute_norm_and_clip (trainer/utils.py:66-75) + optax.adamw(lr, b1, b2, eps, weight_decay) wrapped in
  * optax.apply_if_finite (gcbf_plus.py:109-110,127-128): g <- g / max(max_norm, ||g||) * max_norm; if any
  * gradient entry is non-finite nothing is changed; step[0] (device int32) counts applied updates. */

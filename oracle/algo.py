@@ -49,9 +49,11 @@ def safe_mask_horizon(unsafe_mask: np.ndarray, horizon: int) -> np.ndarray:
 def gcbf_plus_loss(env: OracleEnv, cbf_p, actor_p, graphs: List[Graph], safe_mask: torch.Tensor,
                    unsafe_mask: torch.Tensor, u_qp: torch.Tensor, *, alpha: float = 1.0, eps: float = 0.02,
                    coef_action: float = 1e-4, coef_unsafe: float = 1.0, coef_safe: float = 1.0,
-                   coef_h_dot: float = 0.01) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+                   coef_h_dot: float = 0.01, denoms=None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
     """gcbf_plus.py:362-431 `get_loss` for one minibatch.
-    graphs: B graphs; safe/unsafe_mask [B, N] bool; u_qp [B, N, nu]."""
+    graphs: B graphs; safe/unsafe_mask [B, N] bool; u_qp [B, N, nu].
+    denoms = (n_unsafe, n_safe, n_agents) overrides the local counts: with the GLOBAL counts the
+    losses of the shards of a minibatch add up to the full-minibatch loss."""
     dtype = u_qp.dtype
     cbf_ng = {k: v.detach() for k, v in cbf_p.items()}               # stop_gradient(cbf_params)
     h = torch.stack([get_cbf(cbf_p, g).squeeze(-1) for g in graphs]).reshape(-1)
@@ -61,11 +63,14 @@ def gcbf_plus_loss(env: OracleEnv, cbf_p, actor_p, graphs: List[Graph], safe_mas
     # unsafe region h < 0
     unsafe_ratio = um.to(dtype).mean()
     h_unsafe = torch.where(um, h, -one * eps * 2)
-    loss_unsafe = torch.relu(h_unsafe + eps).sum() / (um.sum().to(dtype) + 1e-6)
+    n_us = um.sum().to(dtype) if denoms is None else torch.tensor(float(denoms[0]), dtype=dtype)
+    n_sf = sm.sum().to(dtype) if denoms is None else torch.tensor(float(denoms[1]), dtype=dtype)
+    n_tot = float(h.numel()) if denoms is None else float(denoms[2])
+    loss_unsafe = torch.relu(h_unsafe + eps).sum() / (n_us + 1e-6)
     acc_unsafe = ((torch.where(um, h, one) < 0).sum().to(dtype) + 1e-6) / (um.sum().to(dtype) + 1e-6)
     # safe region h > 0
     h_safe = torch.where(sm, h, one * eps * 2)
-    loss_safe = torch.relu(-h_safe + eps).sum() / (sm.sum().to(dtype) + 1e-6)
+    loss_safe = torch.relu(-h_safe + eps).sum() / (n_sf + 1e-6)
     acc_safe = ((torch.where(sm, h, -one) > 0).sum().to(dtype) + 1e-6) / (sm.sum().to(dtype) + 1e-6)
     # actions and next graphs
     actions = [act(env, actor_p, g) for g in graphs]
@@ -77,10 +82,10 @@ def gcbf_plus_loss(env: OracleEnv, cbf_p, actor_p, graphs: List[Graph], safe_mas
     labeled = um | sm
     v = torch.relu(-h_dot - alpha * h + eps)
     v_ng = torch.relu(-h_dot_ng - alpha * h + eps)
-    loss_h_dot = torch.where(labeled, v, v_ng).mean()
+    loss_h_dot = torch.where(labeled, v, v_ng).sum() / n_tot
     acc_h_dot = ((h_dot + alpha * h) > 0).to(dtype).mean()
     action = torch.stack(actions)
-    loss_action = ((action - u_qp) ** 2).sum(dim=-1).mean()
+    loss_action = ((action - u_qp) ** 2).sum(dim=-1).sum() / n_tot
     total = coef_action * loss_action + coef_unsafe * loss_unsafe + coef_safe * loss_safe + coef_h_dot * loss_h_dot
     info = {"loss/action": loss_action, "loss/unsafe": loss_unsafe, "loss/safe": loss_safe,
             "loss/h_dot": loss_h_dot, "loss/total": total, "acc/unsafe": acc_unsafe, "acc/safe": acc_safe,

@@ -1,0 +1,66 @@
+"""Worker for tests/test_gpu_multi.py (launched by torch.distributed.run, one rank per GPU):
+the sharded train step (denominator all-reduce + one packed gradient all-reduce over NCCL) must
+reproduce the single-GPU full-minibatch gradient, and every rank must end with identical params."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+
+def main(out_path):
+    from helpers import product_algo, product_env, product_obstacles, random_scene
+    from gcbfplus_b200 import dist as gd
+    from gcbfplus_b200.algo import train as T
+    rank, local_rank, world = gd.init_from_env()
+    torch.cuda.set_device(local_rank)
+    env_id, N, B, area, n_obs = "DoubleIntegrator", 16, 8, 2.0, 4
+    agent, goal, obs = random_scene(env_id, N, B, area, n_obs, seed=5)
+    env = product_env(env_id, N, area, n_obs, device=f"cuda:{local_rank}")
+    env.edge_cap_per_agent = 48
+    algo = product_algo(env, env_id)
+    algo.loss_action_coef, algo.loss_h_dot_coef, algo.lr_cbf, algo.lr_actor = 0.05, 0.3, 1e-3, 1e-3
+    pobs = product_obstacles(env_id, obs, device=env.device)
+    dev = env.device
+    full = env.get_graph(torch.from_numpy(agent).to(dev), torch.from_numpy(goal).to(dev), pobs)
+    rng = np.random.default_rng(1)
+    unsafe = env.unsafe_mask(full)
+    safe = (~unsafe) & torch.from_numpy(rng.uniform(size=(B, N)) < 0.6).to(dev)
+    u_qp = env.u_ref(full) + 0.1
+    # --- reference: full minibatch on this GPU, collectives disabled
+    T._dist = lambda: None
+    ts = T.train_minibatch(algo, full, safe, unsafe, u_qp, apply=False)
+    ref = ts.packed.clone()
+    # --- sharded: this rank's graphs only, collectives on
+    del T._dist
+    import importlib
+    importlib.reload(T)
+    lo, hi = gd.shard_bounds(B, rank, world)
+    sel = slice(lo, hi)
+    shard = env.get_graph(full.agent[sel], full.goal[sel], pobs.select(sel), hits=full.hits[sel].contiguous())
+    algo._trainer_state = None
+    ts2 = T.train_minibatch(algo, shard, safe[sel], unsafe[sel], u_qp[sel], apply=True)
+    torch.cuda.synchronize()
+    n = ts2.n_cbf + ts2.n_act
+    gmax = float(ref[:n].abs().max())
+    err = float((ts2.packed[:n] - ref[:n]).abs().max())
+    stats_err = float((ts2.packed[n:n + 10] - ref[n:n + 10]).abs().max())
+    # params identical on all ranks after the update
+    p = torch.cat([algo.cbf_params.flat, algo.actor_net_params.flat])
+    pmax, pmin = p.clone(), p.clone()
+    torch.distributed.all_reduce(pmax, op=torch.distributed.ReduceOp.MAX)
+    torch.distributed.all_reduce(pmin, op=torch.distributed.ReduceOp.MIN)
+    same = bool(torch.equal(pmax, pmin))
+    if rank == 0:
+        json.dump({"world": world, "grad_err": err, "grad_max": gmax, "stats_err": stats_err, "params_identical": same},
+                  open(out_path, "w"))
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
