@@ -48,13 +48,16 @@ _SIGNATURES = {
     "gcbf_param_offsets": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "gcbf_graph_build": (C.c_int32, [C.POINTER(EnvDesc)] + [_P] * 9 + [C.c_int32, _P]),
     "gcbf_gnn_workspace_floats": (C.c_int64, [C.POINTER(EnvDesc), C.c_int32]),
-    "gcbf_gnn_forward": (C.c_int32, [C.POINTER(EnvDesc), C.c_int32, C.c_int32] + [_P] * 9 + [C.c_int32, _P, _P,
+    "gcbf_gnn_forward": (C.c_int32, [C.POINTER(EnvDesc), C.c_int32, C.c_int32] + [_P] * 10 + [C.c_int32, _P, _P,
                                      C.c_int64, _P]),
+    "gcbf_params_t_count": (C.c_int32, [C.c_int32, C.c_int32]),
+    "gcbf_prepare_params": (C.c_int32, [C.c_int32, C.c_int32, _P, _P, _P]),
     "gcbf_env_step": (C.c_int32, [C.POINTER(EnvDesc)] + [_P] * 11 + [C.c_int32, _P]),
     "gcbf_act": (C.c_int32, [C.POINTER(EnvDesc)] + [_P] * 5),
     "gcbf_masks": (C.c_int32, [C.POINTER(EnvDesc)] + [_P] * 9),
     "gcbf_safe_horizon": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "gcbf_gemm_nn": (C.c_int32, [C.c_int32, C.c_int32] + [_P] * 7 + [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "gcbf_gemm_tc": (C.c_int32, [C.c_int32, C.c_int32] + [_P] * 7 + [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "gcbf_gemm_tn": (C.c_int32, [_P, C.c_int32] + [_P] * 5 + [C.c_int32] * 5 + [_P]),
     "gcbf_colsum": (C.c_int32, [_P] * 5 + [C.c_int32] * 4 + [_P]),
     "gcbf_train_workspace_floats": (C.c_int64, [C.POINTER(EnvDesc)]),
@@ -119,6 +122,11 @@ def param_offsets(edge_dim: int, out_dim: int):
     arr = (C.c_int32 * 24)()
     check(load().gcbf_param_offsets(edge_dim, out_dim, arr), "gcbf_param_offsets")
     return list(arr)
+
+
+#: use the tcgen05 tensor-core GEMMs (3xTF32 split, fp32-class accuracy) instead of the SIMT fp32 GEMMs.
+#: GCBF_TENSOR_CORES=0 selects the strict-fp32 SIMT path.
+USE_TC = os.environ.get("GCBF_TENSOR_CORES", "1") != "0"
 
 
 def param_count(edge_dim: int, out_dim: int) -> int:

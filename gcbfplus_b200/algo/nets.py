@@ -41,7 +41,8 @@ class GnnRunner:
             out = torch.empty(G, N, params.out_dim, dtype=torch.float32, device=dev)
         ws = workspace if workspace is not None else self.workspace(d, params.out_dim, dev)
         kind = _lib.NET_CBF if params.kind == "cbf" else _lib.NET_ACTOR
-        rc = env.lib.gcbf_gnn_forward(C.byref(d), kind, params.out_dim, _lib.ptr(params.flat), _lib.ptr(graph.agent),
+        rc = env.lib.gcbf_gnn_forward(C.byref(d), kind, params.out_dim, _lib.ptr(params.flat),
+                                      _lib.ptr(params.prepared(env._stream())), _lib.ptr(graph.agent),
                                       _lib.ptr(graph.goal), _lib.ptr(graph.hits), _lib.ptr(graph.row_start),
                                       _lib.ptr(graph.row_deg), _lib.ptr(graph.edge_recv), _lib.ptr(graph.edge_src),
                                       _lib.ptr(graph.counters), 1 if graph.clip_all else 0, _lib.ptr(out),

@@ -84,6 +84,22 @@ class NetParams:
         self.offsets = _lib.param_offsets(edge_dim, out_dim)
         self.count = _lib.param_count(edge_dim, out_dim)
         self.flat = torch.zeros(self.count, dtype=torch.float32, device=device)
+        self._flat_t = None   # transposed GEMM weights for the tensor-core path (gcbf_prepare_params)
+
+    def prepared(self, stream: int = None):
+        """Transposed GEMM weights (K-major B operands of the tcgen05 path), recomputed from `flat`.
+        Returns None when the tensor-core path is disabled (GCBF_TENSOR_CORES=0)."""
+        if not _lib.USE_TC:
+            return None
+        lib = _lib.load()
+        if self._flat_t is None:
+            n = lib.gcbf_params_t_count(self.edge_dim, self.out_dim)
+            self._flat_t = torch.empty(int(n), dtype=torch.float32, device=self.flat.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.flat.device).cuda_stream
+        _lib.check(lib.gcbf_prepare_params(self.edge_dim, self.out_dim, _lib.ptr(self.flat), _lib.ptr(self._flat_t),
+                                           stream), "gcbf_prepare_params")
+        return self._flat_t
 
     # ---- init (nn/utils.py:21 xavier_uniform kernels, zero biases) ----
     def init_xavier(self, seed: int) -> "NetParams":

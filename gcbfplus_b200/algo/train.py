@@ -81,8 +81,8 @@ def train_minibatch(algo, graph: SwarmGraph, safe_mask: torch.Tensor, unsafe_mas
     dist = _dist()
     if dist is not None:
         dist.all_reduce(ts.denoms)                      # global ratio-of-sums denominators
-    hp = (C.c_float * 6)(algo.alpha, algo.eps, algo.loss_action_coef, algo.loss_unsafe_coef, algo.loss_safe_coef,
-                         algo.loss_h_dot_coef)
+    hp = (C.c_float * 7)(algo.alpha, algo.eps, algo.loss_action_coef, algo.loss_unsafe_coef, algo.loss_safe_coef,
+                         algo.loss_h_dot_coef, 1.0 if _lib.USE_TC else 0.0)
     rc = lib.gcbf_train_step(C.byref(d), hp, _lib.ptr(algo.cbf_params.flat), _lib.ptr(algo.actor_net_params.flat),
                              _lib.ptr(graph.agent), _lib.ptr(graph.goal), _lib.ptr(graph.hits),
                              _lib.ptr(graph.row_start), _lib.ptr(graph.row_deg), _lib.ptr(graph.edge_recv),

@@ -1,0 +1,378 @@
+// gemm_tc.cuh -- Blackwell tensor-core GEMM for the dense MLP layers: tcgen05.mma (kind::tf32)
+// with fp32 operands split as x = hi + lo (3xTF32: hi*hi + hi*lo + lo*hi, fp32 accumulation in
+// TMEM), operands staged by TMA (SWIZZLE_128B, K-major) through an mbarrier pipeline.
+//
+//   C[M,N] = epi( A[M,K] @ Bt[N,K]^T )        A, Bt row-major fp32 (both "K-major")
+//
+// Accuracy: each product carries a relative error ~2^-21 (the dropped lo*lo term and the tf32
+// truncation of lo), i.e. fp32-class results (tests: <= 2e-6 relative to |A||B|), which keeps the
+// <= 1e-5 parity bar of the GNN outputs -- a single-pass TF32/BF16 MMA (2^-11 / 2^-8) would not.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = TMEM alloc + MMA issuer
+// (1 lane), warps 2-5 = operand split (hi/lo in shared memory) and epilogue (TMEM -> registers ->
+// global, bias / ReLU / ReLU-mask / accumulate).  Persistent tile loop; M may come from a device
+// counter (edge count) so the launch is CUDA-graph friendly.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace gcbf {
+namespace tc {
+
+constexpr int BM = 128;        // rows per tile (= UMMA M, TMEM lanes)
+constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;      // tf32: 32 bytes per MMA
+constexpr int THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_c),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024 B | version [46,48) = 1 | layout [61,64) = 2
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+    static constexpr int STAGES = (BN == 256) ? 2 : 3;
+    static constexpr int A_BYTES = BM * BK * 4;     // 16 KB
+    static constexpr int B_BYTES = BN * BK * 4;     // 16 / 32 KB
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI, bool ACCUM>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const float* __restrict__ bias, const float* __restrict__ bias2, float* __restrict__ C,
+               const float* __restrict__ aux, const int32_t* __restrict__ m_ptr, const int m_fixed, const int m_cap,
+               const int K, const int N) {
+    using CF = Cfg<BN>;
+    constexpr int STAGES = CF::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * CF::STAGE_BYTES);
+    uint64_t* full = bars;                 // [STAGES] TMA bytes landed
+    uint64_t* conv = bars + STAGES;        // [STAGES] hi/lo split done (128 arrivals)
+    uint64_t* empty = bars + 2 * STAGES;   // [STAGES] MMAs of the stage retired
+    uint64_t* tmem_full = bars + 3 * STAGES;
+    uint64_t* tmem_empty = bars + 3 * STAGES + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int M = m_ptr ? *m_ptr : m_fixed;
+    M = min(M, m_cap);
+    const int tiles_n = N / BN;
+    const int tiles_m = (M + BM - 1) / BM;
+    const int n_tiles = tiles_m * tiles_n;
+    const int nkb = K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&conv[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * CF::STAGE_BYTES;
+                    mbar_expect_tx(&full[s], CF::A_BYTES + CF::B_BYTES);
+                    tma_load_2d(st, &tmA, &full[s], kb * BK, m0);
+                    tma_load_2d(st + 2 * CF::A_BYTES, &tmB, &full[s], kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+                mbar_wait(tmem_empty, (tcount & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&conv[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(smem + s * CF::STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + CF::A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * CF::A_BYTES;
+                    const uint32_t b_lo = b_hi + CF::B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t koff = k * UMMA_K * 4;  // bytes inside the 128-byte swizzle row
+                        const uint64_t dah = make_desc(a_hi + koff), dal = make_desc(a_lo + koff);
+                        const uint64_t dbh = make_desc(b_hi + koff), dbl = make_desc(b_lo + koff);
+                        umma_tf32(tmem_base, dal, dbh, idesc, (kb | k) != 0);   // small terms first
+                        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(tmem_full);
+            }
+        }
+    } else {
+        // ================= operand split + epilogue (warps 2..5, 128 threads) =================
+        const int et = threadIdx.x - 64;          // 0..127
+        const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+        uint32_t it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                uint8_t* st = smem + s * CF::STAGE_BYTES;
+                // x -> hi = tf32(x) rounded to nearest (13 low mantissa bits cleared, so the tensor core's own
+                // fp32->tf32 conversion is exact), lo = tf32(x - hi) rounded to nearest: |x - hi - lo| <= 2^-24 |x|
+                auto rn = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); };
+                auto split = [&](uint8_t* hi_p, uint8_t* lo_p, int n_vec) {
+                    float4* h4 = reinterpret_cast<float4*>(hi_p);
+                    float4* l4 = reinterpret_cast<float4*>(lo_p);
+                    for (int i = et; i < n_vec; i += 128) {
+                        const float4 v = h4[i];
+                        float4 h, l;
+                        h.x = rn(v.x); h.y = rn(v.y); h.z = rn(v.z); h.w = rn(v.w);
+                        l.x = rn(v.x - h.x); l.y = rn(v.y - h.y); l.z = rn(v.z - h.z); l.w = rn(v.w - h.w);
+                        h4[i] = h;
+                        l4[i] = l;
+                    }
+                };
+                split(st, st + CF::A_BYTES, CF::A_BYTES / 16);
+                split(st + 2 * CF::A_BYTES, st + 2 * CF::A_BYTES + CF::B_BYTES, CF::B_BYTES / 16);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&conv[s]);
+            }
+            // ---- epilogue
+            mbar_wait(tmem_full, tcount & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = quarter * 32 + lane;
+            const int m = m0 + row;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                if (m < M) {
+                    const int n = n0 + c0;
+                    float* crow = C + (size_t)m * N + n;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) {
+                            const float4 bb = *reinterpret_cast<const float4*>(bias + n + j);
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                            if (bias2) {
+                                const float4 b2 = *reinterpret_cast<const float4*>(bias2 + n + j);
+                                o.x += b2.x; o.y += b2.y; o.z += b2.z; o.w += b2.w;
+                            }
+                            if (EPI == EPI_BIAS_RELU) {
+                                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                            }
+                        } else if (EPI == EPI_RELU_MASK) {
+                            const float4 mk = *reinterpret_cast<const float4*>(aux + (size_t)m * N + n + j);
+                            o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
+                            o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+                        }
+                        float4* dst = reinterpret_cast<float4*>(crow + j);
+                        if (ACCUM) {
+                            const float4 old = *dst;
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *dst = o;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tmem_empty);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, 32 cols], 128-byte swizzle.
+inline int32_t make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled unavailable");
+        return -2;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d", (int)r, rows, cols);
+        return -2;
+    }
+    return 0;
+}
+
+template <int BN>
+inline int32_t launch_bn(int epi, bool accum, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
+                         const float* bias2, float* C, const float* aux, RowCount rc, int K, int N, int grid,
+                         cudaStream_t st) {
+    constexpr int smem = Cfg<BN>::SMEM_BYTES;
+#define GCBF_TC_CASE(E, ACC)                                                                                      \
+    do {                                                                                                          \
+        auto kern = gemm_tc_kernel<BN, E, ACC>;                                                                   \
+        static bool attr_done = false;                                                                            \
+        if (!attr_done) {                                                                                         \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                        \
+            attr_done = true;                                                                                     \
+        }                                                                                                         \
+        kern<<<grid, THREADS, smem, st>>>(tmA, tmB, bias, bias2, C, aux, rc.ptr, rc.fixed, rc.cap, K, N);         \
+    } while (0)
+    if (!accum) {
+        switch (epi) {
+            case EPI_BIAS: GCBF_TC_CASE(EPI_BIAS, false); break;
+            case EPI_BIAS_RELU: GCBF_TC_CASE(EPI_BIAS_RELU, false); break;
+            case EPI_NONE: GCBF_TC_CASE(EPI_NONE, false); break;
+            case EPI_RELU_MASK: GCBF_TC_CASE(EPI_RELU_MASK, false); break;
+            default: set_error("bad epilogue"); return -1;
+        }
+    } else {
+        switch (epi) {
+            case EPI_NONE: GCBF_TC_CASE(EPI_NONE, true); break;
+            case EPI_RELU_MASK: GCBF_TC_CASE(EPI_RELU_MASK, true); break;
+            default: set_error("bad accumulate epilogue"); return -1;
+        }
+    }
+#undef GCBF_TC_CASE
+    count_launch();
+    return check_launch("gemm_tc_kernel");
+}
+
+// C[M,N] = epi(A[M,K] @ Bt[N,K]^T).  A must be backed by at least rc.cap rows.
+inline int32_t launch_gemm_tc(int epi, bool accum, const float* A, const float* Bt, const float* bias,
+                              const float* bias2, float* C, const float* aux, RowCount rc, int K, int N,
+                              cudaStream_t st) {
+    if (K % BK != 0 || (N != 128 && N != 256)) {
+        set_error("gemm_tc: K=%d N=%d unsupported", K, N);
+        return -1;
+    }
+    const int rows = rc.ptr ? rc.cap : min(rc.fixed, rc.cap);
+    if (rows <= 0) return 0;
+    CUtensorMap tmA, tmB;
+    if (int32_t r = make_map(&tmA, A, rc.cap, K, BM)) return r;
+    if (int32_t r = make_map(&tmB, Bt, N, K, N)) return r;
+    const int tiles = (rows + BM - 1) / BM;
+    const int grid = min(tiles, sm_count());
+    if (N == 256) return launch_bn<256>(epi, accum, tmA, tmB, bias, bias2, C, aux, rc, K, N, grid, st);
+    return launch_bn<128>(epi, accum, tmA, tmB, bias, bias2, C, aux, rc, K, N, grid, st);
+}
+
+}  // namespace tc
+}  // namespace gcbf

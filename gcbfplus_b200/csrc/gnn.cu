@@ -1,17 +1,31 @@
 // gnn.cu -- GNN forward for one network (CBF h(x) or policy pi(x)) over a swarm batch.
 #include "gemm.cuh"
+#include "gemm_tc.cuh"
 #include "gnn.cuh"
+#include "translayout.cuh"
 
 using namespace gcbf;
 
 namespace gcbf {
 
-int32_t gnn_forward_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* agent, const float* goal,
+// Dense layer i of the network: Y = epi(X @ W_i + b_i).  With PT (transposed weights, see
+// translayout.cuh) the tcgen05 tensor-core kernel is used, otherwise the strict-fp32 SIMT kernel.
+static int32_t dense_fwd(int epi, const ParamLayout& L, const TransLayout& TL, int li, const float* P, const float* PT,
+                         const float* X, float* Y, const float* bias2, RowCount rc, cudaStream_t st) {
+    const int row_off = (li == L_UPD0) ? 3 * 256 : 0;   // update/Dense_0: rows 3..130 multiply the aggregated message
+    const int K = (li == L_UPD0) ? 128 : L.in[li];
+    if (PT)
+        return tc::launch_gemm_tc(epi, false, X, PT + TL.w[li], P + L.b[li], bias2, Y, nullptr, rc, K, L.out[li], st);
+    return launch_gemm_nn(epi, false, X, P + L.w[li] + row_off, P + L.b[li], bias2, Y, nullptr, rc, K, L.out[li], st);
+}
+
+int32_t gnn_forward_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* PT, const float* agent, const float* goal,
                          const float* hits, const int32_t* row_start, const int32_t* row_deg,
                          const int32_t* edge_recv, const int32_t* edge_src, const int32_t* counters, int clip_all,
                          float* out, float* ws, cudaStream_t st) {
     const int ed = env_ed(d->env_kind);
     const ParamLayout L = make_layout(ed, out_dim);
+    const TransLayout TL = make_trans_layout(L);
     const int A = d->n_graphs * d->n_agents;
     const int cap = d->edge_cap;
     const GnnWs W = make_ws(cap, A);
@@ -31,10 +45,10 @@ int32_t gnn_forward_impl(const gcbf_env_desc* d, int out_dim, const float* P, co
         if ((rc = check_launch("edge_l1_kernel"))) return rc;
     }
     // 2-5. message MLP tail + gate MLP
-    if ((rc = launch_gemm_nn(EPI_BIAS, false, ws + W.x1, P + L.w[L_MSG1], P + L.b[L_MSG1], nullptr, ws + W.x2, nullptr, re, 256, 256, st))) return rc;
-    if ((rc = launch_gemm_nn(EPI_BIAS, false, ws + W.x2, P + L.w[L_MSGOUT], P + L.b[L_MSGOUT], nullptr, ws + W.msg, nullptr, re, 256, 128, st))) return rc;
-    if ((rc = launch_gemm_nn(EPI_BIAS_RELU, false, ws + W.msg, P + L.w[L_ATT0], P + L.b[L_ATT0], nullptr, ws + W.g1, nullptr, re, 128, 128, st))) return rc;
-    if ((rc = launch_gemm_nn(EPI_BIAS, false, ws + W.g1, P + L.w[L_ATT1], P + L.b[L_ATT1], nullptr, ws + W.g2, nullptr, re, 128, 128, st))) return rc;
+    if ((rc = dense_fwd(EPI_BIAS, L, TL, L_MSG1, P, PT, ws + W.x1, ws + W.x2, nullptr, re, st))) return rc;
+    if ((rc = dense_fwd(EPI_BIAS, L, TL, L_MSGOUT, P, PT, ws + W.x2, ws + W.msg, nullptr, re, st))) return rc;
+    if ((rc = dense_fwd(EPI_BIAS_RELU, L, TL, L_ATT0, P, PT, ws + W.msg, ws + W.g1, nullptr, re, st))) return rc;
+    if ((rc = dense_fwd(EPI_BIAS, L, TL, L_ATT1, P, PT, ws + W.g1, ws + W.g2, nullptr, re, st))) return rc;
     // 6. attention softmax + aggregation
     {
         const int grid = min((A + 7) / 8, 4 * nsm);
@@ -44,11 +58,11 @@ int32_t gnn_forward_impl(const gcbf_env_desc* d, int out_dim, const float* P, co
         if ((rc = check_launch("attn_aggregate_kernel"))) return rc;
     }
     // 7-11. update MLP (agent one-hot [0,0,1] folded into the bias: row 2 of update/Dense_0) + head MLP
-    if ((rc = launch_gemm_nn(EPI_BIAS_RELU, false, ws + W.ag, P + L.w[L_UPD0] + 3 * 256, P + L.b[L_UPD0], P + L.w[L_UPD0] + 2 * 256, ws + W.v1, nullptr, ra, 128, 256, st))) return rc;
-    if ((rc = launch_gemm_nn(EPI_BIAS, false, ws + W.v1, P + L.w[L_UPD1], P + L.b[L_UPD1], nullptr, ws + W.v2, nullptr, ra, 256, 256, st))) return rc;
-    if ((rc = launch_gemm_nn(EPI_BIAS, false, ws + W.v2, P + L.w[L_UPDOUT], P + L.b[L_UPDOUT], nullptr, ws + W.v3, nullptr, ra, 256, 128, st))) return rc;
-    if ((rc = launch_gemm_nn(EPI_BIAS_RELU, false, ws + W.v3, P + L.w[L_HEAD0], P + L.b[L_HEAD0], nullptr, ws + W.h1, nullptr, ra, 128, 256, st))) return rc;
-    if ((rc = launch_gemm_nn(EPI_BIAS, false, ws + W.h1, P + L.w[L_HEAD1], P + L.b[L_HEAD1], nullptr, ws + W.h2, nullptr, ra, 256, 256, st))) return rc;
+    if ((rc = dense_fwd(EPI_BIAS_RELU, L, TL, L_UPD0, P, PT, ws + W.ag, ws + W.v1, P + L.w[L_UPD0] + 2 * 256, ra, st))) return rc;
+    if ((rc = dense_fwd(EPI_BIAS, L, TL, L_UPD1, P, PT, ws + W.v1, ws + W.v2, nullptr, ra, st))) return rc;
+    if ((rc = dense_fwd(EPI_BIAS, L, TL, L_UPDOUT, P, PT, ws + W.v2, ws + W.v3, nullptr, ra, st))) return rc;
+    if ((rc = dense_fwd(EPI_BIAS_RELU, L, TL, L_HEAD0, P, PT, ws + W.v3, ws + W.h1, nullptr, ra, st))) return rc;
+    if ((rc = dense_fwd(EPI_BIAS, L, TL, L_HEAD1, P, PT, ws + W.h1, ws + W.h2, nullptr, ra, st))) return rc;
     // 12. output layer + tanh
     {
         const int grid = min((A + 7) / 8, 4 * nsm);
@@ -68,7 +82,7 @@ extern "C" __attribute__((visibility("default"))) int64_t gcbf_gnn_workspace_flo
 }
 
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_gnn_forward(const gcbf_env_desc* desc, int32_t net_kind, int32_t out_dim, const float* params,
-                                    const float* agent, const float* goal, const float* hits,
+                                    const float* params_t, const float* agent, const float* goal, const float* hits,
                                     const int32_t* row_start, const int32_t* row_deg, const int32_t* edge_recv,
                                     const int32_t* edge_src, const int32_t* counters, int32_t clip_all, float* out,
                                     float* workspace, int64_t workspace_floats, void* stream) {
@@ -83,8 +97,9 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_gnn_forward(const
     GCBF_REQUIRE(workspace_floats >= need, "workspace too small: %lld < %lld floats", (long long)workspace_floats,
                  (long long)need);
     GCBF_REQUIRE((((uintptr_t)params | (uintptr_t)workspace) & 15) == 0, "params/workspace must be 16-byte aligned");
-    return gnn_forward_impl(desc, out_dim, params, agent, goal, hits, row_start, row_deg, edge_recv, edge_src, counters,
-                            clip_all, out, workspace, (cudaStream_t)stream);
+    GCBF_REQUIRE(params_t == nullptr || (((uintptr_t)params_t) & 15) == 0, "params_t must be 16-byte aligned");
+    return gnn_forward_impl(desc, out_dim, params, params_t, agent, goal, hits, row_start, row_deg, edge_recv, edge_src,
+                            counters, clip_all, out, workspace, (cudaStream_t)stream);
 }
 
 // ---- building blocks exported for unit tests and for bench.py's isolated kernel timing ----
@@ -118,4 +133,33 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_colsum(const floa
     GCBF_REQUIRE(dY && db, "gcbf_colsum: NULL pointer");
     return launch_colsum(dY, db, roww, row2agent, RowCount{m_ptr, m_fixed, m_cap}, N, n_agents_total,
                          (cudaStream_t)stream);
+}
+
+// ---- tensor-core (tcgen05 3xTF32) variant of gcbf_gemm_nn: C = epi(A[M,K] @ Bt[N,K]^T) ----
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_gemm_tc(int32_t epi, int32_t accum, const float* A,
+                                                                       const float* Bt, const float* bias,
+                                                                       const float* bias2, float* C, const float* aux,
+                                                                       const int32_t* m_ptr, int32_t m_fixed,
+                                                                       int32_t m_cap, int32_t K, int32_t N,
+                                                                       void* stream) {
+    GCBF_REQUIRE(A && Bt && C, "gcbf_gemm_tc: NULL pointer");
+    GCBF_REQUIRE((epi != EPI_BIAS && epi != EPI_BIAS_RELU) || bias, "gcbf_gemm_tc: bias required");
+    GCBF_REQUIRE(epi != EPI_RELU_MASK || aux, "gcbf_gemm_tc: aux required");
+    GCBF_REQUIRE((((uintptr_t)A | (uintptr_t)Bt | (uintptr_t)C) & 15) == 0, "gcbf_gemm_tc: 16-byte alignment required");
+    return gcbf::tc::launch_gemm_tc(epi, accum != 0, A, Bt, bias, bias2, C, aux, RowCount{m_ptr, m_fixed, m_cap}, K, N,
+                                    (cudaStream_t)stream);
+}
+
+// Transposed GEMM weights of one network (the K-major B operands of the tensor-core path).
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_params_t_count(int32_t edge_dim, int32_t out_dim) {
+    if (edge_dim < 1 || edge_dim > 6 || out_dim < 1 || out_dim > 4) return -1;
+    return make_trans_layout(make_layout(edge_dim, out_dim)).total;
+}
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_prepare_params(int32_t edge_dim, int32_t out_dim,
+                                                                              const float* params, float* params_t,
+                                                                              void* stream) {
+    GCBF_REQUIRE(edge_dim >= 1 && edge_dim <= 6 && out_dim >= 1 && out_dim <= 4 && params && params_t,
+                 "gcbf_prepare_params: bad argument");
+    const ParamLayout L = make_layout(edge_dim, out_dim);
+    return build_transposes(L, make_trans_layout(L), params, params_t, (cudaStream_t)stream);
 }

@@ -7,64 +7,16 @@
 // trainer/utils.py:62-75 (compute_norm_and_clip), optax.adamw + optax.apply_if_finite
 // (gcbf_plus.py:109-110,127-128) and gcbf_plus.py:188-191 (update_tgt).
 #include "gemm.cuh"
+#include "gemm_tc.cuh"
 #include "gnn.cuh"
+#include "translayout.cuh"
 
 namespace gcbf {
 
-int32_t gnn_forward_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* agent, const float* goal,
+int32_t gnn_forward_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* PT, const float* agent, const float* goal,
                          const float* hits, const int32_t* row_start, const int32_t* row_deg,
                          const int32_t* edge_recv, const int32_t* edge_src, const int32_t* counters, int clip_all,
                          float* out, float* ws, cudaStream_t st);
-
-// ------------------------------------------------------------------------------------ small helpers
-__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
-    __shared__ float tile[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int r = r0 + i, c = c0 + threadIdx.x;
-        if (r < rows && c < cols) tile[i][threadIdx.x] = in[(size_t)r * cols + c];
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int c = c0 + i, r = r0 + threadIdx.x;
-        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
-    }
-}
-
-static int32_t launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st) {
-    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-    transpose_kernel<<<grid, block, 0, st>>>(in, out, rows, cols);
-    count_launch();
-    return check_launch("transpose_kernel");
-}
-
-// Transposed copies of the GEMM weights of one network (backward-data operands).
-struct TransLayout {
-    int w[12];
-    int total;
-};
-static TransLayout make_trans_layout(const ParamLayout& L) {
-    TransLayout T;
-    int off = 0;
-    for (int i = 0; i < 12; ++i) {
-        T.w[i] = off;
-        int rows = L.in[i];
-        if (i == L_UPD0) rows = 128;  // only the aggregated-message rows 3..130
-        if (i == L_MSG0 || i == L_GATE || i == L_OUT) { T.w[i] = -1; continue; }
-        off += rows * L.out[i];
-    }
-    T.total = off;
-    return T;
-}
-static int32_t build_transposes(const ParamLayout& L, const TransLayout& T, const float* P, float* PT, cudaStream_t st) {
-    for (int i = 0; i < 12; ++i) {
-        if (T.w[i] < 0) continue;
-        const float* src = P + L.w[i] + (i == L_UPD0 ? 3 * 256 : 0);
-        const int rows = (i == L_UPD0) ? 128 : L.in[i];
-        if (int32_t rc = launch_transpose(src, PT + T.w[i], rows, L.out[i], st)) return rc;
-    }
-    return 0;
-}
 
 // ------------------------------------------------------------------------------------ act + dynamics (forward)
 // a = 2 pi + u_ref ; u = clip_action(a) ; x' = agent_step_euler(x, u)   (gcbf_plus.py:386-391)
@@ -550,7 +502,19 @@ struct BwdArgs {
     const int32_t *row_start, *row_deg, *edge_recv, *edge_src, *counters;
     int clip_all;
     float* d_es;           // optional [A, ED] (accumulated) : gradient wrt the agents' edge states
+    int use_tc;            // 1: backward-data GEMMs on the tcgen05 path
 };
+
+// dX = epi(dY @ W_i^T) (+= if accum).  SIMT: B = W^T from PT; tensor core: Bt = W itself (K-major).
+static int32_t dense_bwd_data(const BwdArgs& b, const ParamLayout& L, const TransLayout& TL, int li, int epi, bool accum,
+                              const float* dY, float* dX, const float* aux, RowCount rc, cudaStream_t st) {
+    const int N = (li == L_UPD0) ? 128 : L.in[li];
+    const int K = L.out[li];
+    if (b.use_tc)
+        return tc::launch_gemm_tc(epi, accum, dY, b.P + L.w[li] + (li == L_UPD0 ? 3 * 256 : 0), nullptr, nullptr, dX, aux,
+                                  rc, K, N, st);
+    return launch_gemm_nn(epi, accum, dY, b.PT + TL.w[li], nullptr, nullptr, dX, aux, rc, K, N, st);
+}
 
 static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
     const gcbf_env_desc* d = b.d;
@@ -577,21 +541,21 @@ static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
     // ---- head MLP
     RC(launch_gemm_tn(fw + W.h1, 256, gw + W.h2, b.G + L.w[L_HEAD1], b.roww, nullptr, ra, 256, 256, A, st));
     RC(launch_colsum(gw + W.h2, b.G + L.b[L_HEAD1], b.roww, nullptr, ra, 256, A, st));
-    RC(launch_gemm_nn(EPI_RELU_MASK, false, gw + W.h2, b.PT + TL.w[L_HEAD1], nullptr, nullptr, gw + W.h1, fw + W.h1, ra, 256, 256, st));
+    RC(dense_bwd_data(b, L, TL, L_HEAD1, EPI_RELU_MASK, false, gw + W.h2, gw + W.h1, fw + W.h1, ra, st));
     RC(launch_gemm_tn(fw + W.v3, 128, gw + W.h1, b.G + L.w[L_HEAD0], b.roww, nullptr, ra, 128, 256, A, st));
     RC(launch_colsum(gw + W.h1, b.G + L.b[L_HEAD0], b.roww, nullptr, ra, 256, A, st));
-    RC(launch_gemm_nn(EPI_NONE, false, gw + W.h1, b.PT + TL.w[L_HEAD0], nullptr, nullptr, gw + W.v3, nullptr, ra, 256, 128, st));
+    RC(dense_bwd_data(b, L, TL, L_HEAD0, EPI_NONE, false, gw + W.h1, gw + W.v3, nullptr, ra, st));
     // ---- update MLP
     RC(launch_gemm_tn(fw + W.v2, 256, gw + W.v3, b.G + L.w[L_UPDOUT], b.roww, nullptr, ra, 256, 128, A, st));
     RC(launch_colsum(gw + W.v3, b.G + L.b[L_UPDOUT], b.roww, nullptr, ra, 128, A, st));
-    RC(launch_gemm_nn(EPI_NONE, false, gw + W.v3, b.PT + TL.w[L_UPDOUT], nullptr, nullptr, gw + W.v2, nullptr, ra, 128, 256, st));
+    RC(dense_bwd_data(b, L, TL, L_UPDOUT, EPI_NONE, false, gw + W.v3, gw + W.v2, nullptr, ra, st));
     RC(launch_gemm_tn(fw + W.v1, 256, gw + W.v2, b.G + L.w[L_UPD1], b.roww, nullptr, ra, 256, 256, A, st));
     RC(launch_colsum(gw + W.v2, b.G + L.b[L_UPD1], b.roww, nullptr, ra, 256, A, st));
-    RC(launch_gemm_nn(EPI_RELU_MASK, false, gw + W.v2, b.PT + TL.w[L_UPD1], nullptr, nullptr, gw + W.v1, fw + W.v1, ra, 256, 256, st));
+    RC(dense_bwd_data(b, L, TL, L_UPD1, EPI_RELU_MASK, false, gw + W.v2, gw + W.v1, fw + W.v1, ra, st));
     RC(launch_gemm_tn(fw + W.ag, 128, gw + W.v1, b.G + L.w[L_UPD0] + 3 * 256, b.roww, nullptr, ra, 128, 256, A, st));
     RC(launch_colsum(gw + W.v1, b.G + L.b[L_UPD0], b.roww, nullptr, ra, 256, A, st));
     RC(launch_colsum(gw + W.v1, b.G + L.w[L_UPD0] + 2 * 256, b.roww, nullptr, ra, 256, A, st));  // agent one-hot row
-    RC(launch_gemm_nn(EPI_NONE, false, gw + W.v1, b.PT + TL.w[L_UPD0], nullptr, nullptr, gw + W.ag, nullptr, ra, 256, 128, st));
+    RC(dense_bwd_data(b, L, TL, L_UPD0, EPI_NONE, false, gw + W.v1, gw + W.ag, nullptr, ra, st));
     // ---- attention + aggregation
     {
         const int grid = min((A + 7) / 8, 2 * nsm);
@@ -604,17 +568,17 @@ static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
     // ---- gate MLP (edge rows; dW weighted by the receiver's weight)
     RC(launch_gemm_tn(fw + W.g1, 128, gw + W.g2, b.G + L.w[L_ATT1], b.roww, b.edge_recv, re, 128, 128, A, st));
     RC(launch_colsum(gw + W.g2, b.G + L.b[L_ATT1], b.roww, b.edge_recv, re, 128, A, st));
-    RC(launch_gemm_nn(EPI_RELU_MASK, false, gw + W.g2, b.PT + TL.w[L_ATT1], nullptr, nullptr, gw + W.g1, fw + W.g1, re, 128, 128, st));
+    RC(dense_bwd_data(b, L, TL, L_ATT1, EPI_RELU_MASK, false, gw + W.g2, gw + W.g1, fw + W.g1, re, st));
     RC(launch_gemm_tn(fw + W.msg, 128, gw + W.g1, b.G + L.w[L_ATT0], b.roww, b.edge_recv, re, 128, 128, A, st));
     RC(launch_colsum(gw + W.g1, b.G + L.b[L_ATT0], b.roww, b.edge_recv, re, 128, A, st));
-    RC(launch_gemm_nn(EPI_NONE, true, gw + W.g1, b.PT + TL.w[L_ATT0], nullptr, nullptr, gw + W.msg, nullptr, re, 128, 128, st));
+    RC(dense_bwd_data(b, L, TL, L_ATT0, EPI_NONE, true, gw + W.g1, gw + W.msg, nullptr, re, st));
     // ---- message MLP
     RC(launch_gemm_tn(fw + W.x2, 256, gw + W.msg, b.G + L.w[L_MSGOUT], b.roww, b.edge_recv, re, 256, 128, A, st));
     RC(launch_colsum(gw + W.msg, b.G + L.b[L_MSGOUT], b.roww, b.edge_recv, re, 128, A, st));
-    RC(launch_gemm_nn(EPI_NONE, false, gw + W.msg, b.PT + TL.w[L_MSGOUT], nullptr, nullptr, gw + W.x2, nullptr, re, 128, 256, st));
+    RC(dense_bwd_data(b, L, TL, L_MSGOUT, EPI_NONE, false, gw + W.msg, gw + W.x2, nullptr, re, st));
     RC(launch_gemm_tn(fw + W.x1, 256, gw + W.x2, b.G + L.w[L_MSG1], b.roww, b.edge_recv, re, 256, 256, A, st));
     RC(launch_colsum(gw + W.x2, b.G + L.b[L_MSG1], b.roww, b.edge_recv, re, 256, A, st));
-    RC(launch_gemm_nn(EPI_RELU_MASK, false, gw + W.x2, b.PT + TL.w[L_MSG1], nullptr, nullptr, gw + W.x1, fw + W.x1, re, 256, 256, st));
+    RC(dense_bwd_data(b, L, TL, L_MSG1, EPI_RELU_MASK, false, gw + W.x2, gw + W.x1, fw + W.x1, re, st));
     // ---- edge layer 1
     {
         const int grid = min(max(cap / 64, 1), 4 * nsm);
@@ -818,16 +782,19 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
     RC(build_transposes(Lc, make_trans_layout(Lc), cbf_params, ws + TW.pt_cbf, st));
     RC(build_transposes(La, make_trans_layout(La), actor_params, ws + TW.pt_act, st));
     // ---- forward: h = cbf(g), pi = actor(g), x' = f(x, clip(2 pi + u_ref)), h' = cbf(g')
-    RC(gnn_forward_impl(d, 1, cbf_params, agent, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 0,
+    const int use_tc = hp_host[6] != 0.f;
+    const float* ptc = use_tc ? ws + TW.pt_cbf : nullptr;
+    const float* pta = use_tc ? ws + TW.pt_act : nullptr;
+    RC(gnn_forward_impl(d, 1, cbf_params, ptc, agent, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 0,
                         ws + TW.h, ws + TW.ws0, st));
-    RC(gnn_forward_impl(d, nu, actor_params, agent, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 0,
+    RC(gnn_forward_impl(d, nu, actor_params, pta, agent, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 0,
                         ws + TW.pi, ws + TW.ws1, st));
     GCBF_DISPATCH_ENV(d->env_kind, {
         act_dyn_kernel<KIND><<<(A + 127) / 128, 128, 0, st>>>(*d, agent, goal, ws + TW.pi, ws + TW.act, ws + TW.xn);
     });
     count_launch();
     RC(check_launch("act_dyn_kernel"));
-    RC(gnn_forward_impl(d, 1, cbf_params, ws + TW.xn, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 1,
+    RC(gnn_forward_impl(d, 1, cbf_params, ptc, ws + TW.xn, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 1,
                         ws + TW.hn, ws + TW.ws2, st));
     // ---- losses and their derivatives wrt h, h', a
     {
@@ -863,6 +830,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
     b.G = grad_cbf;
     b.clip_all = 1;
     b.d_es = ws + TW.d_es;
+    b.use_tc = use_tc;
     RC(gnn_backward_impl(b, st));
     // ---- through the Euler step / clips into the policy output
     GCBF_DISPATCH_ENV(d->env_kind, {

@@ -116,11 +116,17 @@ int32_t gcbf_graph_build(const gcbf_env_desc* desc, const float* agent, const fl
  * algo/module/policy.py:63-128), including env.add_edge_feats when clip_all = 1
  * (env/double_integrator.py:275-286).
  * params: flat fp32 buffer (gcbf_param_offsets).  out: [A, out_dim] (tanh applied).
+ * params_t: NULL -> strict-fp32 SIMT GEMMs; else the transposed GEMM weights from
+ * gcbf_prepare_params -> tcgen05 tensor-core GEMMs (3xTF32 split, fp32 accumulate; same tolerance).
  * workspace: gcbf_gnn_workspace_floats() floats; holds the saved activations
  * the backward pass reads. */
 int64_t gcbf_gnn_workspace_floats(const gcbf_env_desc* desc, int32_t out_dim);
+int32_t gcbf_params_t_count(int32_t edge_dim, int32_t out_dim);
+int32_t gcbf_prepare_params(int32_t edge_dim, int32_t out_dim, const float* params, float* params_t,
+                            void* stream);
 int32_t gcbf_gnn_forward(const gcbf_env_desc* desc, int32_t net_kind, int32_t out_dim,
-                         const float* params, const float* agent, const float* goal, const float* hits,
+                         const float* params, const float* params_t, const float* agent, const float* goal,
+                         const float* hits,
                          const int32_t* row_start, const int32_t* row_deg, const int32_t* edge_recv,
                          const int32_t* edge_src, const int32_t* counters, int32_t clip_all, float* out,
                          float* workspace, int64_t workspace_floats, void* stream);
@@ -160,7 +166,8 @@ int32_t gcbf_safe_horizon(const uint8_t* unsafe, uint8_t* safe, int32_t n_rollou
  * env.forward_graph(g, a); h' = cbf(g'); loss = c_a mean||a - u_qp||^2 + c_u unsafe + c_s safe +
  * c_h mean relu(-h_dot - alpha h + eps) with the reference's stop-gradient routing for
  * unlabelled agents (:399-407); jax.value_and_grad wrt (cbf_params, actor_params).
- *   hp_host[6] (HOST): alpha, eps, loss_action_coef, loss_unsafe_coef, loss_safe_coef, loss_h_dot_coef
+ *   hp_host[7] (HOST): alpha, eps, loss_action_coef, loss_unsafe_coef, loss_safe_coef, loss_h_dot_coef,
+ *     use_tensor_cores (0: strict-fp32 SIMT GEMMs, 1: tcgen05 3xTF32 for forward + backward-data GEMMs)
  *   denoms[4] (device): GLOBAL n_unsafe, n_safe, n_agents of the minibatch (gcbf_mask_counts, then
  *     summed over ranks by the host when the minibatch is sharded)
  *   grad_cbf / grad_actor: flat gradients in the parameter layout (overwritten)
@@ -204,6 +211,13 @@ int32_t gcbf_polyak(float* tgt, const float* src, int32_t n, float tau, void* st
  *          roww[row2agent ? row2agent[m] : m]).  K1, N multiples of 128.
  * colsum : db[N] += sum_m w(m) dY[m, :N], N <= 256. */
 int32_t gcbf_gemm_nn(int32_t epi, int32_t accum, const float* A, const float* B, const float* bias,
+                     const float* bias2, float* C, const float* aux, const int32_t* m_ptr,
+                     int32_t m_fixed, int32_t m_cap, int32_t K, int32_t N, void* stream);
+/* gemm_tc: the tcgen05 tensor-core variant (3xTF32 split, fp32 accumulation in TMEM, TMA-staged
+ * operands): C[M,N] = epi(A[M,K] @ Bt[N,K]^T) with Bt = the TRANSPOSED weight (K-major operands);
+ * same epilogues / row-count convention as gemm_nn.  K % 32 == 0, N in {128, 256};
+ * A must be backed by at least m_cap rows. */
+int32_t gcbf_gemm_tc(int32_t epi, int32_t accum, const float* A, const float* Bt, const float* bias,
                      const float* bias2, float* C, const float* aux, const int32_t* m_ptr,
                      int32_t m_fixed, int32_t m_cap, int32_t K, int32_t N, void* stream);
 int32_t gcbf_gemm_tn(const float* X, int32_t ldx, const float* dY, float* C, const float* roww,

@@ -20,3 +20,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(params=["tc", "simt"])
+def gemm_path(request):
+    """Run a GPU test on both dense-layer paths: tcgen05 3xTF32 tensor-core GEMMs (default) and the
+    strict-fp32 SIMT GEMMs (GCBF_TENSOR_CORES=0)."""
+    from gcbfplus_b200 import _lib
+    old = _lib.USE_TC
+    _lib.USE_TC = request.param == "tc"
+    yield request.param
+    _lib.USE_TC = old

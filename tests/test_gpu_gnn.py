@@ -10,13 +10,17 @@ from helpers import (ENVS, oracle_env, oracle_obstacles, oracle_params, product_
 
 pytestmark = pytest.mark.gpu
 
-TOL_NET = 1e-5
+# strict-fp32 SIMT path: 1e-5.  tcgen05 3xTF32 path: 3e-5 -- measured 4-8e-6 vs a float64
+# oracle (tensor-core accumulation rounds toward zero over 3*K/8 partial products per output), far
+# inside the 2e-3 SURVEY 8c grants a tensor-core path.
+TOL = {"simt": 1e-5, "tc": 3e-5}
 CASES = [("SingleIntegrator", 8, 3, 2.0, 4), ("DoubleIntegrator", 8, 4, 2.0, 8), ("DoubleIntegrator", 48, 2, 3.0, 8),
          ("DubinsCar", 12, 3, 2.5, 6), ("LinearDrone", 10, 2, 1.5, 4)]
 
 
 @pytest.mark.parametrize("env_id,N,G,area,n_obs", CASES)
-def test_forward_act_step(env_id, N, G, area, n_obs):
+def test_forward_act_step(env_id, N, G, area, n_obs, gemm_path):
+    TOL_NET = TOL[gemm_path]
     from oracle.algo import act, get_cbf
     from oracle.nn import net_forward
     agent, goal, obs = random_scene(env_id, N, G, area, n_obs, seed=2)
@@ -45,7 +49,7 @@ def test_forward_act_step(env_id, N, G, area, n_obs):
             np.testing.assert_allclose(pi[g], net_forward(ap, og, "actor").numpy(), atol=TOL_NET, rtol=0)
             oa = act(oenv, ap, og)
             np.testing.assert_allclose(u_ref[g], oenv.u_ref(og.agent, og.goal).numpy(), atol=2e-6, rtol=3e-6)
-            np.testing.assert_allclose(a[g].cpu().numpy(), oa.numpy(), atol=3e-5, rtol=0)
+            np.testing.assert_allclose(a[g].cpu().numpy(), oa.numpy(), atol=2 * TOL_NET + 1e-5, rtol=0)
             # env.step from the PRODUCT's action (isolates the dynamics from network rounding)
             ag = torch.from_numpy(a[g].cpu().numpy())
             og2, r, c = oenv.step(og, ag)
@@ -57,7 +61,8 @@ def test_forward_act_step(env_id, N, G, area, n_obs):
             np.testing.assert_allclose(h_next[g], get_cbf(cp, ofwd).numpy(), atol=TOL_NET, rtol=0)
 
 
-def test_dense_reference_layout_equals_sparse_on_gpu_inputs():
+def test_dense_reference_layout_equals_sparse_on_gpu_inputs(gemm_path):
+    TOL_NET = TOL[gemm_path]
     """The CUDA path drops masked edges; the oracle's dense (reference) layout must agree."""
     from oracle.algo import get_cbf
     env_id, N, G, area, n_obs = "DoubleIntegrator", 8, 1, 2.0, 8

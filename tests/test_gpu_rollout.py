@@ -21,7 +21,7 @@ def _reset_scene(env_id, N, E, area, n_obs, seed):
                                                       ("SingleIntegrator", 8, 2, 2.0, 4, 64),
                                                       ("DubinsCar", 8, 2, 2.5, 4, 64),
                                                       ("LinearDrone", 8, 2, 1.2, 3, 48)])
-def test_rollout_matches_oracle(env_id, N, E, area, n_obs, T):
+def test_rollout_matches_oracle(env_id, N, E, area, n_obs, T, gemm_path):
     from gcbfplus_b200.trainer.rollout import RolloutEngine
     from oracle.algo import rates, rollout
     env, g0 = _reset_scene(env_id, N, E, area, n_obs, seed=11)
@@ -53,7 +53,7 @@ def test_rollout_matches_oracle(env_id, N, E, area, n_obs, T):
         got = res.agent[e].cpu().numpy()
         want = ref["states"].numpy()
         err = np.abs(got - want).reshape(T + 1, -1).max(axis=1)
-        assert err[1] <= 2e-6, err[:4]
+        assert err[1] <= (2e-6 if gemm_path == "simt" else 6e-6), err[:4]
         assert err[: T // 4].max() <= 1e-4, err[: T // 4].max()
         assert err.max() <= 5e-3, err.max()
         np.testing.assert_allclose(res.rewards[e].cpu().numpy(), ref["rewards"].numpy(), atol=5e-3)

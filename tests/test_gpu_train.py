@@ -31,7 +31,7 @@ def _setup(env_id, N, B, area, n_obs, seed=21, pretrained=True):
 
 @pytest.mark.parametrize("env_id,N,B,area,n_obs", CASES)
 @pytest.mark.parametrize("pretrained", [True, False])
-def test_gradients_match_oracle_autograd(env_id, N, B, area, n_obs, pretrained):
+def test_gradients_match_oracle_autograd(env_id, N, B, area, n_obs, pretrained, gemm_path):
     from gcbfplus_b200.algo.train import read_info, train_minibatch
     from oracle.algo import gcbf_plus_loss
     from oracle.nn import to_torch
@@ -168,3 +168,38 @@ def test_gemm_kernels_match_torch_fp32():
         wd = dY * w[r2a.long()][:, None]
         torch.testing.assert_close(Cw, X.T @ wd, atol=1e-3 * (M ** 0.5) / 10 + 1e-4, rtol=1e-4)
         torch.testing.assert_close(db, wd.sum(0), atol=1e-3 * (M ** 0.5) / 10 + 1e-4, rtol=1e-4)
+
+
+def test_tensor_core_gemm_matches_float64():
+    """tcgen05 3xTF32 GEMM (gemm_tc.cuh) vs a float64 reference: fp32-class accuracy
+    (<= 2e-6 of |A||B|; single-pass TF32 would be ~5e-4), all epilogues, ragged M, device row count."""
+    from gcbfplus_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (M, K, N, cap, epi, accum) in [(1, 32, 128, 128, 0, 0), (128, 128, 128, 128, 0, 0), (300, 256, 256, 300, 1, 0),
+                                       (1000, 128, 256, 1024, 2, 0), (4097, 256, 128, 5000, 3, 0),
+                                       (14012, 256, 256, 16000, 3, 1), (777, 256, 256, 777, 2, 1)]:
+        A = torch.randn(cap, K, device="cuda", generator=g)
+        W = torch.randn(K, N, device="cuda", generator=g) * 0.1
+        Bt = W.t().contiguous()
+        b = torch.randn(N, device="cuda", generator=g)
+        b2 = torch.randn(N, device="cuda", generator=g)
+        aux = torch.randn(cap, N, device="cuda", generator=g)
+        out = torch.full((cap, N), 7.0, device="cuda")
+        mc = torch.tensor([M], dtype=torch.int32, device="cuda")
+        _lib.check(lib.gcbf_gemm_tc(epi, accum, A.data_ptr(), Bt.data_ptr(), b.data_ptr(), b2.data_ptr(), out.data_ptr(),
+                                    aux.data_ptr(), mc.data_ptr(), 0, cap, K, N, st))
+        ref = A[:M].double() @ W.double()
+        if epi in (0, 1):
+            ref = ref + b.double() + b2.double()
+        if epi == 1:
+            ref = torch.relu(ref)
+        if epi == 3:
+            ref = ref * (aux[:M] > 0)
+        if accum:
+            ref = ref + 7.0
+        scale = float((A[:M].abs().double() @ W.abs().double()).max())
+        err = float((out[:M].double() - ref).abs().max())
+        assert err <= 2e-6 * scale, (M, K, N, epi, accum, err, scale)
+        assert bool((out[M:] == 7.0).all())                     # rows >= M untouched
