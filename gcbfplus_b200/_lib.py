@@ -59,6 +59,7 @@ _SIGNATURES = {
     "gcbf_gemm_nn": (C.c_int32, [C.c_int32, C.c_int32] + [_P] * 7 + [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "gcbf_gemm_tc": (C.c_int32, [C.c_int32, C.c_int32] + [_P] * 7 + [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "gcbf_gemm_tn": (C.c_int32, [_P, C.c_int32] + [_P] * 5 + [C.c_int32] * 5 + [_P]),
+    "gcbf_gemm_tn_tc": (C.c_int32, [_P, C.c_int32] + [_P] * 5 + [C.c_int32] * 5 + [_P]),
     "gcbf_colsum": (C.c_int32, [_P] * 5 + [C.c_int32] * 4 + [_P]),
     "gcbf_train_workspace_floats": (C.c_int64, [C.POINTER(EnvDesc)]),
     "gcbf_mask_counts": (C.c_int32, [_P, _P, C.c_int32, _P, _P]),

@@ -219,26 +219,60 @@ gemm_tn_kernel(const float* __restrict__ X, const int ldx, const float* __restri
     (void)K1;
 }
 
-// db[n] += sum_m w(m) dY[m, n]; N <= 256; each CTA takes a strided set of 32-row chunks.
+// db[n] += sum_m w(m) dY[m, n]; N in {128, 256}.  Bandwidth kernel: a CTA of 256 threads reads 8 rows x 128
+// float4-columns (N = 128: 8 rows of 32 float4) per step with 4 loads in flight per thread, block-reduces
+// through shared memory and issues one atomicAdd per column.
 static __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ dY, float* __restrict__ db, const float* __restrict__ roww,
               const int32_t* __restrict__ row2agent, const int32_t* __restrict__ m_ptr, const int m_fixed,
               const int m_cap, const int N, const int n_agents_total) {
+    __shared__ float4 red[256];
     int M = m_ptr ? *m_ptr : m_fixed;
     M = min(M, m_cap);
-    const int n = threadIdx.x;
-    if (n >= N) return;
-    float acc = 0.f;
-    for (int m = blockIdx.x; m < M; m += gridDim.x) {
-        float w = 1.f;
-        if (roww) {
-            int ag = row2agent ? row2agent[m] : m;
-            ag = min(max(ag, 0), n_agents_total - 1);
-            w = roww[ag];
+    const int vec_per_row = N / 4;                    // 32 or 64
+    const int rows_per_step = 256 / vec_per_row;      // 8 or 4
+    const int c4 = threadIdx.x % vec_per_row, r0 = threadIdx.x / vec_per_row;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int stride = gridDim.x * rows_per_step;
+    for (int m = blockIdx.x * rows_per_step + r0; m < M; m += 4 * stride) {
+        float4 v[4];
+        float w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int mm = m + u * stride;
+            if (mm < M) {
+                v[u] = *reinterpret_cast<const float4*>(dY + (size_t)mm * N + c4 * 4);
+                w[u] = 1.f;
+                if (roww) {
+                    int ag = row2agent ? row2agent[mm] : mm;
+                    ag = min(max(ag, 0), n_agents_total - 1);
+                    w[u] = roww[ag];
+                }
+            } else {
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                w[u] = 0.f;
+            }
         }
-        acc = fmaf(w, dY[(size_t)m * N + n], acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            acc.x = fmaf(w[u], v[u].x, acc.x);
+            acc.y = fmaf(w[u], v[u].y, acc.y);
+            acc.z = fmaf(w[u], v[u].z, acc.z);
+            acc.w = fmaf(w[u], v[u].w, acc.w);
+        }
     }
-    atomicAdd(db + n, acc);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (r0 == 0) {
+        for (int r = 1; r < rows_per_step; ++r) {
+            const float4 o = red[r * vec_per_row + c4];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        atomicAdd(db + c4 * 4 + 0, acc.x);
+        atomicAdd(db + c4 * 4 + 1, acc.y);
+        atomicAdd(db + c4 * 4 + 2, acc.z);
+        atomicAdd(db + c4 * 4 + 3, acc.w);
+    }
 }
 
 struct RowCount {
@@ -301,13 +335,13 @@ inline int32_t launch_gemm_tn(const float* X, int ldx, const float* dY, float* C
 
 inline int32_t launch_colsum(const float* dY, float* db, const float* roww, const int32_t* row2agent, RowCount rc,
                              int N, int n_agents_total, cudaStream_t st) {
-    if (N > 256) {
-        set_error("colsum: N=%d > 256", N);
+    if (N != 128 && N != 256) {
+        set_error("colsum: N=%d unsupported (128 or 256)", N);
         return -1;
     }
     const int rows = rc.ptr ? rc.cap : min(rc.fixed, rc.cap);
     if (rows <= 0) return 0;
-    const int grid = min(max(1, rows / 64), 2 * sm_count());
+    const int grid = min(max(1, rows / 128), 4 * sm_count());
     colsum_kernel<<<grid, 256, 0, st>>>(dY, db, roww, row2agent, rc.ptr, rc.fixed, rc.cap, N, n_agents_total);
     count_launch();
     return check_launch("colsum_kernel");

@@ -374,5 +374,233 @@ inline int32_t launch_gemm_tc(int epi, bool accum, const float* A, const float* 
     return launch_bn<128>(epi, accum, tmA, tmB, bias, bias2, C, aux, rc, K, N, grid, st);
 }
 
+
+// =====================================================================================================
+// backward-weight on tensor cores:  C[K1, N] += sum_m w(m) X[m, k1] dY[m, n]
+// D[M_mma = 128 k1-rows, N_mma = N] += A B^T with A = X^T and B = dY^T, both "MN-major" (the MMA-K index is
+// the row index m of X / dY).  TMA boxes of [32 rows(m) x 32 floats] with SWIZZLE_128B land exactly in the
+// MN-major tf32 swizzle atoms.  For MN-major 32-bit operands the only legal shared-memory layout is
+// SWIZZLE_128B_BASE32B (CUTLASS sm100_common.inl:92; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of
+// 4 m-rows x 128 B with the 32-byte chunks XOR-ed by (row % 4); atoms along MN at LBO = 4096 B (one box),
+// along K at SBO = 512 B.
+// Split over M: CTA (tile, split) walks 32-row chunks {split, split + S, ...}; result red.add'ed to C.
+// =====================================================================================================
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           (1ull << 46) | (1ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
+    return make_idesc(M, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
+}
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                  float* __restrict__ C, const float* __restrict__ roww, const int32_t* __restrict__ row2agent,
+                  const int32_t* __restrict__ m_ptr, const int m_fixed, const int m_cap, const int N, const int splits,
+                  const int n_agents_total) {
+    constexpr int STAGES = (BN == 256) ? 2 : 3;
+    constexpr int A_BYTES = 128 * 32 * 4;            // 4 boxes of [32 m x 32 k1]
+    constexpr int B_BYTES = BN * 32 * 4;             // BN/32 boxes of [32 m x 32 n]
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* conv = bars + STAGES;
+    uint64_t* empty = bars + 2 * STAGES;
+    uint64_t* tmem_full = bars + 3 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int M = m_ptr ? *m_ptr : m_fixed;
+    M = min(M, m_cap);
+    const int tile = blockIdx.x / splits, split = blockIdx.x % splits;
+    const int k1_0 = tile * 128;
+    const int n_chunks = (M + 31) / 32;
+    const int n_my = (split < n_chunks) ? (n_chunks - split + splits - 1) / splits : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&conv[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < n_my; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int m0 = (split + it * splits) * 32;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * STAGE_BYTES;
+                mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tma_load_2d(st + i * 4096, &tmX, &full[s], k1_0 + 32 * i, m0);
+#pragma unroll
+                for (int j = 0; j < BN / 32; ++j) tma_load_2d(st + 2 * A_BYTES + j * 4096, &tmY, &full[s], 32 * j, m0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_mn(128, BN);
+            for (int it = 0; it < n_my; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&conv[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_BYTES;
+                const uint32_t b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t koff = k * 1024;      // 8 m-rows
+                    const uint64_t dah = make_desc_mn(a_hi + koff), dal = make_desc_mn(a_lo + koff);
+                    const uint64_t dbh = make_desc_mn(b_hi + koff), dbl = make_desc_mn(b_lo + koff);
+                    umma_tf32(tmem_base, dal, dbh, idesc, (it | k) != 0);
+                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                    umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+            }
+            if (n_my > 0) umma_commit(tmem_full);
+        }
+    } else {
+        const int et = threadIdx.x - 64;
+        const int quarter = warp & 3;
+        auto rn = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); };
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            const int m0 = (split + it * splits) * 32;
+            // float4 index i covers smem bytes [16 i, 16 i + 16): box row = (i % 256) / 8; this thread sees 2 rows
+            float wrow[2], vrow[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = m0 + ((et + 128 * h) % 256) / 8;
+                vrow[h] = (m < M) ? 1.f : 0.f;
+                float w = 1.f;
+                if (roww && m < M) {
+                    int ag = row2agent ? row2agent[m] : m;
+                    ag = min(max(ag, 0), n_agents_total - 1);
+                    w = roww[ag];
+                }
+                wrow[h] = w * vrow[h];
+            }
+            mbar_wait(&full[s], ph);
+            uint8_t* st = smem + s * STAGE_BYTES;
+            auto split_op = [&](uint8_t* hi_p, uint8_t* lo_p, int n_vec, const float* scale) {
+                float4* h4 = reinterpret_cast<float4*>(hi_p);
+                float4* l4 = reinterpret_cast<float4*>(lo_p);
+#pragma unroll 4
+                for (int i = et, j = 0; i < n_vec; i += 128, ++j) {
+                    float4 v = h4[i];
+                    const float sc = scale[j & 1];
+                    // rows >= M hold stale data (possibly NaN): select, do not multiply
+                    v.x = sc != 0.f ? v.x * sc : 0.f; v.y = sc != 0.f ? v.y * sc : 0.f;
+                    v.z = sc != 0.f ? v.z * sc : 0.f; v.w = sc != 0.f ? v.w * sc : 0.f;
+                    float4 h, l;
+                    h.x = rn(v.x); h.y = rn(v.y); h.z = rn(v.z); h.w = rn(v.w);
+                    l.x = rn(v.x - h.x); l.y = rn(v.y - h.y); l.z = rn(v.z - h.z); l.w = rn(v.w - h.w);
+                    h4[i] = h;
+                    l4[i] = l;
+                }
+            };
+            split_op(st, st + A_BYTES, A_BYTES / 16, vrow);
+            split_op(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, B_BYTES / 16, wrow);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&conv[s]);
+        }
+        if (n_my > 0) {
+            mbar_wait(tmem_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = quarter * 32 + lane;
+            float* crow = C + (size_t)(k1_0 + row) * N;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(crow + c0 + j, __uint_as_float(v[j]));
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+inline int32_t make_map_box(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows, int box_cols,
+                            CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled unavailable");
+        return -2;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+        return -2;
+    }
+    return 0;
+}
+
+// C[K1, N] += sum_m w(m) X[m, :K1] dY[m, :N]; X row stride ldx (>= K1, multiple of 4), K1 % 128 == 0, N in {128, 256}.
+inline int32_t launch_gemm_tn_tc(const float* X, int ldx, const float* dY, float* C, const float* roww,
+                                 const int32_t* row2agent, RowCount rc, int K1, int N, int n_agents_total,
+                                 cudaStream_t st) {
+    if (K1 % 128 != 0 || (N != 128 && N != 256) || ldx % 4 != 0) {
+        set_error("gemm_tn_tc: K1=%d N=%d ldx=%d unsupported", K1, N, ldx);
+        return -1;
+    }
+    const int rows = rc.ptr ? rc.cap : min(rc.fixed, rc.cap);
+    if (rows <= 0) return 0;
+    CUtensorMap tmX, tmY;
+    if (int32_t r = make_map_box(&tmX, X, rc.cap, K1, ldx, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return r;
+    if (int32_t r = make_map_box(&tmY, dY, rc.cap, N, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return r;
+    const int tiles = K1 / 128;
+    const int chunks = (rows + 31) / 32;
+    int splits = max(1, sm_count() / tiles);
+    splits = min(splits, max(1, chunks / 4));       // >= 128 rows per CTA
+    const int grid = tiles * splits;
+    const int smem = ((N == 256) ? 2 : 3) * (2 * 128 * 32 * 4 + 2 * N * 32 * 4) + 1024 + 256;
+    if (N == 256) {
+        static bool done = false;
+        if (!done) { cudaFuncSetAttribute(gemm_tn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); done = true; }
+        gemm_tn_tc_kernel<256><<<grid, THREADS, smem, st>>>(tmX, tmY, C, roww, row2agent, rc.ptr, rc.fixed, rc.cap, N, splits,
+                                                            n_agents_total);
+    } else {
+        static bool done = false;
+        if (!done) { cudaFuncSetAttribute(gemm_tn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); done = true; }
+        gemm_tn_tc_kernel<128><<<grid, THREADS, smem, st>>>(tmX, tmY, C, roww, row2agent, rc.ptr, rc.fixed, rc.cap, N, splits,
+                                                            n_agents_total);
+    }
+    count_launch();
+    return check_launch("gemm_tn_tc_kernel");
+}
+
 }  // namespace tc
 }  // namespace gcbf

@@ -163,3 +163,15 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_prepare_params(in
     const ParamLayout L = make_layout(edge_dim, out_dim);
     return build_transposes(L, make_trans_layout(L), params, params_t, (cudaStream_t)stream);
 }
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_gemm_tn_tc(const float* X, int32_t ldx, const float* dY,
+                                                                          float* C, const float* roww,
+                                                                          const int32_t* row2agent,
+                                                                          const int32_t* m_ptr, int32_t m_fixed,
+                                                                          int32_t m_cap, int32_t K1, int32_t N,
+                                                                          int32_t n_agents_total, void* stream) {
+    GCBF_REQUIRE(X && dY && C, "gcbf_gemm_tn_tc: NULL pointer");
+    GCBF_REQUIRE((((uintptr_t)X | (uintptr_t)dY) & 15) == 0, "gcbf_gemm_tn_tc: 16-byte alignment required");
+    return gcbf::tc::launch_gemm_tn_tc(X, ldx, dY, C, roww, row2agent, RowCount{m_ptr, m_fixed, m_cap}, K1, N,
+                                       n_agents_total, (cudaStream_t)stream);
+}

@@ -505,6 +505,13 @@ struct BwdArgs {
     int use_tc;            // 1: backward-data GEMMs on the tcgen05 path
 };
 
+// dW += X^T (w dY): tensor-core (MN-major 3xTF32) or SIMT split-M kernel.
+static int32_t dense_bwd_weight(const BwdArgs& b, const float* X, int ldx, const float* dY, float* C,
+                                const int32_t* row2agent, RowCount rc, int K1, int N, int A, cudaStream_t st) {
+    if (b.use_tc) return tc::launch_gemm_tn_tc(X, ldx, dY, C, b.roww, row2agent, rc, K1, N, A, st);
+    return launch_gemm_tn(X, ldx, dY, C, b.roww, row2agent, rc, K1, N, A, st);
+}
+
 // dX = epi(dY @ W_i^T) (+= if accum).  SIMT: B = W^T from PT; tensor core: Bt = W itself (K-major).
 static int32_t dense_bwd_data(const BwdArgs& b, const ParamLayout& L, const TransLayout& TL, int li, int epi, bool accum,
                               const float* dY, float* dX, const float* aux, RowCount rc, cudaStream_t st) {
@@ -539,20 +546,20 @@ static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
         RC(check_launch("head_out_bwd_kernel"));
     }
     // ---- head MLP
-    RC(launch_gemm_tn(fw + W.h1, 256, gw + W.h2, b.G + L.w[L_HEAD1], b.roww, nullptr, ra, 256, 256, A, st));
+    RC(dense_bwd_weight(b, fw + W.h1, 256, gw + W.h2, b.G + L.w[L_HEAD1], nullptr, ra, 256, 256, A, st));
     RC(launch_colsum(gw + W.h2, b.G + L.b[L_HEAD1], b.roww, nullptr, ra, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_HEAD1, EPI_RELU_MASK, false, gw + W.h2, gw + W.h1, fw + W.h1, ra, st));
-    RC(launch_gemm_tn(fw + W.v3, 128, gw + W.h1, b.G + L.w[L_HEAD0], b.roww, nullptr, ra, 128, 256, A, st));
+    RC(dense_bwd_weight(b, fw + W.v3, 128, gw + W.h1, b.G + L.w[L_HEAD0], nullptr, ra, 128, 256, A, st));
     RC(launch_colsum(gw + W.h1, b.G + L.b[L_HEAD0], b.roww, nullptr, ra, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_HEAD0, EPI_NONE, false, gw + W.h1, gw + W.v3, nullptr, ra, st));
     // ---- update MLP
-    RC(launch_gemm_tn(fw + W.v2, 256, gw + W.v3, b.G + L.w[L_UPDOUT], b.roww, nullptr, ra, 256, 128, A, st));
+    RC(dense_bwd_weight(b, fw + W.v2, 256, gw + W.v3, b.G + L.w[L_UPDOUT], nullptr, ra, 256, 128, A, st));
     RC(launch_colsum(gw + W.v3, b.G + L.b[L_UPDOUT], b.roww, nullptr, ra, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_UPDOUT, EPI_NONE, false, gw + W.v3, gw + W.v2, nullptr, ra, st));
-    RC(launch_gemm_tn(fw + W.v1, 256, gw + W.v2, b.G + L.w[L_UPD1], b.roww, nullptr, ra, 256, 256, A, st));
+    RC(dense_bwd_weight(b, fw + W.v1, 256, gw + W.v2, b.G + L.w[L_UPD1], nullptr, ra, 256, 256, A, st));
     RC(launch_colsum(gw + W.v2, b.G + L.b[L_UPD1], b.roww, nullptr, ra, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_UPD1, EPI_RELU_MASK, false, gw + W.v2, gw + W.v1, fw + W.v1, ra, st));
-    RC(launch_gemm_tn(fw + W.ag, 128, gw + W.v1, b.G + L.w[L_UPD0] + 3 * 256, b.roww, nullptr, ra, 128, 256, A, st));
+    RC(dense_bwd_weight(b, fw + W.ag, 128, gw + W.v1, b.G + L.w[L_UPD0] + 3 * 256, nullptr, ra, 128, 256, A, st));
     RC(launch_colsum(gw + W.v1, b.G + L.b[L_UPD0], b.roww, nullptr, ra, 256, A, st));
     RC(launch_colsum(gw + W.v1, b.G + L.w[L_UPD0] + 2 * 256, b.roww, nullptr, ra, 256, A, st));  // agent one-hot row
     RC(dense_bwd_data(b, L, TL, L_UPD0, EPI_NONE, false, gw + W.v1, gw + W.ag, nullptr, ra, st));
@@ -566,17 +573,17 @@ static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
         RC(check_launch("attn_aggregate_bwd_kernel"));
     }
     // ---- gate MLP (edge rows; dW weighted by the receiver's weight)
-    RC(launch_gemm_tn(fw + W.g1, 128, gw + W.g2, b.G + L.w[L_ATT1], b.roww, b.edge_recv, re, 128, 128, A, st));
+    RC(dense_bwd_weight(b, fw + W.g1, 128, gw + W.g2, b.G + L.w[L_ATT1], b.edge_recv, re, 128, 128, A, st));
     RC(launch_colsum(gw + W.g2, b.G + L.b[L_ATT1], b.roww, b.edge_recv, re, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_ATT1, EPI_RELU_MASK, false, gw + W.g2, gw + W.g1, fw + W.g1, re, st));
-    RC(launch_gemm_tn(fw + W.msg, 128, gw + W.g1, b.G + L.w[L_ATT0], b.roww, b.edge_recv, re, 128, 128, A, st));
+    RC(dense_bwd_weight(b, fw + W.msg, 128, gw + W.g1, b.G + L.w[L_ATT0], b.edge_recv, re, 128, 128, A, st));
     RC(launch_colsum(gw + W.g1, b.G + L.b[L_ATT0], b.roww, b.edge_recv, re, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_ATT0, EPI_NONE, true, gw + W.g1, gw + W.msg, nullptr, re, st));
     // ---- message MLP
-    RC(launch_gemm_tn(fw + W.x2, 256, gw + W.msg, b.G + L.w[L_MSGOUT], b.roww, b.edge_recv, re, 256, 128, A, st));
+    RC(dense_bwd_weight(b, fw + W.x2, 256, gw + W.msg, b.G + L.w[L_MSGOUT], b.edge_recv, re, 256, 128, A, st));
     RC(launch_colsum(gw + W.msg, b.G + L.b[L_MSGOUT], b.roww, b.edge_recv, re, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_MSGOUT, EPI_NONE, false, gw + W.msg, gw + W.x2, nullptr, re, st));
-    RC(launch_gemm_tn(fw + W.x1, 256, gw + W.x2, b.G + L.w[L_MSG1], b.roww, b.edge_recv, re, 256, 256, A, st));
+    RC(dense_bwd_weight(b, fw + W.x1, 256, gw + W.x2, b.G + L.w[L_MSG1], b.edge_recv, re, 256, 256, A, st));
     RC(launch_colsum(gw + W.x2, b.G + L.b[L_MSG1], b.roww, b.edge_recv, re, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_MSG1, EPI_RELU_MASK, false, gw + W.x2, gw + W.x1, fw + W.x1, re, st));
     // ---- edge layer 1

@@ -209,7 +209,7 @@ int32_t gcbf_polyak(float* tgt, const float* src, int32_t n, float tau, void* st
  *          M = *m_ptr (device) if m_ptr else m_fixed, clamped to m_cap.  K % 16 == 0, N % 128 == 0.
  * gemm_tn: C[K1,N] += sum_m w(m) X[m, :K1] dY[m, :N]  (ldx = row stride of X; w optional:
  *          roww[row2agent ? row2agent[m] : m]).  K1, N multiples of 128.
- * colsum : db[N] += sum_m w(m) dY[m, :N], N <= 256. */
+ * colsum : db[N] += sum_m w(m) dY[m, :N], N in {128, 256}. */
 int32_t gcbf_gemm_nn(int32_t epi, int32_t accum, const float* A, const float* B, const float* bias,
                      const float* bias2, float* C, const float* aux, const int32_t* m_ptr,
                      int32_t m_fixed, int32_t m_cap, int32_t K, int32_t N, void* stream);
@@ -223,6 +223,10 @@ int32_t gcbf_gemm_tc(int32_t epi, int32_t accum, const float* A, const float* Bt
 int32_t gcbf_gemm_tn(const float* X, int32_t ldx, const float* dY, float* C, const float* roww,
                      const int32_t* row2agent, const int32_t* m_ptr, int32_t m_fixed, int32_t m_cap,
                      int32_t K1, int32_t N, int32_t n_agents_total, void* stream);
+/* gemm_tn_tc: tcgen05 variant of gemm_tn (MN-major operands, 3xTF32 split, split-M + red.add). */
+int32_t gcbf_gemm_tn_tc(const float* X, int32_t ldx, const float* dY, float* C, const float* roww,
+                        const int32_t* row2agent, const int32_t* m_ptr, int32_t m_fixed, int32_t m_cap,
+                        int32_t K1, int32_t N, int32_t n_agents_total, void* stream);
 int32_t gcbf_colsum(const float* dY, float* db, const float* roww, const int32_t* row2agent,
                     const int32_t* m_ptr, int32_t m_fixed, int32_t m_cap, int32_t N,
                     int32_t n_agents_total, void* stream);
