@@ -57,7 +57,8 @@ _SIGNATURES = {
     "gcbf_masks": (C.c_int32, [C.POINTER(EnvDesc)] + [_P] * 9),
     "gcbf_safe_horizon": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "gcbf_gemm_nn": (C.c_int32, [C.c_int32, C.c_int32] + [_P] * 7 + [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
-    "gcbf_gemm_tc": (C.c_int32, [C.c_int32, C.c_int32] + [_P] * 7 + [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "gcbf_gemm_tc": (C.c_int32, [C.c_int32, C.c_int32] + [_P] * 8 + [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "gcbf_split_tf32": (C.c_int32, [_P, _P, _P, C.c_int32, _P]),
     "gcbf_gemm_tn": (C.c_int32, [_P, C.c_int32] + [_P] * 5 + [C.c_int32] * 5 + [_P]),
     "gcbf_gemm_tn_tc": (C.c_int32, [_P, C.c_int32] + [_P] * 5 + [C.c_int32] * 5 + [_P]),
     "gcbf_colsum": (C.c_int32, [_P] * 5 + [C.c_int32] * 4 + [_P]),

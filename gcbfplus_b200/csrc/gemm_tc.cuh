@@ -96,6 +96,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+constexpr int THREADS_NN = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 operand split (A), warps 6-9 epilogue
+
 template <int BN>
 struct Cfg {
     static constexpr int STAGES = (BN == 256) ? 2 : 3;
@@ -105,30 +107,42 @@ struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// hi = tf32(x) rounded to nearest (13 low mantissa bits cleared, so the tensor core's own fp32->tf32
+// conversion is exact), lo = tf32(x - hi): |x - hi - lo| <= 2^-24 |x|.
+__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+// Weights are split once per parameter update (gcbf_prepare_params); activations are split in shared memory.
+static __global__ void split_tf32_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float x = in[i];
+        const float h = rn_tf32(x);
+        hi[i] = h;
+        lo[i] = rn_tf32(x - h);
+    }
+}
+
 template <int BN, int EPI, bool ACCUM>
-__global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const float* __restrict__ bias, const float* __restrict__ bias2, float* __restrict__ C,
-               const float* __restrict__ aux, const int32_t* __restrict__ m_ptr, const int m_fixed, const int m_cap,
-               const int K, const int N) {
+__global__ void __launch_bounds__(THREADS_NN, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+               const __grid_constant__ CUtensorMap tmBl, const float* __restrict__ bias,
+               const float* __restrict__ bias2, float* __restrict__ C, const float* __restrict__ aux,
+               const int32_t* __restrict__ m_ptr, const int m_fixed, const int m_cap, const int K, const int N) {
     using CF = Cfg<BN>;
     constexpr int STAGES = CF::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * CF::STAGE_BYTES);
-    uint64_t* full = bars;                 // [STAGES] TMA bytes landed
-    uint64_t* conv = bars + STAGES;        // [STAGES] hi/lo split done (128 arrivals)
-    uint64_t* empty = bars + 2 * STAGES;   // [STAGES] MMAs of the stage retired
-    uint64_t* tmem_full = bars + 3 * STAGES;
-    uint64_t* tmem_empty = bars + 3 * STAGES + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
+    uint64_t* full = bars;                     // [STAGES] TMA bytes landed
+    uint64_t* conv = bars + STAGES;            // [STAGES] A hi/lo split done (128 arrivals)
+    uint64_t* empty = bars + 2 * STAGES;       // [STAGES] MMAs of the stage retired
+    uint64_t* tmem_full = bars + 3 * STAGES;   // [2] accumulator ready for the epilogue
+    uint64_t* tmem_empty = bars + 3 * STAGES + 2;   // [2] accumulator drained (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int M = m_ptr ? *m_ptr : m_fixed;
     M = min(M, m_cap);
-    const int tiles_n = N / BN;
-    const int tiles_m = (M + BM - 1) / BM;
-    const int n_tiles = tiles_m * tiles_n;
+    const int n_tiles = (M + BM - 1) / BM;     // BN == N: one tile column
     const int nkb = K / BK;
 
     if (threadIdx.x == 0) {
@@ -137,13 +151,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&conv[s], 128);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 128);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)BN)
+                     "r"((uint32_t)(2 * BN))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -157,15 +173,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                const int m0 = tile * BM;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * CF::STAGE_BYTES;
-                    mbar_expect_tx(&full[s], CF::A_BYTES + CF::B_BYTES);
+                    mbar_expect_tx(&full[s], CF::A_BYTES + 2 * CF::B_BYTES);
                     tma_load_2d(st, &tmA, &full[s], kb * BK, m0);
-                    tma_load_2d(st + 2 * CF::A_BYTES, &tmB, &full[s], kb * BK, n0);
+                    tma_load_2d(st + 2 * CF::A_BYTES, &tmBh, &full[s], kb * BK, 0);
+                    tma_load_2d(st + 2 * CF::A_BYTES + CF::B_BYTES, &tmBl, &full[s], kb * BK, 0);
                 }
             }
         }
@@ -175,7 +192,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr uint32_t idesc = make_idesc(BM, BN);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-                mbar_wait(tmem_empty, (tcount & 1) ^ 1);
+                const uint32_t acc = tcount & 1;
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -191,58 +210,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t koff = k * UMMA_K * 4;  // bytes inside the 128-byte swizzle row
                         const uint64_t dah = make_desc(a_hi + koff), dal = make_desc(a_lo + koff);
                         const uint64_t dbh = make_desc(b_hi + koff), dbl = make_desc(b_lo + koff);
-                        umma_tf32(tmem_base, dal, dbh, idesc, (kb | k) != 0);   // small terms first
-                        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-                        umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+                        umma_tf32(tmem_d, dal, dbh, idesc, (kb | k) != 0);   // small terms first
+                        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
                     }
                     umma_commit(&empty[s]);
                 }
-                umma_commit(tmem_full);
+                umma_commit(&tmem_full[acc]);
             }
         }
-    } else {
-        // ================= operand split + epilogue (warps 2..5, 128 threads) =================
+    } else if (warp < 6) {
+        // ================= A-operand split (warps 2..5, 128 threads) =================
         const int et = threadIdx.x - 64;          // 0..127
-        const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-        uint32_t it = 0, tcount = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&full[s], ph);
-                uint8_t* st = smem + s * CF::STAGE_BYTES;
-                // x -> hi = tf32(x) rounded to nearest (13 low mantissa bits cleared, so the tensor core's own
-                // fp32->tf32 conversion is exact), lo = tf32(x - hi) rounded to nearest: |x - hi - lo| <= 2^-24 |x|
-                auto rn = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); };
-                auto split = [&](uint8_t* hi_p, uint8_t* lo_p, int n_vec) {
-                    float4* h4 = reinterpret_cast<float4*>(hi_p);
-                    float4* l4 = reinterpret_cast<float4*>(lo_p);
-                    for (int i = et; i < n_vec; i += 128) {
-                        const float4 v = h4[i];
-                        float4 h, l;
-                        h.x = rn(v.x); h.y = rn(v.y); h.z = rn(v.z); h.w = rn(v.w);
-                        l.x = rn(v.x - h.x); l.y = rn(v.y - h.y); l.z = rn(v.z - h.z); l.w = rn(v.w - h.w);
-                        h4[i] = h;
-                        l4[i] = l;
-                    }
-                };
-                split(st, st + CF::A_BYTES, CF::A_BYTES / 16);
-                split(st + 2 * CF::A_BYTES, st + 2 * CF::A_BYTES + CF::B_BYTES, CF::B_BYTES / 16);
+                float4* h4 = reinterpret_cast<float4*>(smem + s * CF::STAGE_BYTES);
+                float4* l4 = reinterpret_cast<float4*>(smem + s * CF::STAGE_BYTES + CF::A_BYTES);
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = h4[et + 128 * j];       // A tile = 1024 float4
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 h, l;
+                    h.x = rn_tf32(v[j].x); h.y = rn_tf32(v[j].y); h.z = rn_tf32(v[j].z); h.w = rn_tf32(v[j].w);
+                    l.x = rn_tf32(v[j].x - h.x); l.y = rn_tf32(v[j].y - h.y);
+                    l.z = rn_tf32(v[j].z - h.z); l.w = rn_tf32(v[j].w - h.w);
+                    h4[et + 128 * j] = h;
+                    l4[et + 128 * j] = l;
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&conv[s]);
             }
-            // ---- epilogue
-            mbar_wait(tmem_full, tcount & 1);
+        }
+    } else {
+        // ================= epilogue (warps 6..9): TMEM -> registers -> global =================
+        const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const int m0 = tile * BM;
+            const uint32_t acc = tcount & 1;
+            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = quarter * 32 + lane;
             const int m = m0 + row;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld32(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
                 if (m < M) {
-                    const int n = n0 + c0;
+                    const int n = c0;
                     float* crow = C + (size_t)m * N + n;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -273,12 +293,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(tmem_empty);
+            mbar_arrive(&tmem_empty[acc]);
         }
     }
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
+                     : "memory");
     }
 }
 
@@ -321,7 +342,8 @@ inline int32_t make_map(CUtensorMap* map, const float* ptr, int rows, int cols, 
 }
 
 template <int BN>
-inline int32_t launch_bn(int epi, bool accum, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
+inline int32_t launch_bn(int epi, bool accum, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBl,
+                         const float* bias,
                          const float* bias2, float* C, const float* aux, RowCount rc, int K, int N, int grid,
                          cudaStream_t st) {
     constexpr int smem = Cfg<BN>::SMEM_BYTES;
@@ -333,7 +355,7 @@ inline int32_t launch_bn(int epi, bool accum, const CUtensorMap& tmA, const CUte
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                        \
             attr_done = true;                                                                                     \
         }                                                                                                         \
-        kern<<<grid, THREADS, smem, st>>>(tmA, tmB, bias, bias2, C, aux, rc.ptr, rc.fixed, rc.cap, K, N);         \
+        kern<<<grid, THREADS_NN, smem, st>>>(tmA, tmB, tmBl, bias, bias2, C, aux, rc.ptr, rc.fixed, rc.cap, K, N); \
     } while (0)
     if (!accum) {
         switch (epi) {
@@ -355,23 +377,25 @@ inline int32_t launch_bn(int epi, bool accum, const CUtensorMap& tmA, const CUte
     return check_launch("gemm_tc_kernel");
 }
 
-// C[M,N] = epi(A[M,K] @ Bt[N,K]^T).  A must be backed by at least rc.cap rows.
-inline int32_t launch_gemm_tc(int epi, bool accum, const float* A, const float* Bt, const float* bias,
-                              const float* bias2, float* C, const float* aux, RowCount rc, int K, int N,
-                              cudaStream_t st) {
+// C[M,N] = epi(A[M,K] @ Bt[N,K]^T) with Bt given as its tf32 split (Bt_hi + Bt_lo, split_tf32_kernel).
+// A must be backed by at least rc.cap rows.
+inline int32_t launch_gemm_tc(int epi, bool accum, const float* A, const float* Bt_hi, const float* Bt_lo,
+                              const float* bias, const float* bias2, float* C, const float* aux, RowCount rc, int K,
+                              int N, cudaStream_t st) {
     if (K % BK != 0 || (N != 128 && N != 256)) {
         set_error("gemm_tc: K=%d N=%d unsupported", K, N);
         return -1;
     }
     const int rows = rc.ptr ? rc.cap : min(rc.fixed, rc.cap);
     if (rows <= 0) return 0;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmBl;
     if (int32_t r = make_map(&tmA, A, rc.cap, K, BM)) return r;
-    if (int32_t r = make_map(&tmB, Bt, N, K, N)) return r;
+    if (int32_t r = make_map(&tmB, Bt_hi, N, K, N)) return r;
+    if (int32_t r = make_map(&tmBl, Bt_lo, N, K, N)) return r;
     const int tiles = (rows + BM - 1) / BM;
     const int grid = min(tiles, sm_count());
-    if (N == 256) return launch_bn<256>(epi, accum, tmA, tmB, bias, bias2, C, aux, rc, K, N, grid, st);
-    return launch_bn<128>(epi, accum, tmA, tmB, bias, bias2, C, aux, rc, K, N, grid, st);
+    if (N == 256) return launch_bn<256>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st);
+    return launch_bn<128>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st);
 }
 
 
@@ -483,7 +507,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     } else {
         const int et = threadIdx.x - 64;
         const int quarter = warp & 3;
-        auto rn = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); };
+        auto rn = [](float x) { return rn_tf32(x); };
         for (int it = 0; it < n_my; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;

@@ -14,8 +14,11 @@ static int32_t dense_fwd(int epi, const ParamLayout& L, const TransLayout& TL, i
                          const float* X, float* Y, const float* bias2, RowCount rc, cudaStream_t st) {
     const int row_off = (li == L_UPD0) ? 3 * 256 : 0;   // update/Dense_0: rows 3..130 multiply the aggregated message
     const int K = (li == L_UPD0) ? 128 : L.in[li];
-    if (PT)
-        return tc::launch_gemm_tc(epi, false, X, PT + TL.w[li], P + L.b[li], bias2, Y, nullptr, rc, K, L.out[li], st);
+    if (PT) {   // PT = prepared parameters (PreparedLayout): tf32-split transposed weights
+        const PreparedLayout Q = make_prepared_layout(L, TL);
+        return tc::launch_gemm_tc(epi, false, X, PT + Q.pt_hi + TL.w[li], PT + Q.pt_lo + TL.w[li], P + L.b[li], bias2, Y,
+                                  nullptr, rc, K, L.out[li], st);
+    }
     return launch_gemm_nn(epi, false, X, P + L.w[li] + row_off, P + L.b[li], bias2, Y, nullptr, rc, K, L.out[li], st);
 }
 
@@ -137,31 +140,58 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_colsum(const floa
 
 // ---- tensor-core (tcgen05 3xTF32) variant of gcbf_gemm_nn: C = epi(A[M,K] @ Bt[N,K]^T) ----
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_gemm_tc(int32_t epi, int32_t accum, const float* A,
-                                                                       const float* Bt, const float* bias,
+                                                                       const float* Bt_hi, const float* Bt_lo,
+                                                                       const float* bias,
                                                                        const float* bias2, float* C, const float* aux,
                                                                        const int32_t* m_ptr, int32_t m_fixed,
                                                                        int32_t m_cap, int32_t K, int32_t N,
                                                                        void* stream) {
-    GCBF_REQUIRE(A && Bt && C, "gcbf_gemm_tc: NULL pointer");
+    GCBF_REQUIRE(A && Bt_hi && Bt_lo && C, "gcbf_gemm_tc: NULL pointer");
     GCBF_REQUIRE((epi != EPI_BIAS && epi != EPI_BIAS_RELU) || bias, "gcbf_gemm_tc: bias required");
     GCBF_REQUIRE(epi != EPI_RELU_MASK || aux, "gcbf_gemm_tc: aux required");
-    GCBF_REQUIRE((((uintptr_t)A | (uintptr_t)Bt | (uintptr_t)C) & 15) == 0, "gcbf_gemm_tc: 16-byte alignment required");
-    return gcbf::tc::launch_gemm_tc(epi, accum != 0, A, Bt, bias, bias2, C, aux, RowCount{m_ptr, m_fixed, m_cap}, K, N,
-                                    (cudaStream_t)stream);
+    GCBF_REQUIRE((((uintptr_t)A | (uintptr_t)Bt_hi | (uintptr_t)Bt_lo | (uintptr_t)C) & 15) == 0,
+                 "gcbf_gemm_tc: 16-byte alignment required");
+    return gcbf::tc::launch_gemm_tc(epi, accum != 0, A, Bt_hi, Bt_lo, bias, bias2, C, aux,
+                                    RowCount{m_ptr, m_fixed, m_cap}, K, N, (cudaStream_t)stream);
 }
 
 // Transposed GEMM weights of one network (the K-major B operands of the tensor-core path).
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_params_t_count(int32_t edge_dim, int32_t out_dim) {
     if (edge_dim < 1 || edge_dim > 6 || out_dim < 1 || out_dim > 4) return -1;
-    return make_trans_layout(make_layout(edge_dim, out_dim)).total;
+    const ParamLayout L = make_layout(edge_dim, out_dim);
+    return make_prepared_layout(L, make_trans_layout(L)).total;
+}
+
+namespace gcbf {
+// Builds the prepared-parameter blob (PreparedLayout) of one network.
+int32_t build_prepared(const ParamLayout& L, const float* P, float* out, cudaStream_t st) {
+    const TransLayout TL = make_trans_layout(L);
+    const PreparedLayout Q = make_prepared_layout(L, TL);
+    if (int32_t rc = build_transposes(L, TL, P, out + Q.pt_hi, st)) return rc;
+    const int nsm = sm_count();
+    tc::split_tf32_kernel<<<min((TL.total + 255) / 256, 4 * nsm), 256, 0, st>>>(out + Q.pt_hi, out + Q.pt_hi, out + Q.pt_lo,
+                                                                               TL.total);
+    count_launch();
+    if (int32_t rc = check_launch("split_tf32_kernel")) return rc;
+    tc::split_tf32_kernel<<<min((L.total + 255) / 256, 4 * nsm), 256, 0, st>>>(P, out + Q.p_hi, out + Q.p_lo, L.total);
+    count_launch();
+    return check_launch("split_tf32_kernel");
+}
+}  // namespace gcbf
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_split_tf32(const float* in, float* hi, float* lo, int32_t n,
+                                                                          void* stream) {
+    GCBF_REQUIRE(in && hi && lo && n > 0, "gcbf_split_tf32: bad argument");
+    gcbf::tc::split_tf32_kernel<<<min((n + 255) / 256, 4 * sm_count()), 256, 0, (cudaStream_t)stream>>>(in, hi, lo, n);
+    count_launch();
+    return check_launch("split_tf32_kernel");
 }
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_prepare_params(int32_t edge_dim, int32_t out_dim,
                                                                               const float* params, float* params_t,
                                                                               void* stream) {
     GCBF_REQUIRE(edge_dim >= 1 && edge_dim <= 6 && out_dim >= 1 && out_dim <= 4 && params && params_t,
                  "gcbf_prepare_params: bad argument");
-    const ParamLayout L = make_layout(edge_dim, out_dim);
-    return build_transposes(L, make_trans_layout(L), params, params_t, (cudaStream_t)stream);
+    return build_prepared(make_layout(edge_dim, out_dim), params, params_t, (cudaStream_t)stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_gemm_tn_tc(const float* X, int32_t ldx, const float* dY,

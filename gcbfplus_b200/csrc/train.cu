@@ -13,6 +13,7 @@
 
 namespace gcbf {
 
+int32_t build_prepared(const ParamLayout& L, const float* P, float* out, cudaStream_t st);
 int32_t gnn_forward_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* PT, const float* agent, const float* goal,
                          const float* hits, const int32_t* row_start, const int32_t* row_deg,
                          const int32_t* edge_recv, const int32_t* edge_src, const int32_t* counters, int clip_all,
@@ -517,9 +518,12 @@ static int32_t dense_bwd_data(const BwdArgs& b, const ParamLayout& L, const Tran
                               const float* dY, float* dX, const float* aux, RowCount rc, cudaStream_t st) {
     const int N = (li == L_UPD0) ? 128 : L.in[li];
     const int K = L.out[li];
-    if (b.use_tc)
-        return tc::launch_gemm_tc(epi, accum, dY, b.P + L.w[li] + (li == L_UPD0 ? 3 * 256 : 0), nullptr, nullptr, dX, aux,
-                                  rc, K, N, st);
+    if (b.use_tc) {   // b.PT = prepared blob: the W planes are the K-major B operand of dX = dY @ W^T
+        const PreparedLayout Q = make_prepared_layout(L, TL);
+        const int off = L.w[li] + (li == L_UPD0 ? 3 * 256 : 0);
+        return tc::launch_gemm_tc(epi, accum, dY, b.PT + Q.p_hi + off, b.PT + Q.p_lo + off, nullptr, nullptr, dX, aux, rc,
+                                  K, N, st);
+    }
     return launch_gemm_nn(epi, accum, dY, b.PT + TL.w[li], nullptr, nullptr, dX, aux, rc, K, N, st);
 }
 
@@ -703,8 +707,8 @@ static TrainWs make_train_ws(const gcbf_env_desc* d) {
     t.ws1 = take(W.total);
     t.ws2 = take(W.total);
     t.gws = take(W.total);
-    t.pt_cbf = take(Tc.total);
-    t.pt_act = take(Ta.total);
+    t.pt_cbf = take(make_prepared_layout(make_layout(ed, 1), Tc).total);
+    t.pt_act = take(make_prepared_layout(make_layout(ed, nu), Ta).total);
     t.h = take(A);
     t.hn = take(A);
     t.pi = take(A * nu);
@@ -786,10 +790,15 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
         set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
         return (int32_t)e;
     }
-    RC(build_transposes(Lc, make_trans_layout(Lc), cbf_params, ws + TW.pt_cbf, st));
-    RC(build_transposes(La, make_trans_layout(La), actor_params, ws + TW.pt_act, st));
-    // ---- forward: h = cbf(g), pi = actor(g), x' = f(x, clip(2 pi + u_ref)), h' = cbf(g')
     const int use_tc = hp_host[6] != 0.f;
+    if (use_tc) {
+        RC(build_prepared(Lc, cbf_params, ws + TW.pt_cbf, st));
+        RC(build_prepared(La, actor_params, ws + TW.pt_act, st));
+    } else {
+        RC(build_transposes(Lc, make_trans_layout(Lc), cbf_params, ws + TW.pt_cbf, st));
+        RC(build_transposes(La, make_trans_layout(La), actor_params, ws + TW.pt_act, st));
+    }
+    // ---- forward: h = cbf(g), pi = actor(g), x' = f(x, clip(2 pi + u_ref)), h' = cbf(g')
     const float* ptc = use_tc ? ws + TW.pt_cbf : nullptr;
     const float* pta = use_tc ? ws + TW.pt_act : nullptr;
     RC(gnn_forward_impl(d, 1, cbf_params, ptc, agent, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 0,

@@ -55,4 +55,21 @@ static int32_t build_transposes(const ParamLayout& L, const TransLayout& T, cons
 }
 
 
+
+// "Prepared" parameters of one network for the tensor-core path (gcbf_prepare_params):
+//   [ W^T hi | W^T lo | W hi | W lo ]   (tf32 split planes; W^T in TransLayout order, W in ParamLayout order)
+// forward GEMMs read the W^T planes (K-major B operand), backward-data GEMMs the W planes.
+struct PreparedLayout {
+    int pt_hi, pt_lo, p_hi, p_lo, total;
+};
+inline PreparedLayout make_prepared_layout(const ParamLayout& L, const TransLayout& T) {
+    PreparedLayout q;
+    q.pt_hi = 0;
+    q.pt_lo = T.total;
+    q.p_hi = 2 * T.total;
+    q.p_lo = 2 * T.total + L.total;
+    q.total = 2 * T.total + 2 * L.total;
+    return q;
+}
+
 }  // namespace gcbf

@@ -215,11 +215,15 @@ int32_t gcbf_gemm_nn(int32_t epi, int32_t accum, const float* A, const float* B,
                      int32_t m_fixed, int32_t m_cap, int32_t K, int32_t N, void* stream);
 /* gemm_tc: the tcgen05 tensor-core variant (3xTF32 split, fp32 accumulation in TMEM, TMA-staged
  * operands): C[M,N] = epi(A[M,K] @ Bt[N,K]^T) with Bt = the TRANSPOSED weight (K-major operands);
+ * Bt is passed as its tf32 split Bt_hi + Bt_lo (gcbf_split_tf32; weights are split once per update);
  * same epilogues / row-count convention as gemm_nn.  K % 32 == 0, N in {128, 256};
  * A must be backed by at least m_cap rows. */
-int32_t gcbf_gemm_tc(int32_t epi, int32_t accum, const float* A, const float* Bt, const float* bias,
-                     const float* bias2, float* C, const float* aux, const int32_t* m_ptr,
-                     int32_t m_fixed, int32_t m_cap, int32_t K, int32_t N, void* stream);
+int32_t gcbf_gemm_tc(int32_t epi, int32_t accum, const float* A, const float* Bt_hi, const float* Bt_lo,
+                     const float* bias, const float* bias2, float* C, const float* aux,
+                     const int32_t* m_ptr, int32_t m_fixed, int32_t m_cap, int32_t K, int32_t N,
+                     void* stream);
+/* hi = tf32(x) (round to nearest), lo = tf32(x - hi): the operand split of the 3xTF32 scheme. */
+int32_t gcbf_split_tf32(const float* in, float* hi, float* lo, int32_t n, void* stream);
 int32_t gcbf_gemm_tn(const float* X, int32_t ldx, const float* dY, float* C, const float* roww,
                      const int32_t* row2agent, const int32_t* m_ptr, int32_t m_fixed, int32_t m_cap,
                      int32_t K1, int32_t N, int32_t n_agents_total, void* stream);

@@ -183,12 +183,15 @@ def test_tensor_core_gemm_matches_float64():
         A = torch.randn(cap, K, device="cuda", generator=g)
         W = torch.randn(K, N, device="cuda", generator=g) * 0.1
         Bt = W.t().contiguous()
+        Bh, Bl = torch.empty_like(Bt), torch.empty_like(Bt)
+        _lib.check(lib.gcbf_split_tf32(Bt.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), Bt.numel(), st))
+        assert float((Bh + Bl - Bt).abs().max()) <= 2 ** -23 * float(Bt.abs().max())
         b = torch.randn(N, device="cuda", generator=g)
         b2 = torch.randn(N, device="cuda", generator=g)
         aux = torch.randn(cap, N, device="cuda", generator=g)
         out = torch.full((cap, N), 7.0, device="cuda")
         mc = torch.tensor([M], dtype=torch.int32, device="cuda")
-        _lib.check(lib.gcbf_gemm_tc(epi, accum, A.data_ptr(), Bt.data_ptr(), b.data_ptr(), b2.data_ptr(), out.data_ptr(),
+        _lib.check(lib.gcbf_gemm_tc(epi, accum, A.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), b.data_ptr(), b2.data_ptr(), out.data_ptr(),
                                     aux.data_ptr(), mc.data_ptr(), 0, cap, K, N, st))
         ref = A[:M].double() @ W.double()
         if epi in (0, 1):
