@@ -50,6 +50,10 @@ _SIGNATURES = {
     "gcbf_gnn_workspace_floats": (C.c_int64, [C.POINTER(EnvDesc), C.c_int32]),
     "gcbf_gnn_forward": (C.c_int32, [C.POINTER(EnvDesc), C.c_int32, C.c_int32] + [_P] * 10 + [C.c_int32, _P, _P,
                                      C.c_int64, _P]),
+    "gcbf_infer_count": (C.c_int32, [C.c_int32, C.c_int32]),
+    "gcbf_prepare_infer": (C.c_int32, [C.c_int32, C.c_int32, _P, _P, _P]),
+    "gcbf_gnn_infer": (C.c_int32, [C.POINTER(EnvDesc), C.c_int32, C.c_int32, _P, _P, C.c_int32] + [_P] * 8 +
+                       [C.c_int32, _P, _P, C.c_int64, _P]),
     "gcbf_params_t_count": (C.c_int32, [C.c_int32, C.c_int32]),
     "gcbf_prepare_params": (C.c_int32, [C.c_int32, C.c_int32, _P, _P, _P]),
     "gcbf_env_step": (C.c_int32, [C.POINTER(EnvDesc)] + [_P] * 11 + [C.c_int32, _P]),

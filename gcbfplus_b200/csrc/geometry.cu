@@ -14,7 +14,7 @@
 
 namespace gcbf {
 
-static constexpr int GB_WARPS = 8;  // agents (warps) per CTA in graph_build
+static constexpr int GB_WARPS = 32;  // agents (warps) per CTA in graph_build
 #define NO_HIT 1e6f
 
 // ------------------------------------------------------------------------------------
@@ -162,6 +162,11 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
     }
     for (int i = tid; i < d.n_rays * PD; i += blockDim.x) stab[i] = ray_table[i];
     __syncthreads();
+    if (PD == 2) {   // slot 14 of a packed rectangle (padding): bounding radius, for the exact far-obstacle skip
+        for (int o = tid; o < O; o += blockDim.x)
+            sobs[16 * o + 14] = sqrtf(sobs[16 * o + 2] * sobs[16 * o + 2] + sobs[16 * o + 3] * sobs[16 * o + 3]);
+        __syncthreads();
+    }
 
     const int i = blockIdx.x * GB_WARPS + warp;
     const bool valid = i < N;
@@ -185,8 +190,28 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
             if (O == 0) {
                 alpha = 1.f * NO_HIT;
             } else {
-                alpha = rect_raytrace(sobs, x1, y1, x2, y2);
-                for (int o = 1; o < O; ++o) alpha = nanmin(alpha, rect_raytrace(sobs + 16 * o, x1, y1, x2, y2));
+                // A rectangle whose bounding circle is out of the ray's reach cannot be hit: every edge test gives
+                // valid = 0 and alpha = 0 * alpha + 1e6 = 1e6 exactly -- unless an edge is exactly parallel to the
+                // ray (det == 0 -> alpha = x/0 -> NaN in the reference, obstacle.py:88-94).  The skip below is
+                // therefore taken only when it is bit-identical to the full evaluation (agent-uniform branch).
+                alpha = NO_HIT;
+                for (int o = 0; o < O; ++o) {
+                    const float* ob = sobs + 16 * o;
+                    const float cx = x1 - ob[0], cy = y1 - ob[1];
+                    const bool far = sqrtf(cx * cx + cy * cy) > d.comm_radius + ob[14] + 1e-3f;
+                    bool degenerate = false;
+                    if (far) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int kp = (k + 3) & 3;
+                            const float det = (x1 - x2) * (ob[7 + 2 * kp] - ob[7 + 2 * k]) -
+                                              (y1 - y2) * (ob[6 + 2 * kp] - ob[6 + 2 * k]);
+                            degenerate = degenerate || (det == 0.f) || isnan(det);
+                        }
+                    }
+                    if (!far || __any_sync(0xffffffffu, degenerate))
+                        alpha = nanmin(alpha, rect_raytrace(ob, x1, y1, x2, y2));
+                }
                 alpha = alpha * keep;
             }
             const float hx = x1 + (x2 - x1) * alpha;

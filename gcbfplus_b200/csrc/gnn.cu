@@ -205,3 +205,178 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_gemm_tn_tc(const 
     return gcbf::tc::launch_gemm_tn_tc(X, ldx, dY, C, roww, row2agent, RowCount{m_ptr, m_fixed, m_cap}, K1, N,
                                        n_agents_total, (cudaStream_t)stream);
 }
+
+// =====================================================================================================
+// Inference path with folded weights.  Every MLP block of the GNN ends in two linear layers with no
+// activation in between (act_final=False, gcbfplus/nn/mlp.py:23-29), so for rollouts
+//   msg   = relu1 @ (W2 W3) + (b2 W3 + b3)                      256 -> 128
+//   gate  = relu(msg A1 + ba1) . (A2 a3) + (ba2 . a3 + ba3)     128 -> 128 -> 1
+//   h1    = relu(relu(aggr U1' + bu1') @ (U2 U3 H1) + ((bu2 U3 + bu3) H1 + bh1))   128 -> 256 -> 256
+//   out   = tanh(h1 @ (H2 H3) + (bh2 H3 + bh3))                 256 -> nu
+// 4 GEMMs + 3 small kernels per forward instead of 9 + 3, 2.4x fewer FLOPs.  The folded weights are
+// rebuilt from the training parameters by gcbf_prepare_infer (once per parameter update).
+// =====================================================================================================
+namespace gcbf {
+
+struct InferLayout {
+    int w23, b23, a23, c23, uh, buh, ho, bho;          // folded fp32 weights
+    int t_w23, t_a1, t_u1, t_uh;                       // transposed tf32 planes: hi at t_x, lo at t_x + size
+    int total;
+};
+static InferLayout make_infer_layout(int out_dim) {
+    InferLayout I;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+    I.w23 = take(256 * 128);
+    I.b23 = take(128);
+    I.a23 = take(128);
+    I.c23 = take(4);
+    I.uh = take(256 * 256);
+    I.buh = take(256);
+    I.ho = take(256 * out_dim);
+    I.bho = take(4);
+    I.t_w23 = take(2 * 128 * 256);
+    I.t_a1 = take(2 * 128 * 128);
+    I.t_u1 = take(2 * 256 * 128);
+    I.t_uh = take(2 * 256 * 256);
+    I.total = o;
+    return I;
+}
+
+// C[m,n] = A[m,k] @ B[k,n] (+ bias[n]); one thread per output, fp32 sequential accumulation (setup work).
+static __global__ void small_matmul_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                           const float* __restrict__ bias, float* __restrict__ C, int m, int k, int n) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * n) return;
+    const int r = idx / n, c = idx % n;
+    float s = 0.f;
+    for (int j = 0; j < k; ++j) s = fmaf(A[(size_t)r * k + j], B[(size_t)j * n + c], s);
+    C[idx] = s + (bias ? bias[c] : 0.f);
+}
+static int32_t small_matmul(const float* A, const float* B, const float* bias, float* C, int m, int k, int n,
+                            cudaStream_t st) {
+    small_matmul_kernel<<<(m * n + 127) / 128, 128, 0, st>>>(A, B, bias, C, m, k, n);
+    count_launch();
+    return check_launch("small_matmul_kernel");
+}
+
+static int32_t prepare_infer_impl(int ed, int out_dim, const float* P, float* blob, cudaStream_t st) {
+    const ParamLayout L = make_layout(ed, out_dim);
+    const InferLayout I = make_infer_layout(out_dim);
+    int32_t rc;
+#define RC(x) do { if ((rc = (x))) return rc; } while (0)
+    // message tail
+    RC(small_matmul(P + L.w[L_MSG1], P + L.w[L_MSGOUT], nullptr, blob + I.w23, 256, 256, 128, st));
+    RC(small_matmul(P + L.b[L_MSG1], P + L.w[L_MSGOUT], P + L.b[L_MSGOUT], blob + I.b23, 1, 256, 128, st));
+    // gate tail: a23 = A2 a3 ; c = ba2 . a3 + ba3
+    RC(small_matmul(P + L.w[L_ATT1], P + L.w[L_GATE], nullptr, blob + I.a23, 128, 128, 1, st));
+    RC(small_matmul(P + L.b[L_ATT1], P + L.w[L_GATE], P + L.b[L_GATE], blob + I.c23, 1, 128, 1, st));
+    // update tail + head first layer: UH = U2 U3 H1 (scratch for U2 U3 lives in the t_uh region until it is overwritten)
+    float* tmp = blob + I.t_uh;                          // 256*128 (+128) floats of scratch
+    RC(small_matmul(P + L.w[L_UPD1], P + L.w[L_UPDOUT], nullptr, tmp, 256, 256, 128, st));
+    RC(small_matmul(tmp, P + L.w[L_HEAD0], nullptr, blob + I.uh, 256, 128, 256, st));
+    RC(small_matmul(P + L.b[L_UPD1], P + L.w[L_UPDOUT], P + L.b[L_UPDOUT], tmp, 1, 256, 128, st));
+    RC(small_matmul(tmp, P + L.w[L_HEAD0], P + L.b[L_HEAD0], blob + I.buh, 1, 128, 256, st));
+    // head tail
+    RC(small_matmul(P + L.w[L_HEAD1], P + L.w[L_OUT], nullptr, blob + I.ho, 256, 256, out_dim, st));
+    RC(small_matmul(P + L.b[L_HEAD1], P + L.w[L_OUT], P + L.b[L_OUT], blob + I.bho, 1, 256, out_dim, st));
+    // transposed + tf32-split planes of the 4 GEMM weights (tensor-core path)
+    struct { const float* src; int rows, cols, dst; } T[4] = {
+        {blob + I.w23, 256, 128, I.t_w23}, {P + L.w[L_ATT0], 128, 128, I.t_a1},
+        {P + L.w[L_UPD0] + 3 * 256, 128, 256, I.t_u1}, {blob + I.uh, 256, 256, I.t_uh}};
+    const int nsm = sm_count();
+    for (int i = 0; i < 4; ++i) {
+        const int n = T[i].rows * T[i].cols;
+        RC(launch_transpose(T[i].src, blob + T[i].dst, T[i].rows, T[i].cols, st));
+        tc::split_tf32_kernel<<<min((n + 255) / 256, 4 * nsm), 256, 0, st>>>(blob + T[i].dst, blob + T[i].dst,
+                                                                            blob + T[i].dst + n, n);
+        count_launch();
+        RC(check_launch("split_tf32_kernel"));
+    }
+#undef RC
+    return 0;
+}
+
+static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* blob, int use_tc,
+                              const float* agent, const float* goal, const float* hits, const int32_t* row_start,
+                              const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src,
+                              const int32_t* counters, int clip_all, float* out, float* ws, cudaStream_t st) {
+    const int ed = env_ed(d->env_kind);
+    const ParamLayout L = make_layout(ed, out_dim);
+    const InferLayout I = make_infer_layout(out_dim);
+    const int A = d->n_graphs * d->n_agents, cap = d->edge_cap;
+    const GnnWs W = make_ws(cap, A);
+    const RowCount re{counters, 0, cap};
+    const RowCount ra{nullptr, A, A};
+    const int nsm = sm_count();
+    int32_t rc;
+    auto gemm = [&](int epi, const float* X, const float* Wf, int t_off, int K, int N, const float* bias,
+                    const float* bias2, float* Y, RowCount rows) -> int32_t {
+        if (use_tc) return tc::launch_gemm_tc(epi, false, X, blob + t_off, blob + t_off + K * N, bias, bias2, Y, nullptr, rows, K, N, st);
+        return launch_gemm_nn(epi, false, X, Wf, bias, bias2, Y, nullptr, rows, K, N, st);
+    };
+    {
+        const int grid = min((cap + 7) / 8, 4 * nsm);
+        GCBF_DISPATCH_ENV(d->env_kind, {
+            edge_l1_kernel<KIND><<<grid, 256, 0, st>>>(*d, P + L.w[L_MSG0], P + L.b[L_MSG0], agent, goal, hits,
+                                                       edge_recv, edge_src, counters, clip_all, ws + W.feat, ws + W.x1);
+        });
+        count_launch();
+        if ((rc = check_launch("edge_l1_kernel"))) return rc;
+    }
+    if ((rc = gemm(EPI_BIAS, ws + W.x1, blob + I.w23, I.t_w23, 256, 128, blob + I.b23, nullptr, ws + W.msg, re))) return rc;
+    if ((rc = gemm(EPI_BIAS_RELU, ws + W.msg, P + L.w[L_ATT0], I.t_a1, 128, 128, P + L.b[L_ATT0], nullptr, ws + W.g1, re))) return rc;
+    {
+        const int grid = min((A + 7) / 8, 4 * nsm);
+        attn_aggregate_kernel<<<grid, 256, 0, st>>>(A, cap, ws + W.g1, ws + W.msg, blob + I.a23, blob + I.c23, row_start,
+                                                    row_deg, ws + W.att, ws + W.ag);
+        count_launch();
+        if ((rc = check_launch("attn_aggregate_kernel"))) return rc;
+    }
+    if ((rc = gemm(EPI_BIAS_RELU, ws + W.ag, P + L.w[L_UPD0] + 3 * 256, I.t_u1, 128, 256, P + L.b[L_UPD0],
+                   P + L.w[L_UPD0] + 2 * 256, ws + W.v1, ra))) return rc;
+    if ((rc = gemm(EPI_BIAS_RELU, ws + W.v1, blob + I.uh, I.t_uh, 256, 256, blob + I.buh, nullptr, ws + W.h1, ra))) return rc;
+    {
+        const int grid = min((A + 7) / 8, 4 * nsm);
+        head_out_kernel<<<grid, 256, 0, st>>>(A, out_dim, ws + W.h1, blob + I.ho, blob + I.bho, out);
+        count_launch();
+        if ((rc = check_launch("head_out_kernel"))) return rc;
+    }
+    return 0;
+}
+
+}  // namespace gcbf
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_infer_count(int32_t edge_dim, int32_t out_dim) {
+    if (edge_dim < 1 || edge_dim > 6 || out_dim < 1 || out_dim > 4) return -1;
+    return make_infer_layout(out_dim).total;
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_prepare_infer(int32_t edge_dim, int32_t out_dim,
+                                                                             const float* params, float* infer_blob,
+                                                                             void* stream) {
+    GCBF_REQUIRE(edge_dim >= 1 && edge_dim <= 6 && out_dim >= 1 && out_dim <= 4 && params && infer_blob,
+                 "gcbf_prepare_infer: bad argument");
+    GCBF_REQUIRE((((uintptr_t)params | (uintptr_t)infer_blob) & 15) == 0, "gcbf_prepare_infer: 16-byte alignment required");
+    return prepare_infer_impl(edge_dim, out_dim, params, infer_blob, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_gnn_infer(
+    const gcbf_env_desc* desc, int32_t net_kind, int32_t out_dim, const float* params, const float* infer_blob,
+    int32_t use_tensor_cores, const float* agent, const float* goal, const float* hits, const int32_t* row_start,
+    const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src, const int32_t* counters,
+    int32_t clip_all, float* out, float* workspace, int64_t workspace_floats, void* stream) {
+    GCBF_REQUIRE(desc && params && infer_blob && agent && goal && hits && row_start && row_deg && edge_recv && edge_src &&
+                     counters && out && workspace, "gcbf_gnn_infer: NULL pointer argument");
+    GCBF_REQUIRE(desc->env_kind >= 0 && desc->env_kind <= 3, "bad env_kind");
+    GCBF_REQUIRE(net_kind == GCBF_NET_CBF || net_kind == GCBF_NET_ACTOR, "bad net_kind %d", net_kind);
+    GCBF_REQUIRE(out_dim >= 1 && out_dim <= 4 && (net_kind != GCBF_NET_CBF || out_dim == 1), "bad out_dim %d", out_dim);
+    GCBF_REQUIRE(desc->edge_cap > 0, "edge_cap must be positive");
+    const int64_t need = make_ws(desc->edge_cap, (int64_t)desc->n_graphs * desc->n_agents).total;
+    GCBF_REQUIRE(workspace_floats >= need, "workspace too small: %lld < %lld floats", (long long)workspace_floats,
+                 (long long)need);
+    GCBF_REQUIRE((((uintptr_t)params | (uintptr_t)workspace | (uintptr_t)infer_blob) & 15) == 0,
+                 "params/infer_blob/workspace must be 16-byte aligned");
+    return gnn_infer_impl(desc, out_dim, params, infer_blob, use_tensor_cores, agent, goal, hits, row_start, row_deg,
+                          edge_recv, edge_src, counters, clip_all, out, workspace, (cudaStream_t)stream);
+}

@@ -49,8 +49,9 @@ class RolloutEngine:
         n_ws = env.lib.gcbf_gnn_workspace_floats(C.byref(self.desc), nu)
         self.ws = torch.empty(int(n_ws), dtype=f32, device=dev)
         self.params_buf = torch.zeros(_lib.param_count(env.edge_dim, nu), dtype=f32, device=dev)
-        self.params_t = (torch.zeros(int(env.lib.gcbf_params_t_count(env.edge_dim, nu)), dtype=f32, device=dev)
-                         if _lib.USE_TC else None)
+        # folded inference weights (gcbf_prepare_infer), rebuilt by set_params()
+        self.infer_blob = torch.zeros(int(env.lib.gcbf_infer_count(env.edge_dim, nu)), dtype=f32, device=dev)
+        self.use_tc = 1 if _lib.USE_TC else 0
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_run = 0
         self._obstacle_obj = None
@@ -70,13 +71,14 @@ class RolloutEngine:
         nu = env.action_dim
         mode = 2
         if self.policy == "actor":
-            rc = env.lib.gcbf_gnn_forward(C.byref(d), _lib.NET_ACTOR, nu, self.params_buf.data_ptr(),
-                                          _lib.ptr(self.params_t), self.agent[t].data_ptr(), self.goal.data_ptr(), self.hits[t].data_ptr(),
+            rc = env.lib.gcbf_gnn_infer(C.byref(d), _lib.NET_ACTOR, nu, self.params_buf.data_ptr(),
+                                        self.infer_blob.data_ptr(), self.use_tc, self.agent[t].data_ptr(),
+                                        self.goal.data_ptr(), self.hits[t].data_ptr(),
                                           self.row_start.data_ptr(), self.row_deg.data_ptr(),
                                           self.edge_recv.data_ptr(), self.edge_src.data_ptr(),
                                           self.counters[t].data_ptr(), 0, self.pi.data_ptr(), self.ws.data_ptr(),
                                           self.ws.numel(), stream)
-            _lib.check(rc, "gcbf_gnn_forward")
+            _lib.check(rc, "gcbf_gnn_infer")
             mode = 0
         rc = env.lib.gcbf_env_step(C.byref(d), self.agent[t].data_ptr(), self.goal.data_ptr(),
                                    self.obstacles.data_ptr() if self.O > 0 else None, self.pi.data_ptr(),
@@ -103,10 +105,9 @@ class RolloutEngine:
 
     def set_params(self, params: NetParams) -> None:
         self.params_buf.copy_(params.flat, non_blocking=True)
-        if self.params_t is not None:
-            env = self.env
-            _lib.check(env.lib.gcbf_prepare_params(env.edge_dim, env.action_dim, _lib.ptr(self.params_buf),
-                                                   _lib.ptr(self.params_t), env._stream()), "gcbf_prepare_params")
+        env = self.env
+        _lib.check(env.lib.gcbf_prepare_infer(env.edge_dim, env.action_dim, _lib.ptr(self.params_buf),
+                                              _lib.ptr(self.infer_blob), env._stream()), "gcbf_prepare_infer")
 
     def run(self, check: bool = True) -> None:
         """Run the T-step rollout from the current initial conditions (async)."""
