@@ -27,7 +27,8 @@ class EnvDesc(C.Structure):
         ("dt", C.c_float), ("mass", C.c_float), ("radius", C.c_float), ("two_r", C.c_float),
         ("two_r_p1", C.c_float), ("half_r", C.c_float), ("unsafe_agent", C.c_float), ("unsafe_obs", C.c_float),
         ("warn_agent", C.c_float), ("warn_obs", C.c_float), ("four_r_sq", C.c_float), ("r_sq", C.c_float),
-        ("safe_agent", C.c_float), ("safe_obs", C.c_float), ("v_lim", C.c_float), ("u_lim", C.c_float),
+        ("safe_agent", C.c_float), ("safe_obs", C.c_float), ("comm_sq_thr", C.c_float), ("lidar_sq_thr", C.c_float),
+        ("v_lim", C.c_float), ("u_lim", C.c_float),
         ("K", C.c_float * 18), ("A", C.c_float * 36), ("B", C.c_float * 18),
     ]
 
@@ -54,6 +55,8 @@ _SIGNATURES = {
     "gcbf_prepare_infer": (C.c_int32, [C.c_int32, C.c_int32, _P, _P, _P]),
     "gcbf_gnn_infer": (C.c_int32, [C.POINTER(EnvDesc), C.c_int32, C.c_int32, _P, _P, C.c_int32] + [_P] * 8 +
                        [C.c_int32, _P, _P, C.c_int64, _P]),
+    "gcbf_rollout_workspace_floats": (C.c_int64, [C.POINTER(EnvDesc)]),
+    "gcbf_rollout_step": (C.c_int32, [C.POINTER(EnvDesc), _P, _P, C.c_int32] + [_P] * 17 + [C.c_int64, _P]),
     "gcbf_params_t_count": (C.c_int32, [C.c_int32, C.c_int32]),
     "gcbf_prepare_params": (C.c_int32, [C.c_int32, C.c_int32, _P, _P, _P]),
     "gcbf_env_step": (C.c_int32, [C.POINTER(EnvDesc)] + [_P] * 11 + [C.c_int32, _P]),
@@ -122,6 +125,18 @@ def ptr(t) -> int:
 def f32(v: float) -> float:
     """Round a python double to fp32 (where JAX's weak typing rounds a python scalar)."""
     return float(np.float32(v))
+
+
+def sqrt_threshold(r: float) -> float:
+    """Smallest fp32 a such that the correctly rounded fp32 sqrt(a) >= fp32(r), i.e.
+    (sqrtf(x) < r) == (x < a) for every fp32 x >= 0: lets the kernels drop the sqrt bit-exactly."""
+    r32 = np.float32(r)
+    a = np.float32(r32 * r32)
+    while np.sqrt(a) >= r32:
+        a = np.nextafter(a, np.float32(0), dtype=np.float32)
+    while np.sqrt(a) < r32:
+        a = np.nextafter(a, np.float32(np.inf), dtype=np.float32)
+    return float(a)
 
 
 def param_offsets(edge_dim: int, out_dim: int):

@@ -142,7 +142,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int M = m_ptr ? *m_ptr : m_fixed;
     M = min(M, m_cap);
-    const int n_tiles = (M + BM - 1) / BM;     // BN == N: one tile column
+    const int tiles_n = N / BN;                // 1, or 2 when a 256-wide layer is split to fill more SMs
+    const int n_tiles = ((M + BM - 1) / BM) * tiles_n;
     const int nkb = K / BK;
 
     if (threadIdx.x == 0) {
@@ -173,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = tile * BM;
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -181,8 +182,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* st = smem + s * CF::STAGE_BYTES;
                     mbar_expect_tx(&full[s], CF::A_BYTES + 2 * CF::B_BYTES);
                     tma_load_2d(st, &tmA, &full[s], kb * BK, m0);
-                    tma_load_2d(st + 2 * CF::A_BYTES, &tmBh, &full[s], kb * BK, 0);
-                    tma_load_2d(st + 2 * CF::A_BYTES + CF::B_BYTES, &tmBl, &full[s], kb * BK, 0);
+                    tma_load_2d(st + 2 * CF::A_BYTES, &tmBh, &full[s], kb * BK, n0);
+                    tma_load_2d(st + 2 * CF::A_BYTES + CF::B_BYTES, &tmBl, &full[s], kb * BK, n0);
                 }
             }
         }
@@ -251,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quarter = warp & 3;             // TMEM lane quarter this warp may access
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-            const int m0 = tile * BM;
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             const uint32_t acc = tcount & 1;
             mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -262,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t v[32];
                 tmem_ld32(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
                 if (m < M) {
-                    const int n = c0;
+                    const int n = n0 + c0;
                     float* crow = C + (size_t)m * N + n;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -388,13 +389,16 @@ inline int32_t launch_gemm_tc(int epi, bool accum, const float* A, const float* 
     }
     const int rows = rc.ptr ? rc.cap : min(rc.fixed, rc.cap);
     if (rows <= 0) return 0;
+    const int tiles_m = (rows + BM - 1) / BM;
+    // a 256-wide layer over few row tiles is split into two 128-wide column tiles: twice the CTAs (more SMs
+    // busy), half the weight traffic and MMA time per CTA, 3 pipeline stages instead of 2
+    const int bn = (N == 256 && 2 * tiles_m <= sm_count()) ? 128 : N;
     CUtensorMap tmA, tmB, tmBl;
     if (int32_t r = make_map(&tmA, A, rc.cap, K, BM)) return r;
-    if (int32_t r = make_map(&tmB, Bt_hi, N, K, N)) return r;
-    if (int32_t r = make_map(&tmBl, Bt_lo, N, K, N)) return r;
-    const int tiles = (rows + BM - 1) / BM;
-    const int grid = min(tiles, sm_count());
-    if (N == 256) return launch_bn<256>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st);
+    if (int32_t r = make_map(&tmB, Bt_hi, N, K, bn)) return r;
+    if (int32_t r = make_map(&tmBl, Bt_lo, N, K, bn)) return r;
+    const int grid = min(tiles_m * (N / bn), sm_count());
+    if (bn == 256) return launch_bn<256>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st);
     return launch_bn<128>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st);
 }
 

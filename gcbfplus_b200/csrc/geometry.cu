@@ -136,16 +136,46 @@ __global__ void __launch_bounds__(GB_WARPS * 32)
 graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const float* __restrict__ obstacles,
                    const float* __restrict__ ray_table, float* __restrict__ hits, int32_t* __restrict__ row_start,
                    int32_t* __restrict__ row_deg, int32_t* __restrict__ edge_recv, int32_t* __restrict__ edge_src,
-                   int32_t* __restrict__ counters, const int do_cast) {
+                   int32_t* __restrict__ counters, const int do_cast, const float* __restrict__ terms,
+                   float* __restrict__ reward, float* __restrict__ cost) {
     using T = EnvTraits<KIND>;
     constexpr int SD = T::SD, PD = T::PD;
     constexpr int OBW = (PD == 2) ? 16 : 4;
     extern __shared__ float smem[];
     const int N = d.n_agents, O = d.n_obs, R = d.n_hits;
+    // ---- optional: per-env reward / cost of the step that produced these states (policy_tail_kernel wrote the
+    // per-agent terms); deterministic fixed-order reduction by the first CTA of each graph.
+    if (terms != nullptr && blockIdx.x == 0) {
+        __shared__ float s_red[3][GB_WARPS];
+        const int A_tot = d.n_graphs * N;
+        float acc[3] = {0.f, 0.f, 0.f};
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) acc[q] += terms[(size_t)q * A_tot + (size_t)blockIdx.y * N + i];
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float v = warp_sum(acc[q]);
+            if ((threadIdx.x & 31) == 0) s_red[q][threadIdx.x >> 5] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t[3] = {0.f, 0.f, 0.f};
+            for (int w = 0; w < GB_WARPS; ++w) {
+                t[0] += s_red[0][w];
+                t[1] += s_red[1][w];
+                t[2] += s_red[2][w];
+            }
+            reward[blockIdx.y] = -(t[0] / (float)N);
+            cost[blockIdx.y] = t[1] / (float)N + t[2] / (float)N;
+        }
+    }
     float* spos = smem;                         // [N, PD]
     float* sobs = spos + N * PD;                // [O, OBW]
     float* stab = sobs + O * OBW;               // [n_rays, PD]
     float* salpha = stab + d.n_rays * PD;       // 3-D only: [GB_WARPS, n_rays]
+    const int n_words = (N + 31) / 32;
+    unsigned* sbits = reinterpret_cast<unsigned*>(salpha + (PD == 3 ? GB_WARPS * d.n_rays : 0));  // [GB_WARPS, n_words]
     __shared__ int s_off[GB_WARPS + 1];
     __shared__ int s_base;
 
@@ -293,12 +323,15 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
                 const float dlt = p[c] - my_hits[lane * PD + c];
                 acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
             }
-            act = sqrtf(acc) < d.lidar_radius;
+            act = acc < d.lidar_sq_thr;   // == (sqrtf(acc) < lidar_radius), threshold precomputed exactly on the host
         }
         hit_bits = __ballot_sync(0xffffffffu, act);
     }
-    // ---------------- neighbour count: ||p_i - p_j|| < comm_radius, j != i (double_integrator.py:227-232)
+    // ---------------- neighbours: ||p_i - p_j|| < comm_radius, j != i (double_integrator.py:227-232).
+    // sqrtf(acc) < Rc  <=>  acc < comm_sq_thr (smallest fp32 whose correctly rounded sqrt is >= Rc; host-computed),
+    // so the scan needs no sqrt; the ballots are kept in shared memory for the fill pass.
     int cnt = 0;
+    unsigned* my_bits = sbits + warp * n_words;
     for (int j0 = 0; j0 < N; j0 += 32) {
         const int j = j0 + lane;
         bool ok = false;
@@ -309,9 +342,11 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
                 const float dlt = p[c] - spos[j * PD + c];
                 acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
             }
-            ok = sqrtf(acc) < d.comm_radius;
+            ok = acc < d.comm_sq_thr;
         }
-        cnt += __popc(__ballot_sync(0xffffffffu, ok));
+        const unsigned bits = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) my_bits[j0 >> 5] = bits;
+        cnt += __popc(bits);
     }
     const int deg = valid ? (1 + cnt + __popc(hit_bits)) : 0;
     if (lane == 0) s_off[warp + 1] = deg;
@@ -341,23 +376,13 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
     }
     int pos = base + 1;
     const unsigned lt = (1u << lane) - 1u;
-    for (int j0 = 0; j0 < N; j0 += 32) {
-        const int j = j0 + lane;
-        bool ok = false;
-        if (j < N && j != i) {
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < PD; ++c) {
-                const float dlt = p[c] - spos[j * PD + c];
-                acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
-            }
-            ok = sqrtf(acc) < d.comm_radius;
-        }
-        const unsigned bits = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
+    __syncwarp();
+    for (int w = 0; w < n_words; ++w) {
+        const unsigned bits = my_bits[w];
+        if ((bits >> lane) & 1u) {
             const int e = pos + __popc(bits & lt);
             edge_recv[e] = a_id;
-            edge_src[e] = g * N + j;
+            edge_src[e] = g * N + (w << 5) + lane;
         }
         pos += __popc(bits);
     }
@@ -556,6 +581,81 @@ env_step_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const fl
 }
 
 // ------------------------------------------------------------------------------------
+// policy tail: pi = tanh(H1 @ HO + bHO) (policy.py:72), a = 2 pi + u_ref (gcbf_plus.py:182-186), clip_action,
+// agent_step_euler, per-agent reward / cost terms (double_integrator.py:145-198).  Warp per agent.
+// ------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256)
+policy_tail_kernel(const gcbf_env_desc d, const float* __restrict__ H1, const float* __restrict__ HO,
+                   const float* __restrict__ bHO, const float* __restrict__ agent, const float* __restrict__ goal,
+                   const float* __restrict__ obstacles, const int32_t* __restrict__ row_start,
+                   const int32_t* __restrict__ row_deg, const int32_t* __restrict__ edge_src,
+                   float* __restrict__ action, float* __restrict__ next_agent, float* __restrict__ terms) {
+    using T = EnvTraits<KIND>;
+    constexpr int SD = T::SD, NU = T::NU, PD = T::PD;
+    constexpr int OBW = (PD == 2) ? 16 : 4;
+    const int lane = threadIdx.x & 31;
+    const int A = d.n_graphs * d.n_agents;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < A; a += warps_total) {
+        const float4 h0 = *reinterpret_cast<const float4*>(H1 + (size_t)a * 256 + lane * 8);
+        const float4 h1 = *reinterpret_cast<const float4*>(H1 + (size_t)a * 256 + lane * 8 + 4);
+        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        float pi[NU];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += hv[k] * HO[(lane * 8 + k) * NU + j];
+            pi[j] = tanhf(warp_sum(s) + bHO[j]);
+        }
+        if (lane != 0) continue;
+        const int g = a / d.n_agents;
+        float x[SD], gl[SD], ur[NU], u[NU], xn[SD];
+#pragma unroll
+        for (int c = 0; c < SD; ++c) {
+            x[c] = agent[(size_t)a * SD + c];
+            gl[c] = goal[(size_t)a * SD + c];
+        }
+        u_ref_dev<KIND>(d, x, gl, ur);
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) {
+            const float act = 2.f * pi[c] + ur[c];
+            action[(size_t)a * NU + c] = act;
+            u[c] = isnan(act) ? act : fminf(fmaxf(act, -d.u_lim), d.u_lim);
+            const float df = u[c] - ur[c];
+            sq = (c == 0) ? df * df : sq + df * df;
+        }
+        euler_dev<KIND>(d, x, gl, u, xn);
+#pragma unroll
+        for (int c = 0; c < SD; ++c) next_agent[(size_t)a * SD + c] = xn[c];
+        const float nr = sqrtf(sq);
+        bool col = false;
+        const int rs = row_start[a], rd = row_deg[a];
+        for (int e = rs + 1; e < rs + rd; ++e) {
+            const int s = edge_src[e];
+            if (s < 0) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < PD; ++c) {
+                const float dlt = x[c] - agent[(size_t)s * SD + c];
+                acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
+            }
+            col = col || (d.two_r > sqrtf(acc));
+        }
+        bool in_obs = false;
+        if (d.n_obs > 0) {
+            const float* ob = obstacles + (d.obs_per_graph ? (size_t)g * d.n_obs * OBW : 0);
+            in_obs = inside_any<PD>(ob, d.n_obs, x, d.radius);
+        }
+        terms[a] = nr * nr;
+        terms[(size_t)A + a] = col ? 1.f : 0.f;
+        terms[(size_t)2 * A + a] = in_obs ? 1.f : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // masks: warp per agent; brute force over the graph's agents + own hit nodes.
 // ------------------------------------------------------------------------------------
 template <int KIND>
@@ -713,10 +813,39 @@ static int32_t check_desc(const gcbf_env_desc* d) {
     return 0;
 }
 
+namespace gcbf {
+int32_t graph_build_impl(const gcbf_env_desc* desc, const float* agent, const float* obstacles, const float* ray_table,
+                         float* hits, int32_t* row_start, int32_t* row_deg, int32_t* edge_recv, int32_t* edge_src,
+                         int32_t* counters, int32_t flags, const float* terms, float* reward, float* cost, void* stream);
+
+// policy tail launcher (used by gcbf_rollout_step in gnn.cu)
+int32_t policy_tail_impl(const gcbf_env_desc* desc, const float* H1, const float* HO, const float* bHO,
+                         const float* agent, const float* goal, const float* obstacles, const int32_t* row_start,
+                         const int32_t* row_deg, const int32_t* edge_src, float* action, float* next_agent, float* terms,
+                         cudaStream_t st) {
+    const int A = desc->n_graphs * desc->n_agents;
+    const int grid = min((A + 7) / 8, 4 * sm_count());
+    GCBF_DISPATCH_ENV(desc->env_kind, {
+        policy_tail_kernel<KIND><<<grid, 256, 0, st>>>(*desc, H1, HO, bHO, agent, goal, obstacles, row_start, row_deg,
+                                                       edge_src, action, next_agent, terms);
+    });
+    count_launch();
+    return check_launch("policy_tail_kernel");
+}
+}  // namespace gcbf
+
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_graph_build(const gcbf_env_desc* desc, const float* agent, const float* obstacles,
                                     const float* ray_table, float* hits, int32_t* row_start, int32_t* row_deg,
                                     int32_t* edge_recv, int32_t* edge_src, int32_t* counters, int32_t flags,
                                     void* stream) {
+    return graph_build_impl(desc, agent, obstacles, ray_table, hits, row_start, row_deg, edge_recv, edge_src, counters,
+                            flags, nullptr, nullptr, nullptr, stream);
+}
+
+int32_t gcbf::graph_build_impl(const gcbf_env_desc* desc, const float* agent, const float* obstacles,
+                               const float* ray_table, float* hits, int32_t* row_start, int32_t* row_deg,
+                               int32_t* edge_recv, int32_t* edge_src, int32_t* counters, int32_t flags,
+                               const float* terms, float* reward, float* cost, void* stream) {
     if (int32_t rc = check_desc(desc)) return rc;
     GCBF_REQUIRE(agent && hits && row_start && row_deg && edge_recv && edge_src && counters, "NULL pointer argument");
     GCBF_REQUIRE(desc->n_obs == 0 || obstacles, "obstacles is NULL but n_obs > 0");
@@ -726,7 +855,8 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_graph_build(const
     const int pd = env_pd(desc->env_kind);
     const int obw = pd == 2 ? 16 : 4;
     const size_t smem = sizeof(float) * ((size_t)desc->n_agents * pd + (size_t)desc->n_obs * obw +
-                                         (size_t)desc->n_rays * pd + (pd == 3 ? (size_t)GB_WARPS * desc->n_rays : 0));
+                                         (size_t)desc->n_rays * pd + (pd == 3 ? (size_t)GB_WARPS * desc->n_rays : 0) +
+                                         (size_t)GB_WARPS * ((desc->n_agents + 31) / 32));
     GCBF_REQUIRE(smem <= 200 * 1024, "graph_build needs %zu B shared memory (> 200 KB): too many agents/obstacles", smem);
     cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int32_t)e; }
@@ -735,7 +865,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_graph_build(const
         auto kern = graph_build_kernel<KIND>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, GB_WARPS * 32, smem, st>>>(*desc, agent, obstacles, ray_table, hits, row_start, row_deg,
-                                                edge_recv, edge_src, counters, flags & 1);
+                                                edge_recv, edge_src, counters, flags & 1, terms, reward, cost);
     });
     count_launch();
     return check_launch("graph_build_kernel");

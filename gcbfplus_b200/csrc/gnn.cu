@@ -301,6 +301,7 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
                               const float* agent, const float* goal, const float* hits, const int32_t* row_start,
                               const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src,
                               const int32_t* counters, int clip_all, float* out, float* ws, cudaStream_t st) {
+    // out == nullptr: stop after the last hidden layer (ws + W.h1); the caller applies the output layer
     const int ed = env_ed(d->env_kind);
     const ParamLayout L = make_layout(ed, out_dim);
     const InferLayout I = make_infer_layout(out_dim);
@@ -336,7 +337,7 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
     if ((rc = gemm(EPI_BIAS_RELU, ws + W.ag, P + L.w[L_UPD0] + 3 * 256, I.t_u1, 128, 256, P + L.b[L_UPD0],
                    P + L.w[L_UPD0] + 2 * 256, ws + W.v1, ra))) return rc;
     if ((rc = gemm(EPI_BIAS_RELU, ws + W.v1, blob + I.uh, I.t_uh, 256, 256, blob + I.buh, nullptr, ws + W.h1, ra))) return rc;
-    {
+    if (out != nullptr) {
         const int grid = min((A + 7) / 8, 4 * nsm);
         head_out_kernel<<<grid, 256, 0, st>>>(A, out_dim, ws + W.h1, blob + I.ho, blob + I.bho, out);
         count_launch();
@@ -379,4 +380,56 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_gnn_infer(
                  "params/infer_blob/workspace must be 16-byte aligned");
     return gnn_infer_impl(desc, out_dim, params, infer_blob, use_tensor_cores, agent, goal, hits, row_start, row_deg,
                           edge_recv, edge_src, counters, clip_all, out, workspace, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One closed-loop rollout step in a single call: policy forward (folded weights) -> a = 2 pi + u_ref,
+// clip, Euler, reward / cost terms -> LiDAR + neighbour lists of the next state (+ reward / cost reduction).
+// 8 kernel launches.
+// ---------------------------------------------------------------------------------------------------
+namespace gcbf {
+int32_t graph_build_impl(const gcbf_env_desc* desc, const float* agent, const float* obstacles, const float* ray_table,
+                         float* hits, int32_t* row_start, int32_t* row_deg, int32_t* edge_recv, int32_t* edge_src,
+                         int32_t* counters, int32_t flags, const float* terms, float* reward, float* cost, void* stream);
+int32_t policy_tail_impl(const gcbf_env_desc* desc, const float* H1, const float* HO, const float* bHO,
+                         const float* agent, const float* goal, const float* obstacles, const int32_t* row_start,
+                         const int32_t* row_deg, const int32_t* edge_src, float* action, float* next_agent, float* terms,
+                         cudaStream_t st);
+}  // namespace gcbf
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step(
+    const gcbf_env_desc* desc, const float* actor_params, const float* infer_blob, int32_t use_tensor_cores,
+    const float* agent, const float* goal, const float* obstacles, const float* ray_table, const float* hits,
+    int32_t* row_start, int32_t* row_deg, int32_t* edge_recv, int32_t* edge_src, const int32_t* counters,
+    float* action, float* next_agent, float* next_hits, int32_t* next_counters, float* reward, float* cost,
+    float* workspace, int64_t workspace_floats, void* stream) {
+    GCBF_REQUIRE(desc && actor_params && infer_blob && agent && goal && ray_table && hits && row_start && row_deg &&
+                     edge_recv && edge_src && counters && action && next_agent && next_hits && next_counters && reward &&
+                     cost && workspace, "gcbf_rollout_step: NULL pointer argument");
+    GCBF_REQUIRE(desc->env_kind >= 0 && desc->env_kind <= 3 && desc->edge_cap > 0, "gcbf_rollout_step: bad descriptor");
+    GCBF_REQUIRE(desc->n_obs == 0 || obstacles, "obstacles is NULL but n_obs > 0");
+    const int nu = env_nu(desc->env_kind);
+    const int64_t A = (int64_t)desc->n_graphs * desc->n_agents;
+    const GnnWs W = make_ws(desc->edge_cap, A);
+    const int64_t need = W.total + 3 * A + 4;
+    GCBF_REQUIRE(workspace_floats >= need, "workspace too small: %lld < %lld floats", (long long)workspace_floats,
+                 (long long)need);
+    GCBF_REQUIRE((((uintptr_t)actor_params | (uintptr_t)workspace | (uintptr_t)infer_blob) & 15) == 0,
+                 "params/infer_blob/workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const InferLayout I = make_infer_layout(nu);
+    float* terms = workspace + ((W.total + 3) & ~(int64_t)3);
+    int32_t rc;
+    if ((rc = gnn_infer_impl(desc, nu, actor_params, infer_blob, use_tensor_cores, agent, goal, hits, row_start, row_deg,
+                             edge_recv, edge_src, counters, 0, nullptr, workspace, st))) return rc;
+    if ((rc = policy_tail_impl(desc, workspace + W.h1, infer_blob + I.ho, infer_blob + I.bho, agent, goal, obstacles,
+                               row_start, row_deg, edge_src, action, next_agent, terms, st))) return rc;
+    return graph_build_impl(desc, next_agent, obstacles, ray_table, next_hits, row_start, row_deg, edge_recv, edge_src,
+                            next_counters, 1, terms, reward, cost, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t gcbf_rollout_workspace_floats(const gcbf_env_desc* desc) {
+    if (!desc || desc->edge_cap <= 0 || desc->n_graphs <= 0 || desc->n_agents <= 0) return -1;
+    const int64_t A = (int64_t)desc->n_graphs * desc->n_agents;
+    return make_ws(desc->edge_cap, A).total + 3 * A + 8;
 }

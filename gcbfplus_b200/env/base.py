@@ -207,6 +207,7 @@ class MultiAgentEnv(ABC):
         d.safe_agent, d.safe_obs = f(th["safe_agent"]), f(th["safe_obs"])
         d.warn_agent, d.warn_obs = f(3 * r), f(2 * r)
         d.four_r_sq, d.r_sq = f(4 * r ** 2), f(r ** 2)
+        d.comm_sq_thr, d.lidar_sq_thr = _lib.sqrt_threshold(rc), _lib.sqrt_threshold(rc - 1e-1)
         lo, up = self.state_lim()
         fin = [float(v) for v in up if math.isfinite(float(v))]
         d.v_lim = f(fin[0]) if fin else float("inf")

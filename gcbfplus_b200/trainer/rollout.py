@@ -16,10 +16,35 @@ from ..utils.graph import SwarmGraph
 from .data import Rollout
 
 
+class _Chain:
+    """Per-chain scratch: a contiguous slice [e0, e1) of the environments with its own topology arrays,
+    policy output and activation workspace, so that chains are independent branches of the CUDA graph."""
+
+    def __init__(self, eng: "RolloutEngine", e0: int, e1: int):
+        env, dev = eng.env, eng.env.device
+        self.e0, self.e1 = e0, e1
+        E, N, nu = e1 - e0, env.num_agents, env.action_dim
+        f32, i32 = torch.float32, torch.int32
+        self.desc = env.desc(E, eng.O)
+        cap = self.desc.edge_cap
+        self.pi = torch.zeros(E, N, nu, dtype=f32, device=dev)
+        self.row_start = torch.zeros(E * N, dtype=i32, device=dev)
+        self.row_deg = torch.zeros(E * N, dtype=i32, device=dev)
+        self.edge_recv = torch.zeros(cap, dtype=i32, device=dev)
+        self.edge_src = torch.zeros(cap, dtype=i32, device=dev)
+        self.counters = torch.zeros(eng.T + 1, 4, dtype=i32, device=dev)
+        n_ws = env.lib.gcbf_rollout_workspace_floats(C.byref(self.desc))
+        self.ws = torch.empty(int(n_ws), dtype=f32, device=dev)
+        self.stream = None
+
+
 class RolloutEngine:
     def __init__(self, env, n_envs: int, T: Optional[int] = None, n_obs: Optional[int] = None,
-                 use_cuda_graph: bool = True, policy: str = "actor"):
-        """policy: 'actor' (a = 2 pi + u_ref, algo.step) or 'u_ref' (test.py --u-ref)."""
+                 use_cuda_graph: bool = True, policy: str = "actor", n_chains: Optional[int] = None):
+        """policy: 'actor' (a = 2 pi + u_ref, algo.step) or 'u_ref' (test.py --u-ref).
+        n_chains: the environments are split into independent chains that run as parallel branches of
+        the CUDA graph (each per-step kernel is latency-bound and fills a fraction of the 148 SMs, so
+        concurrent chains overlap their launch / tail latencies).  Results do not depend on it."""
         self.env = env
         self.E = n_envs
         self.T = T or env.max_episode_steps
@@ -38,16 +63,14 @@ class RolloutEngine:
         self.actions = torch.zeros(T, E, N, nu, dtype=f32, device=dev)
         self.rewards = torch.zeros(T, E, dtype=f32, device=dev)
         self.costs = torch.zeros(T, E, dtype=f32, device=dev)
-        self.pi = torch.zeros(E, N, nu, dtype=f32, device=dev)
-        self.desc = env.desc(E, self.O)
-        cap = self.desc.edge_cap
-        self.row_start = torch.zeros(E * N, dtype=i32, device=dev)
-        self.row_deg = torch.zeros(E * N, dtype=i32, device=dev)
-        self.edge_recv = torch.zeros(cap, dtype=i32, device=dev)
-        self.edge_src = torch.zeros(cap, dtype=i32, device=dev)
-        self.counters = torch.zeros(T + 1, 4, dtype=i32, device=dev)
-        n_ws = env.lib.gcbf_gnn_workspace_floats(C.byref(self.desc), nu)
-        self.ws = torch.empty(int(n_ws), dtype=f32, device=dev)
+        if n_chains is None:
+            n_chains = 1   # measured: no gain at fixed E (each chain's step latency does not shrink with its batch)
+        if not use_cuda_graph:
+            n_chains = 1
+        assert E % n_chains == 0
+        per = E // n_chains
+        self.chains = [_Chain(self, c * per, (c + 1) * per) for c in range(n_chains)]
+        self.desc = self.chains[0].desc
         self.params_buf = torch.zeros(_lib.param_count(env.edge_dim, nu), dtype=f32, device=dev)
         # folded inference weights (gcbf_prepare_infer), rebuilt by set_params()
         self.infer_blob = torch.zeros(int(env.lib.gcbf_infer_count(env.edge_dim, nu)), dtype=f32, device=dev)
@@ -56,42 +79,62 @@ class RolloutEngine:
         self.launches_per_run = 0
         self._obstacle_obj = None
 
+    @property
+    def counters(self) -> torch.Tensor:
+        """[T+1, 4]: per step total edge count (col 0) and overflow flag (col 1) over all chains."""
+        c = torch.stack([ch.counters for ch in self.chains])
+        return torch.stack([c[:, :, 0].sum(0), c[:, :, 1].amax(0), c[:, :, 2].sum(0), c[:, :, 3].sum(0)], dim=1)
+
     # ------------------------------------------------------------------ one env step (enqueue only)
-    def _build(self, t: int, stream: int) -> None:
-        env, d = self.env, self.desc
-        rc = env.lib.gcbf_graph_build(C.byref(d), self.agent[t].data_ptr(),
-                                      self.obstacles.data_ptr() if self.O > 0 else None, env.ray_table.data_ptr(),
-                                      self.hits[t].data_ptr(), self.row_start.data_ptr(), self.row_deg.data_ptr(),
-                                      self.edge_recv.data_ptr(), self.edge_src.data_ptr(),
-                                      self.counters[t].data_ptr(), 1, stream)
+    def _build(self, ch: _Chain, t: int, stream: int) -> None:
+        env, d = self.env, ch.desc
+        rc = env.lib.gcbf_graph_build(C.byref(d), self.agent[t, ch.e0].data_ptr(),
+                                      self.obstacles[ch.e0].data_ptr() if self.O > 0 else None,
+                                      env.ray_table.data_ptr(), self.hits[t, ch.e0].data_ptr(),
+                                      ch.row_start.data_ptr(), ch.row_deg.data_ptr(), ch.edge_recv.data_ptr(),
+                                      ch.edge_src.data_ptr(), ch.counters[t].data_ptr(), 1, stream)
         _lib.check(rc, "gcbf_graph_build")
 
-    def _step(self, t: int, stream: int) -> None:
-        env, d = self.env, self.desc
-        nu = env.action_dim
-        mode = 2
-        if self.policy == "actor":
-            rc = env.lib.gcbf_gnn_infer(C.byref(d), _lib.NET_ACTOR, nu, self.params_buf.data_ptr(),
-                                        self.infer_blob.data_ptr(), self.use_tc, self.agent[t].data_ptr(),
-                                        self.goal.data_ptr(), self.hits[t].data_ptr(),
-                                          self.row_start.data_ptr(), self.row_deg.data_ptr(),
-                                          self.edge_recv.data_ptr(), self.edge_src.data_ptr(),
-                                          self.counters[t].data_ptr(), 0, self.pi.data_ptr(), self.ws.data_ptr(),
-                                          self.ws.numel(), stream)
-            _lib.check(rc, "gcbf_gnn_infer")
-            mode = 0
-        rc = env.lib.gcbf_env_step(C.byref(d), self.agent[t].data_ptr(), self.goal.data_ptr(),
-                                   self.obstacles.data_ptr() if self.O > 0 else None, self.pi.data_ptr(),
-                                   self.row_start.data_ptr(), self.row_deg.data_ptr(), self.edge_src.data_ptr(),
-                                   self.actions[t].data_ptr(), self.agent[t + 1].data_ptr(),
-                                   self.rewards[t].data_ptr(), self.costs[t].data_ptr(), mode, stream)
+    def _step(self, ch: _Chain, t: int, stream: int) -> None:
+        env, d = self.env, ch.desc
+        obs = self.obstacles[ch.e0].data_ptr() if self.O > 0 else None
+        if self.policy == "actor":      # algo.step + env.step + get_graph(next) in one call (8 launches)
+            rc = env.lib.gcbf_rollout_step(
+                C.byref(d), self.params_buf.data_ptr(), self.infer_blob.data_ptr(), self.use_tc,
+                self.agent[t, ch.e0].data_ptr(), self.goal[ch.e0].data_ptr(), obs, env.ray_table.data_ptr(),
+                self.hits[t, ch.e0].data_ptr(), ch.row_start.data_ptr(), ch.row_deg.data_ptr(), ch.edge_recv.data_ptr(),
+                ch.edge_src.data_ptr(), ch.counters[t].data_ptr(), self.actions[t, ch.e0].data_ptr(),
+                self.agent[t + 1, ch.e0].data_ptr(), self.hits[t + 1, ch.e0].data_ptr(), ch.counters[t + 1].data_ptr(),
+                self.rewards[t, ch.e0:].data_ptr(), self.costs[t, ch.e0:].data_ptr(), ch.ws.data_ptr(), ch.ws.numel(),
+                stream)
+            _lib.check(rc, "gcbf_rollout_step")
+            return
+        rc = env.lib.gcbf_env_step(C.byref(d), self.agent[t, ch.e0].data_ptr(), self.goal[ch.e0].data_ptr(), obs,
+                                   None, ch.row_start.data_ptr(), ch.row_deg.data_ptr(), ch.edge_src.data_ptr(),
+                                   self.actions[t, ch.e0].data_ptr(), self.agent[t + 1, ch.e0].data_ptr(),
+                                   self.rewards[t, ch.e0:].data_ptr(), self.costs[t, ch.e0:].data_ptr(), 2, stream)
         _lib.check(rc, "gcbf_env_step")
-        self._build(t + 1, stream)
+        self._build(ch, t + 1, stream)
 
-    def _enqueue_all(self, stream: int) -> None:
-        self._build(0, stream)
+    def _enqueue_chain(self, ch: _Chain, stream: int) -> None:
+        self._build(ch, 0, stream)
         for t in range(self.T):
-            self._step(t, stream)
+            self._step(ch, t, stream)
+
+    def _enqueue_all(self) -> None:
+        dev = self.env.device
+        main = torch.cuda.current_stream(dev)
+        if len(self.chains) == 1:
+            self._enqueue_chain(self.chains[0], main.cuda_stream)
+            return
+        for ch in self.chains:                              # fork: parallel branches
+            if ch.stream is None:
+                ch.stream = torch.cuda.Stream(dev)
+            ch.stream.wait_stream(main)
+            with torch.cuda.stream(ch.stream):
+                self._enqueue_chain(ch, ch.stream.cuda_stream)
+        for ch in self.chains:                              # join
+            main.wait_stream(ch.stream)
 
     # ------------------------------------------------------------------ public
     def set_initial(self, agent0: torch.Tensor, goal: torch.Tensor, obstacle) -> None:
@@ -112,25 +155,28 @@ class RolloutEngine:
     def run(self, check: bool = True) -> None:
         """Run the T-step rollout from the current initial conditions (async)."""
         dev = self.env.device
-        self.counters.zero_()
+        for ch in self.chains:
+            ch.counters.zero_()
+        lib = self.env.lib
         if self.use_cuda_graph:
             if self._graph is None:
-                lib = self.env.lib
                 # warm-up outside capture (lazy module load, function attributes)
-                self._build(0, torch.cuda.current_stream(dev).cuda_stream)
-                self._step(0, torch.cuda.current_stream(dev).cuda_stream)
+                st = torch.cuda.current_stream(dev).cuda_stream
+                for ch in self.chains:
+                    self._build(ch, 0, st)
+                    self._step(ch, 0, st)
                 torch.cuda.synchronize(dev)
                 g = torch.cuda.CUDAGraph()
                 n0 = lib.gcbf_launch_count()
                 with torch.cuda.graph(g):
-                    self._enqueue_all(torch.cuda.current_stream(dev).cuda_stream)
+                    self._enqueue_all()
                 self.launches_per_run = int(lib.gcbf_launch_count() - n0)
                 self._graph = g
             self._graph.replay()
         else:
-            n0 = self.env.lib.gcbf_launch_count()
-            self._enqueue_all(torch.cuda.current_stream(dev).cuda_stream)
-            self.launches_per_run = int(self.env.lib.gcbf_launch_count() - n0)
+            n0 = lib.gcbf_launch_count()
+            self._enqueue_all()
+            self.launches_per_run = int(lib.gcbf_launch_count() - n0)
         if check:
             self.check_overflow()
 
@@ -138,7 +184,7 @@ class RolloutEngine:
         c = self.counters.cpu()
         if int(c[:, 1].max()) != 0:
             raise RuntimeError(f"edge capacity overflow during rollout: up to {int(c[:, 0].max())} edges > edge_cap="
-                               f"{self.desc.edge_cap}; raise env.edge_cap_per_agent")
+                               f"{self.desc.edge_cap} per chain; raise env.edge_cap_per_agent")
 
     def result(self) -> Rollout:
         """trainer/data.py Rollout in the reference's (b, T) order (views/transposes of the record)."""
@@ -147,7 +193,3 @@ class RolloutEngine:
                        obstacle=self._obstacle_obj, actions=self.actions.transpose(0, 1),
                        rewards=self.rewards.transpose(0, 1), costs=self.costs.transpose(0, 1), dones=dones,
                        log_pis=None, n_edges=self.counters[:, 0])
-
-    def final_graph(self) -> SwarmGraph:
-        return SwarmGraph(self.env, self.agent[self.T], self.goal, self._obstacle_obj, self.hits[self.T],
-                          self.row_start, self.row_deg, self.edge_recv, self.edge_src, self.counters[self.T])

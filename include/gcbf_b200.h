@@ -80,6 +80,8 @@ typedef struct gcbf_env_desc {
     float r_sq;             /* r**2 */
     float safe_agent;       /* safe_mask distance (4r; SI 2.5r) */
     float safe_obs;         /* safe_mask inflation (2r; SI 1.5r) */
+    float comm_sq_thr;      /* smallest fp32 a with sqrtf(a) >= comm_radius:  (sqrtf(x) < Rc) == (x < comm_sq_thr) */
+    float lidar_sq_thr;     /* same for lidar_radius */
     float v_lim;            /* state_lim on velocity components (inf if none) */
     float u_lim;            /* action_lim */
     float K[18];            /* LQR gain [nu, sd] row-major (u_ref), fp32 */
@@ -161,6 +163,23 @@ int32_t gcbf_env_step(const gcbf_env_desc* desc, const float* agent, const float
  * and env.u_ref (env/double_integrator.py:332-338, env/dubins_car.py:328-379). */
 int32_t gcbf_act(const gcbf_env_desc* desc, const float* agent, const float* goal, const float* pi,
                  float* action, void* stream);
+
+/* ---------------------------------------------------------------- fused rollout step (a8 body)
+ * One iteration of the scan body of rollout() (gcbfplus/trainer/utils.py:46-49): algo.step
+ * (algo/gcbf_plus.py:182-186) + env.step incl. get_graph of the next state
+ * (env/double_integrator.py:145-181) for the G envs of the batch, 8 kernel launches:
+ * policy forward with folded weights -> {tanh head, a = 2 pi + u_ref, clip, Euler, per-agent
+ * reward / cost terms} -> {LiDAR, neighbour lists of the next state, per-env reward / cost}.
+ * The edge lists are rebuilt in place for the next state; counters / next_counters are the
+ * 4-int counter blocks of the current / next graph.  workspace: gcbf_rollout_workspace_floats(). */
+int64_t gcbf_rollout_workspace_floats(const gcbf_env_desc* desc);
+int32_t gcbf_rollout_step(const gcbf_env_desc* desc, const float* actor_params, const float* infer_blob,
+                          int32_t use_tensor_cores, const float* agent, const float* goal,
+                          const float* obstacles, const float* ray_table, const float* hits,
+                          int32_t* row_start, int32_t* row_deg, int32_t* edge_recv, int32_t* edge_src,
+                          const int32_t* counters, float* action, float* next_agent, float* next_hits,
+                          int32_t* next_counters, float* reward, float* cost, float* workspace,
+                          int64_t workspace_floats, void* stream);
 
 /* ---------------------------------------------------------------- labels / masks (a9)
  * Replaces env.unsafe_mask / collision_mask / finish_mask / safe_mask

@@ -59,5 +59,17 @@ def test_error_reporting_without_gpu():
 
 def test_desc_struct_size_matches_header():
     from gcbfplus_b200 import _lib
-    # 8 int32 + 19 float + K[18] + A[36] + B[18]
-    assert ctypes.sizeof(_lib.EnvDesc) == 4 * (8 + 19 + 18 + 36 + 18)
+    # 8 int32 + 21 float + K[18] + A[36] + B[18]
+    assert ctypes.sizeof(_lib.EnvDesc) == 4 * (8 + 21 + 18 + 36 + 18)
+
+
+def test_sqrt_threshold_is_exact():
+    import numpy as np
+    from gcbfplus_b200 import _lib
+    for r in (0.5, 0.4, 0.1, 0.15000000000000002):
+        a = np.float32(_lib.sqrt_threshold(r))
+        r32 = np.float32(r)
+        below = np.nextafter(a, np.float32(0), dtype=np.float32)
+        assert np.sqrt(a) >= r32 and np.sqrt(below) < r32
+        xs = np.linspace(float(a) * 0.999, float(a) * 1.001, 20001).astype(np.float32)
+        assert np.array_equal(np.sqrt(xs) < r32, xs < a)

@@ -68,3 +68,21 @@ def _as_rollout_result(res):
          "obstacle": res.obstacle}
     return RolloutResult(g, res.actions.transpose(0, 1), res.rewards.transpose(0, 1), res.costs.transpose(0, 1),
                          res.dones.transpose(0, 1), {})
+
+
+def test_parallel_chains_give_identical_results():
+    """Splitting the environments into parallel CUDA-graph branches must not change any result."""
+    from gcbfplus_b200.trainer.rollout import RolloutEngine
+    env, g0 = _reset_scene("DoubleIntegrator", 16, 8, 3.0, 4, seed=4)
+    algo = product_algo(env, "DoubleIntegrator")
+    outs = []
+    for n_chains in (1, 4):
+        eng = RolloutEngine(env, 8, T=24, n_obs=4, n_chains=n_chains)
+        eng.set_params(algo.actor_params)
+        eng.set_initial(g0.agent, g0.goal, g0.obstacle)
+        eng.run()
+        torch.cuda.synchronize()
+        outs.append({k: getattr(eng, k).clone() for k in ("agent", "hits", "actions", "rewards", "costs")})
+        outs[-1]["n_edges"] = eng.counters[:, 0].clone()
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
