@@ -19,6 +19,7 @@ enum GemmEpi {
     EPI_BIAS_RELU = 1,  // C = relu(acc + bias (+ bias2))
     EPI_NONE = 2,       // C = acc
     EPI_RELU_MASK = 3,  // C = aux > 0 ? acc : 0      (backward through ReLU, aux = saved activation)
+    EPI_RELU_DOT = 4,   // C[m] = sum_n relu(acc + bias)[n] * aux[n] + bias2[0]   (tensor-core path only; N == BN)
 };
 
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 16, GEMM_THREADS = 256;

@@ -258,10 +258,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = quarter * 32 + lane;
             const int m = m0 + row;
+            float dot = 0.f;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                if (EPI == EPI_RELU_DOT) {   // gate logit: relu(acc + bias) . aux  (the row never leaves the SM)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        dot = fmaf(fmaxf(__uint_as_float(v[j]) + bias[c0 + j], 0.f), aux[c0 + j], dot);
+                    if (c0 + 32 == BN && m < M) C[m] = dot + bias2[0];
+                    continue;
+                }
                 if (m < M) {
                     const int n = n0 + c0;
                     float* crow = C + (size_t)m * N + n;
@@ -364,6 +372,7 @@ inline int32_t launch_bn(int epi, bool accum, const CUtensorMap& tmA, const CUte
             case EPI_BIAS_RELU: GCBF_TC_CASE(EPI_BIAS_RELU, false); break;
             case EPI_NONE: GCBF_TC_CASE(EPI_NONE, false); break;
             case EPI_RELU_MASK: GCBF_TC_CASE(EPI_RELU_MASK, false); break;
+            case EPI_RELU_DOT: GCBF_TC_CASE(EPI_RELU_DOT, false); break;
             default: set_error("bad epilogue"); return -1;
         }
     } else {
@@ -392,7 +401,7 @@ inline int32_t launch_gemm_tc(int epi, bool accum, const float* A, const float* 
     const int tiles_m = (rows + BM - 1) / BM;
     // a 256-wide layer over few row tiles is split into two 128-wide column tiles: twice the CTAs (more SMs
     // busy), half the weight traffic and MMA time per CTA, 3 pipeline stages instead of 2
-    const int bn = (N == 256 && 2 * tiles_m <= sm_count()) ? 128 : N;
+    const int bn = (N == 256 && 2 * tiles_m <= sm_count() && epi != EPI_RELU_DOT) ? 128 : N;
     CUtensorMap tmA, tmB, tmBl;
     if (int32_t r = make_map(&tmA, A, rc.cap, K, BM)) return r;
     if (int32_t r = make_map(&tmB, Bt_hi, N, K, bn)) return r;

@@ -326,10 +326,15 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
         if ((rc = check_launch("edge_l1_kernel"))) return rc;
     }
     if ((rc = gemm(EPI_BIAS, ws + W.x1, blob + I.w23, I.t_w23, 256, 128, blob + I.b23, nullptr, ws + W.msg, re))) return rc;
-    if ((rc = gemm(EPI_BIAS_RELU, ws + W.msg, P + L.w[L_ATT0], I.t_a1, 128, 128, P + L.b[L_ATT0], nullptr, ws + W.g1, re))) return rc;
+    if (use_tc) {   // gate MLP layer 1 + folded gate vector in the GEMM epilogue: logits straight into ATT
+        if ((rc = tc::launch_gemm_tc(EPI_RELU_DOT, false, ws + W.msg, blob + I.t_a1, blob + I.t_a1 + 128 * 128,
+                                     P + L.b[L_ATT0], blob + I.c23, ws + W.att, blob + I.a23, re, 128, 128, st))) return rc;
+    } else {
+        if ((rc = gemm(EPI_BIAS_RELU, ws + W.msg, P + L.w[L_ATT0], I.t_a1, 128, 128, P + L.b[L_ATT0], nullptr, ws + W.g1, re))) return rc;
+    }
     {
         const int grid = min((A + 7) / 8, 4 * nsm);
-        attn_aggregate_kernel<<<grid, 256, 0, st>>>(A, cap, ws + W.g1, ws + W.msg, blob + I.a23, blob + I.c23, row_start,
+        attn_aggregate_kernel<<<grid, 256, 0, st>>>(A, cap, use_tc ? nullptr : ws + W.g1, ws + W.msg, blob + I.a23, blob + I.c23, row_start,
                                                     row_deg, ws + W.att, ws + W.ag);
         count_launch();
         if ((rc = check_launch("attn_aggregate_kernel"))) return rc;

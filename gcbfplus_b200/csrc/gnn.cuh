@@ -147,23 +147,28 @@ attn_aggregate_kernel(const int A, const int edge_cap, const float* __restrict__
                       const float* __restrict__ a3, const float* __restrict__ ba3,
                       const int32_t* __restrict__ row_start, const int32_t* __restrict__ row_deg,
                       float* __restrict__ ATT, float* __restrict__ AG) {
+    // G2 == nullptr: ATT already holds the gate logits (written by the EPI_RELU_DOT GEMM epilogue)
     const int lane = threadIdx.x & 31;
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
-    const float4 w = *reinterpret_cast<const float4*>(a3 + lane * 4);
-    const float bias = ba3[0];
+    const float4 w = G2 ? *reinterpret_cast<const float4*>(a3 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float bias = G2 ? ba3[0] : 0.f;
     for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < A; a += warps_total) {
         const int rs = row_start[a];
         int rd = row_deg[a];
         if (rs < 0 || rs + rd > edge_cap) rd = 0;
         float mx = -INFINITY;
-        for (int e = rs; e < rs + rd; ++e) {
-            const float4 g = *reinterpret_cast<const float4*>(G2 + (size_t)e * 128 + lane * 4);
-            float s = g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
-            s = warp_sum(s) + bias;
-            if (lane == 0) ATT[e] = s;
-            mx = fmaxf(mx, s);
+        if (G2) {
+            for (int e = rs; e < rs + rd; ++e) {
+                const float4 g = *reinterpret_cast<const float4*>(G2 + (size_t)e * 128 + lane * 4);
+                float s = g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
+                s = warp_sum(s) + bias;
+                if (lane == 0) ATT[e] = s;
+                mx = fmaxf(mx, s);
+            }
+            __syncwarp();
+        } else {
+            for (int e = rs; e < rs + rd; ++e) mx = fmaxf(mx, ATT[e]);
         }
-        __syncwarp();
         float den = 0.f;
         for (int e = rs; e < rs + rd; ++e) den += expf(ATT[e] - mx);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
