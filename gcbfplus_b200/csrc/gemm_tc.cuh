@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(THREADS_NN, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                const __grid_constant__ CUtensorMap tmBl, const float* __restrict__ bias,
                const float* __restrict__ bias2, float* __restrict__ C, const float* __restrict__ aux,
-               const int32_t* __restrict__ m_ptr, const int m_fixed, const int m_cap, const int K, const int N) {
+               const int32_t* __restrict__ m_ptr, const int m_fixed, const int m_cap, const int K, const int N,
+               const int ndot) {
     using CF = Cfg<BN>;
     constexpr int STAGES = CF::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -259,10 +260,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int row = quarter * 32 + lane;
             const int m = m0 + row;
             float dot = 0.f;
+            float dq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                if (EPI == EPI_RELU_DOTN) {  // output layer partial sums over this column tile
+                    const float* hw = aux + (size_t)(n0 + c0) * ndot;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float h = fmaxf(__uint_as_float(v[j]) + bias[n0 + c0 + j], 0.f);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < ndot) dq[q] = fmaf(h, hw[j * ndot + q], dq[q]);
+                    }
+                    if (c0 + 32 == BN && m < M)
+                        *reinterpret_cast<float4*>(C + ((size_t)(n0 / BN) * m_cap + m) * 4) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+                    continue;
+                }
                 if (EPI == EPI_RELU_DOT) {   // gate logit: relu(acc + bias) . aux  (the row never leaves the SM)
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -354,7 +369,7 @@ template <int BN>
 inline int32_t launch_bn(int epi, bool accum, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBl,
                          const float* bias,
                          const float* bias2, float* C, const float* aux, RowCount rc, int K, int N, int grid,
-                         cudaStream_t st) {
+                         cudaStream_t st, int ndot = 0) {
     constexpr int smem = Cfg<BN>::SMEM_BYTES;
 #define GCBF_TC_CASE(E, ACC)                                                                                      \
     do {                                                                                                          \
@@ -364,7 +379,8 @@ inline int32_t launch_bn(int epi, bool accum, const CUtensorMap& tmA, const CUte
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                        \
             attr_done = true;                                                                                     \
         }                                                                                                         \
-        kern<<<grid, THREADS_NN, smem, st>>>(tmA, tmB, tmBl, bias, bias2, C, aux, rc.ptr, rc.fixed, rc.cap, K, N); \
+        kern<<<grid, THREADS_NN, smem, st>>>(tmA, tmB, tmBl, bias, bias2, C, aux, rc.ptr, rc.fixed, rc.cap, K, N, \
+                                             ndot);                                                               \
     } while (0)
     if (!accum) {
         switch (epi) {
@@ -373,6 +389,7 @@ inline int32_t launch_bn(int epi, bool accum, const CUtensorMap& tmA, const CUte
             case EPI_NONE: GCBF_TC_CASE(EPI_NONE, false); break;
             case EPI_RELU_MASK: GCBF_TC_CASE(EPI_RELU_MASK, false); break;
             case EPI_RELU_DOT: GCBF_TC_CASE(EPI_RELU_DOT, false); break;
+            case EPI_RELU_DOTN: GCBF_TC_CASE(EPI_RELU_DOTN, false); break;
             default: set_error("bad epilogue"); return -1;
         }
     } else {
@@ -391,7 +408,7 @@ inline int32_t launch_bn(int epi, bool accum, const CUtensorMap& tmA, const CUte
 // A must be backed by at least rc.cap rows.
 inline int32_t launch_gemm_tc(int epi, bool accum, const float* A, const float* Bt_hi, const float* Bt_lo,
                               const float* bias, const float* bias2, float* C, const float* aux, RowCount rc, int K,
-                              int N, cudaStream_t st) {
+                              int N, cudaStream_t st, int ndot = 0, int* parts_out = nullptr) {
     if (K % BK != 0 || (N != 128 && N != 256)) {
         set_error("gemm_tc: K=%d N=%d unsupported", K, N);
         return -1;
@@ -407,8 +424,9 @@ inline int32_t launch_gemm_tc(int epi, bool accum, const float* A, const float* 
     if (int32_t r = make_map(&tmB, Bt_hi, N, K, bn)) return r;
     if (int32_t r = make_map(&tmBl, Bt_lo, N, K, bn)) return r;
     const int grid = min(tiles_m * (N / bn), sm_count());
-    if (bn == 256) return launch_bn<256>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st);
-    return launch_bn<128>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st);
+    if (parts_out) *parts_out = N / bn;
+    if (bn == 256) return launch_bn<256>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st, ndot);
+    return launch_bn<128>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st, ndot);
 }
 
 

@@ -170,9 +170,10 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
             cost[blockIdx.y] = t[1] / (float)N + t[2] / (float)N;
         }
     }
+    constexpr int OBS2 = (PD == 2) ? 24 : 4;    // 2-D: packed rectangle + derived [14] reach^2, [15..18] edge dx, [19..22] edge dy
     float* spos = smem;                         // [N, PD]
-    float* sobs = spos + N * PD;                // [O, OBW]
-    float* stab = sobs + O * OBW;               // [n_rays, PD]
+    float* sobs = spos + N * PD;                // [O, OBS2]
+    float* stab = sobs + O * OBS2;              // [n_rays, PD]
     float* salpha = stab + d.n_rays * PD;       // 3-D only: [GB_WARPS, n_rays]
     const int n_words = (N + 31) / 32;
     unsigned* sbits = reinterpret_cast<unsigned*>(salpha + (PD == 3 ? GB_WARPS * d.n_rays : 0));  // [GB_WARPS, n_words]
@@ -188,13 +189,22 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
     }
     if (O > 0) {
         const float* ob = obstacles + (d.obs_per_graph ? (size_t)g * O * OBW : 0);
-        for (int i = tid; i < O * OBW; i += blockDim.x) sobs[i] = ob[i];
+        for (int i = tid; i < O * OBW; i += blockDim.x) sobs[(i / OBW) * OBS2 + (i % OBW)] = ob[i];
     }
     for (int i = tid; i < d.n_rays * PD; i += blockDim.x) stab[i] = ray_table[i];
     __syncthreads();
-    if (PD == 2) {   // slot 14 of a packed rectangle (padding): bounding radius, for the exact far-obstacle skip
-        for (int o = tid; o < O; o += blockDim.x)
-            sobs[16 * o + 14] = sqrtf(sobs[16 * o + 2] * sobs[16 * o + 2] + sobs[16 * o + 3] * sobs[16 * o + 3]);
+    if (PD == 2) {   // derived fields for the (conservative, exactness-preserving) far-obstacle skip
+        for (int o = tid; o < O; o += blockDim.x) {
+            float* ob = sobs + OBS2 * o;
+            const float reach = d.comm_radius + sqrtf(ob[2] * ob[2] + ob[3] * ob[3]) + 2e-3f;
+            ob[14] = reach * reach;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int kp = (k + 3) & 3;
+                ob[15 + k] = ob[6 + 2 * kp] - ob[6 + 2 * k];   // x4 - x3
+                ob[19 + k] = ob[7 + 2 * kp] - ob[7 + 2 * k];   // y4 - y3
+            }
+        }
         __syncthreads();
     }
 
@@ -209,40 +219,39 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
 
     // ---------------- LiDAR (env/utils.py:49-131)
     if (do_cast && valid) {
-        const bool is_in = (O > 0) ? inside_any<PD>(sobs, O, p, 0.f) : false;
-        const float keep = 1.f - (is_in ? 1.f : 0.f);
         if (PD == 2) {
             const bool ray_ok = lane < d.n_rays;
             const int rl = ray_ok ? lane : 0;
             const float x1 = p[0], y1 = p[1];
             const float x2 = x1 + stab[rl * 2 + 0], y2 = y1 + stab[rl * 2 + 1];
+            const float rdx = x1 - x2, rdy = y1 - y2;
             float alpha;
             if (O == 0) {
                 alpha = 1.f * NO_HIT;
             } else {
-                // A rectangle whose bounding circle is out of the ray's reach cannot be hit: every edge test gives
-                // valid = 0 and alpha = 0 * alpha + 1e6 = 1e6 exactly -- unless an edge is exactly parallel to the
-                // ray (det == 0 -> alpha = x/0 -> NaN in the reference, obstacle.py:88-94).  The skip below is
-                // therefore taken only when it is bit-identical to the full evaluation (agent-uniform branch).
+                // A rectangle whose bounding circle is out of the ray's reach cannot be hit or contain the agent:
+                // every edge test gives valid = 0 and alpha = 0 * alpha + 1e6 = 1e6 exactly -- unless an edge is
+                // exactly parallel to the ray (det == 0 -> alpha = x/0 -> NaN in the reference, obstacle.py:88-94).
+                // The skip is taken only when it is bit-identical to the full evaluation (agent-uniform branch).
                 alpha = NO_HIT;
+                bool is_in = false;
                 for (int o = 0; o < O; ++o) {
-                    const float* ob = sobs + 16 * o;
+                    const float* ob = sobs + OBS2 * o;
                     const float cx = x1 - ob[0], cy = y1 - ob[1];
-                    const bool far = sqrtf(cx * cx + cy * cy) > d.comm_radius + ob[14] + 1e-3f;
+                    const bool far = (cx * cx + cy * cy) > ob[14];
                     bool degenerate = false;
                     if (far) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const int kp = (k + 3) & 3;
-                            const float det = (x1 - x2) * (ob[7 + 2 * kp] - ob[7 + 2 * k]) -
-                                              (y1 - y2) * (ob[6 + 2 * kp] - ob[6 + 2 * k]);
-                            degenerate = degenerate || (det == 0.f) || isnan(det);
+                            const float det = rdx * ob[19 + k] - rdy * ob[15 + k];
+                            degenerate = degenerate || !(det != 0.f);   // det == 0 or NaN
                         }
                     }
+                    if (!far) is_in = is_in || rect_inside(ob, x1, y1, 0.f);
                     if (!far || __any_sync(0xffffffffu, degenerate))
                         alpha = nanmin(alpha, rect_raytrace(ob, x1, y1, x2, y2));
                 }
-                alpha = alpha * keep;
+                alpha = alpha * (1.f - (is_in ? 1.f : 0.f));
             }
             const float hx = x1 + (x2 - x1) * alpha;
             const float hy = y1 + (y2 - y1) * alpha;
@@ -250,7 +259,10 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
             k.flag = ray_ok ? (isnan(alpha) ? 1 : 0) : 2;
             k.alpha = alpha;
             k.idx = lane;
-            k = warp_sort32(k, lane);
+            // argsort is stable: when no ray of this agent hit anything (every alpha == 1e6) the order is the
+            // identity and the 15-stage warp sort can be skipped (warp-uniform, the common case in open space)
+            const bool all_miss = __all_sync(0xffffffffu, !ray_ok || alpha == NO_HIT);
+            if (!all_miss) k = warp_sort32(k, lane);
             const float shx = __shfl_sync(0xffffffffu, hx, k.idx);
             const float shy = __shfl_sync(0xffffffffu, hy, k.idx);
             if (lane < R) {
@@ -258,6 +270,8 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
                 my_hits[lane * 2 + 1] = shy;
             }
         } else {
+            const bool is_in = (O > 0) ? inside_any<PD>(sobs, O, p, 0.f) : false;
+            const float keep = 1.f - (is_in ? 1.f : 0.f);
             float* al = salpha + warp * d.n_rays;
             const float x1 = p[0], y1 = p[1], z1 = p[PD - 1];
             for (int r = lane; r < d.n_rays; r += 32) {
@@ -581,12 +595,13 @@ env_step_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const fl
 }
 
 // ------------------------------------------------------------------------------------
-// policy tail: pi = tanh(H1 @ HO + bHO) (policy.py:72), a = 2 pi + u_ref (gcbf_plus.py:182-186), clip_action,
-// agent_step_euler, per-agent reward / cost terms (double_integrator.py:145-198).  Warp per agent.
+// policy tail, thread per agent: pi = tanh(sum_parts z[part] + bHO) (policy.py:72; z = partial sums of the output
+// layer written by the EPI_RELU_DOTN GEMM epilogue or by head_z_kernel), a = 2 pi + u_ref (gcbf_plus.py:182-186),
+// clip_action, agent_step_euler, per-agent reward / cost terms (double_integrator.py:145-198).
 // ------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(256)
-policy_tail_kernel(const gcbf_env_desc d, const float* __restrict__ H1, const float* __restrict__ HO,
+__global__ void __launch_bounds__(128)
+policy_tail_kernel(const gcbf_env_desc d, const float* __restrict__ z, const int parts, const int z_cap,
                    const float* __restrict__ bHO, const float* __restrict__ agent, const float* __restrict__ goal,
                    const float* __restrict__ obstacles, const int32_t* __restrict__ row_start,
                    const int32_t* __restrict__ row_deg, const int32_t* __restrict__ edge_src,
@@ -594,65 +609,56 @@ policy_tail_kernel(const gcbf_env_desc d, const float* __restrict__ H1, const fl
     using T = EnvTraits<KIND>;
     constexpr int SD = T::SD, NU = T::NU, PD = T::PD;
     constexpr int OBW = (PD == 2) ? 16 : 4;
-    const int lane = threadIdx.x & 31;
     const int A = d.n_graphs * d.n_agents;
-    const int warps_total = (gridDim.x * blockDim.x) >> 5;
-    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < A; a += warps_total) {
-        const float4 h0 = *reinterpret_cast<const float4*>(H1 + (size_t)a * 256 + lane * 8);
-        const float4 h1 = *reinterpret_cast<const float4*>(H1 + (size_t)a * 256 + lane * 8 + 4);
-        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-        float pi[NU];
-#pragma unroll
-        for (int j = 0; j < NU; ++j) {
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s += hv[k] * HO[(lane * 8 + k) * NU + j];
-            pi[j] = tanhf(warp_sum(s) + bHO[j]);
-        }
-        if (lane != 0) continue;
-        const int g = a / d.n_agents;
-        float x[SD], gl[SD], ur[NU], u[NU], xn[SD];
-#pragma unroll
-        for (int c = 0; c < SD; ++c) {
-            x[c] = agent[(size_t)a * SD + c];
-            gl[c] = goal[(size_t)a * SD + c];
-        }
-        u_ref_dev<KIND>(d, x, gl, ur);
-        float sq = 0.f;
-#pragma unroll
-        for (int c = 0; c < NU; ++c) {
-            const float act = 2.f * pi[c] + ur[c];
-            action[(size_t)a * NU + c] = act;
-            u[c] = isnan(act) ? act : fminf(fmaxf(act, -d.u_lim), d.u_lim);
-            const float df = u[c] - ur[c];
-            sq = (c == 0) ? df * df : sq + df * df;
-        }
-        euler_dev<KIND>(d, x, gl, u, xn);
-#pragma unroll
-        for (int c = 0; c < SD; ++c) next_agent[(size_t)a * SD + c] = xn[c];
-        const float nr = sqrtf(sq);
-        bool col = false;
-        const int rs = row_start[a], rd = row_deg[a];
-        for (int e = rs + 1; e < rs + rd; ++e) {
-            const int s = edge_src[e];
-            if (s < 0) break;
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < PD; ++c) {
-                const float dlt = x[c] - agent[(size_t)s * SD + c];
-                acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
-            }
-            col = col || (d.two_r > sqrtf(acc));
-        }
-        bool in_obs = false;
-        if (d.n_obs > 0) {
-            const float* ob = obstacles + (d.obs_per_graph ? (size_t)g * d.n_obs * OBW : 0);
-            in_obs = inside_any<PD>(ob, d.n_obs, x, d.radius);
-        }
-        terms[a] = nr * nr;
-        terms[(size_t)A + a] = col ? 1.f : 0.f;
-        terms[(size_t)2 * A + a] = in_obs ? 1.f : 0.f;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p < parts; ++p) {
+        const float4 v = *reinterpret_cast<const float4*>(z + ((size_t)p * z_cap + a) * 4);
+        zz[0] += v.x; zz[1] += v.y; zz[2] += v.z; zz[3] += v.w;
     }
+    const int g = a / d.n_agents;
+    float x[SD], gl[SD], ur[NU], u[NU], xn[SD];
+#pragma unroll
+    for (int c = 0; c < SD; ++c) {
+        x[c] = agent[(size_t)a * SD + c];
+        gl[c] = goal[(size_t)a * SD + c];
+    }
+    u_ref_dev<KIND>(d, x, gl, ur);
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+        const float act = 2.f * tanhf(zz[c] + bHO[c]) + ur[c];
+        action[(size_t)a * NU + c] = act;
+        u[c] = isnan(act) ? act : fminf(fmaxf(act, -d.u_lim), d.u_lim);
+        const float df = u[c] - ur[c];
+        sq = (c == 0) ? df * df : sq + df * df;
+    }
+    euler_dev<KIND>(d, x, gl, u, xn);
+#pragma unroll
+    for (int c = 0; c < SD; ++c) next_agent[(size_t)a * SD + c] = xn[c];
+    const float nr = sqrtf(sq);
+    bool col = false;
+    const int rs = row_start[a], rd = row_deg[a];
+    for (int e = rs + 1; e < rs + rd; ++e) {
+        const int s = edge_src[e];
+        if (s < 0) break;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < PD; ++c) {
+            const float dlt = x[c] - agent[(size_t)s * SD + c];
+            acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
+        }
+        col = col || (d.two_r > sqrtf(acc));
+    }
+    bool in_obs = false;
+    if (d.n_obs > 0) {
+        const float* ob = obstacles + (d.obs_per_graph ? (size_t)g * d.n_obs * OBW : 0);
+        in_obs = inside_any<PD>(ob, d.n_obs, x, d.radius);
+    }
+    terms[a] = nr * nr;
+    terms[(size_t)A + a] = col ? 1.f : 0.f;
+    terms[(size_t)2 * A + a] = in_obs ? 1.f : 0.f;
 }
 
 // ------------------------------------------------------------------------------------
@@ -819,15 +825,14 @@ int32_t graph_build_impl(const gcbf_env_desc* desc, const float* agent, const fl
                          int32_t* counters, int32_t flags, const float* terms, float* reward, float* cost, void* stream);
 
 // policy tail launcher (used by gcbf_rollout_step in gnn.cu)
-int32_t policy_tail_impl(const gcbf_env_desc* desc, const float* H1, const float* HO, const float* bHO,
+int32_t policy_tail_impl(const gcbf_env_desc* desc, const float* z, int parts, int z_cap, const float* bHO,
                          const float* agent, const float* goal, const float* obstacles, const int32_t* row_start,
                          const int32_t* row_deg, const int32_t* edge_src, float* action, float* next_agent, float* terms,
                          cudaStream_t st) {
     const int A = desc->n_graphs * desc->n_agents;
-    const int grid = min((A + 7) / 8, 4 * sm_count());
     GCBF_DISPATCH_ENV(desc->env_kind, {
-        policy_tail_kernel<KIND><<<grid, 256, 0, st>>>(*desc, H1, HO, bHO, agent, goal, obstacles, row_start, row_deg,
-                                                       edge_src, action, next_agent, terms);
+        policy_tail_kernel<KIND><<<(A + 127) / 128, 128, 0, st>>>(*desc, z, parts, z_cap, bHO, agent, goal, obstacles,
+                                                                  row_start, row_deg, edge_src, action, next_agent, terms);
     });
     count_launch();
     return check_launch("policy_tail_kernel");
@@ -854,7 +859,7 @@ int32_t gcbf::graph_build_impl(const gcbf_env_desc* desc, const float* agent, co
     cudaStream_t st = (cudaStream_t)stream;
     const int pd = env_pd(desc->env_kind);
     const int obw = pd == 2 ? 16 : 4;
-    const size_t smem = sizeof(float) * ((size_t)desc->n_agents * pd + (size_t)desc->n_obs * obw +
+    const size_t smem = sizeof(float) * ((size_t)desc->n_agents * pd + (size_t)desc->n_obs * (pd == 2 ? 24 : 4) +
                                          (size_t)desc->n_rays * pd + (pd == 3 ? (size_t)GB_WARPS * desc->n_rays : 0) +
                                          (size_t)GB_WARPS * ((desc->n_agents + 31) / 32));
     GCBF_REQUIRE(smem <= 200 * 1024, "graph_build needs %zu B shared memory (> 200 KB): too many agents/obstacles", smem);

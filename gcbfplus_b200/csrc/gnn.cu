@@ -300,8 +300,10 @@ static int32_t prepare_infer_impl(int ed, int out_dim, const float* P, float* bl
 static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* blob, int use_tc,
                               const float* agent, const float* goal, const float* hits, const int32_t* row_start,
                               const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src,
-                              const int32_t* counters, int clip_all, float* out, float* ws, cudaStream_t st) {
-    // out == nullptr: stop after the last hidden layer (ws + W.h1); the caller applies the output layer
+                              const int32_t* counters, int clip_all, float* out, float* ws, cudaStream_t st,
+                              float* z_out = nullptr, int* z_parts = nullptr) {
+    // z_out != nullptr (rollout step): instead of `out`, write the output layer's pre-activation partial sums
+    // z[part][A][4] (no bias, no tanh) for policy_tail_kernel
     const int ed = env_ed(d->env_kind);
     const ParamLayout L = make_layout(ed, out_dim);
     const InferLayout I = make_infer_layout(out_dim);
@@ -341,6 +343,18 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
     }
     if ((rc = gemm(EPI_BIAS_RELU, ws + W.ag, P + L.w[L_UPD0] + 3 * 256, I.t_u1, 128, 256, P + L.b[L_UPD0],
                    P + L.w[L_UPD0] + 2 * 256, ws + W.v1, ra))) return rc;
+    if (z_out != nullptr) {
+        if (use_tc) {   // last hidden layer + output layer partial sums in the GEMM epilogue (h1 never leaves the SM)
+            return tc::launch_gemm_tc(EPI_RELU_DOTN, false, ws + W.v1, blob + I.t_uh, blob + I.t_uh + 256 * 256, blob + I.buh,
+                                      nullptr, z_out, blob + I.ho, ra, 256, 256, st, out_dim, z_parts);
+        }
+        if ((rc = gemm(EPI_BIAS_RELU, ws + W.v1, blob + I.uh, I.t_uh, 256, 256, blob + I.buh, nullptr, ws + W.h1, ra))) return rc;
+        const int grid = min((A + 7) / 8, 4 * nsm);
+        head_z_kernel<<<grid, 256, 0, st>>>(A, out_dim, ws + W.h1, blob + I.ho, z_out);
+        count_launch();
+        *z_parts = 1;
+        return check_launch("head_z_kernel");
+    }
     if ((rc = gemm(EPI_BIAS_RELU, ws + W.v1, blob + I.uh, I.t_uh, 256, 256, blob + I.buh, nullptr, ws + W.h1, ra))) return rc;
     if (out != nullptr) {
         const int grid = min((A + 7) / 8, 4 * nsm);
@@ -396,7 +410,7 @@ namespace gcbf {
 int32_t graph_build_impl(const gcbf_env_desc* desc, const float* agent, const float* obstacles, const float* ray_table,
                          float* hits, int32_t* row_start, int32_t* row_deg, int32_t* edge_recv, int32_t* edge_src,
                          int32_t* counters, int32_t flags, const float* terms, float* reward, float* cost, void* stream);
-int32_t policy_tail_impl(const gcbf_env_desc* desc, const float* H1, const float* HO, const float* bHO,
+int32_t policy_tail_impl(const gcbf_env_desc* desc, const float* z, int parts, int z_cap, const float* bHO,
                          const float* agent, const float* goal, const float* obstacles, const int32_t* row_start,
                          const int32_t* row_deg, const int32_t* edge_src, float* action, float* next_agent, float* terms,
                          cudaStream_t st);
@@ -416,7 +430,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step(
     const int nu = env_nu(desc->env_kind);
     const int64_t A = (int64_t)desc->n_graphs * desc->n_agents;
     const GnnWs W = make_ws(desc->edge_cap, A);
-    const int64_t need = W.total + 3 * A + 4;
+    const int64_t need = W.total + 3 * A + 8 * A + 8;
     GCBF_REQUIRE(workspace_floats >= need, "workspace too small: %lld < %lld floats", (long long)workspace_floats,
                  (long long)need);
     GCBF_REQUIRE((((uintptr_t)actor_params | (uintptr_t)workspace | (uintptr_t)infer_blob) & 15) == 0,
@@ -424,11 +438,13 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step(
     cudaStream_t st = (cudaStream_t)stream;
     const InferLayout I = make_infer_layout(nu);
     float* terms = workspace + ((W.total + 3) & ~(int64_t)3);
+    float* z = terms + ((3 * A + 3) & ~(int64_t)3);          // [2][A][4] output-layer partial sums
     int32_t rc;
+    int parts = 1;
     if ((rc = gnn_infer_impl(desc, nu, actor_params, infer_blob, use_tensor_cores, agent, goal, hits, row_start, row_deg,
-                             edge_recv, edge_src, counters, 0, nullptr, workspace, st))) return rc;
-    if ((rc = policy_tail_impl(desc, workspace + W.h1, infer_blob + I.ho, infer_blob + I.bho, agent, goal, obstacles,
-                               row_start, row_deg, edge_src, action, next_agent, terms, st))) return rc;
+                             edge_recv, edge_src, counters, 0, nullptr, workspace, st, z, &parts))) return rc;
+    if ((rc = policy_tail_impl(desc, z, parts, (int)A, infer_blob + I.bho, agent, goal, obstacles, row_start, row_deg,
+                               edge_src, action, next_agent, terms, st))) return rc;
     return graph_build_impl(desc, next_agent, obstacles, ray_table, next_hits, row_start, row_deg, edge_recv, edge_src,
                             next_counters, 1, terms, reward, cost, stream);
 }
@@ -436,5 +452,5 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step(
 extern "C" __attribute__((visibility("default"))) int64_t gcbf_rollout_workspace_floats(const gcbf_env_desc* desc) {
     if (!desc || desc->edge_cap <= 0 || desc->n_graphs <= 0 || desc->n_agents <= 0) return -1;
     const int64_t A = (int64_t)desc->n_graphs * desc->n_agents;
-    return make_ws(desc->edge_cap, A).total + 3 * A + 8;
+    return make_ws(desc->edge_cap, A).total + 3 * A + 8 * A + 16;
 }

@@ -186,6 +186,28 @@ attn_aggregate_kernel(const int A, const int edge_cap, const float* __restrict__
     }
 }
 
+// ---- output layer pre-activations z[a][0..3] = H @ W[256, nout] (no bias / tanh): SIMT-path producer of the
+// policy tail's input (the tensor-core path gets it from the EPI_RELU_DOTN epilogue).  Warp per agent.
+static __global__ void __launch_bounds__(256)
+head_z_kernel(const int A, const int nout, const float* __restrict__ H, const float* __restrict__ W,
+              float* __restrict__ z) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < A; a += warps_total) {
+        const float4 h0 = *reinterpret_cast<const float4*>(H + (size_t)a * 256 + lane * 8);
+        const float4 h1 = *reinterpret_cast<const float4*>(H + (size_t)a * 256 + lane * 8 + 4);
+        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        float out[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < nout; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = fmaf(hv[k], W[(lane * 8 + k) * nout + j], s);
+            out[j] = warp_sum(s);
+        }
+        if (lane == 0) *reinterpret_cast<float4*>(z + (size_t)a * 4) = make_float4(out[0], out[1], out[2], out[3]);
+    }
+}
+
 // ---- output head: out = tanh(H2 @ W[256, nout] + b); warp per agent.
 static __global__ void __launch_bounds__(256)
 head_out_kernel(const int A, const int nout, const float* __restrict__ H2, const float* __restrict__ W,
