@@ -2,6 +2,7 @@
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
 #include "gnn.cuh"
+#include "gemm_tc_prod.cuh"
 #include "translayout.cuh"
 
 using namespace gcbf;
@@ -318,31 +319,48 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
         if (use_tc) return tc::launch_gemm_tc(epi, false, X, blob + t_off, blob + t_off + K * N, bias, bias2, Y, nullptr, rows, K, N, st);
         return launch_gemm_nn(epi, false, X, Wf, bias, bias2, Y, nullptr, rows, K, N, st);
     };
-    {
-        const int grid = min((cap + 7) / 8, 4 * nsm);
-        GCBF_DISPATCH_ENV(d->env_kind, {
-            edge_l1_kernel<KIND><<<grid, 256, 0, st>>>(*d, P + L.w[L_MSG0], P + L.b[L_MSG0], agent, goal, hits,
-                                                       edge_recv, edge_src, counters, clip_all, ws + W.feat, ws + W.x1);
-        });
-        count_launch();
-        if ((rc = check_launch("edge_l1_kernel"))) return rc;
-    }
-    if ((rc = gemm(EPI_BIAS, ws + W.x1, blob + I.w23, I.t_w23, 256, 128, blob + I.b23, nullptr, ws + W.msg, re))) return rc;
-    if (use_tc) {   // gate MLP layer 1 + folded gate vector in the GEMM epilogue: logits straight into ATT
+    if (use_tc) {
+        // tensor-core path, 4 launches: {edge features + layer 1 produced in-kernel -> folded message GEMM},
+        // {gate layer + folded gate vector -> logits}, {softmax-aggregate produced in-kernel -> update layer 1},
+        // {update/head folded layer (+ output layer) below}
+        if ((rc = tc::launch_edge_msg(d, P + L.w[L_MSG0], P + L.b[L_MSG0], agent, goal, hits, edge_recv, edge_src, counters,
+                                      clip_all, blob + I.t_w23, blob + I.t_w23 + 256 * 128, blob + I.b23, ws + W.msg, st))) return rc;
         if ((rc = tc::launch_gemm_tc(EPI_RELU_DOT, false, ws + W.msg, blob + I.t_a1, blob + I.t_a1 + 128 * 128,
                                      P + L.b[L_ATT0], blob + I.c23, ws + W.att, blob + I.a23, re, 128, 128, st))) return rc;
+        // (measured: producing the aggregate inside the update GEMM (tc::launch_attn_upd) is slower than the
+        //  separate warp-per-receiver kernel + TMA-fed GEMM: 36.6 us vs 13.2 + 11.7 us -- its N-split repeats
+        //  the aggregation and the per-thread MSG gathers are latency-bound; the edge producer above is a win)
+        {
+            const int grid = min((A + 7) / 8, 4 * nsm);
+            attn_aggregate_kernel<<<grid, 256, 0, st>>>(A, cap, nullptr, ws + W.msg, blob + I.a23, blob + I.c23, row_start,
+                                                        row_deg, ws + W.att, ws + W.ag);
+            count_launch();
+            if ((rc = check_launch("attn_aggregate_kernel"))) return rc;
+        }
+        if ((rc = gemm(EPI_BIAS_RELU, ws + W.ag, P + L.w[L_UPD0] + 3 * 256, I.t_u1, 128, 256, P + L.b[L_UPD0],
+                       P + L.w[L_UPD0] + 2 * 256, ws + W.v1, ra))) return rc;
     } else {
+        {
+            const int grid = min((cap + 7) / 8, 4 * nsm);
+            GCBF_DISPATCH_ENV(d->env_kind, {
+                edge_l1_kernel<KIND><<<grid, 256, 0, st>>>(*d, P + L.w[L_MSG0], P + L.b[L_MSG0], agent, goal, hits,
+                                                           edge_recv, edge_src, counters, clip_all, ws + W.feat, ws + W.x1);
+            });
+            count_launch();
+            if ((rc = check_launch("edge_l1_kernel"))) return rc;
+        }
+        if ((rc = gemm(EPI_BIAS, ws + W.x1, blob + I.w23, I.t_w23, 256, 128, blob + I.b23, nullptr, ws + W.msg, re))) return rc;
         if ((rc = gemm(EPI_BIAS_RELU, ws + W.msg, P + L.w[L_ATT0], I.t_a1, 128, 128, P + L.b[L_ATT0], nullptr, ws + W.g1, re))) return rc;
+        {
+            const int grid = min((A + 7) / 8, 4 * nsm);
+            attn_aggregate_kernel<<<grid, 256, 0, st>>>(A, cap, ws + W.g1, ws + W.msg, blob + I.a23, blob + I.c23, row_start,
+                                                        row_deg, ws + W.att, ws + W.ag);
+            count_launch();
+            if ((rc = check_launch("attn_aggregate_kernel"))) return rc;
+        }
+        if ((rc = gemm(EPI_BIAS_RELU, ws + W.ag, P + L.w[L_UPD0] + 3 * 256, I.t_u1, 128, 256, P + L.b[L_UPD0],
+                       P + L.w[L_UPD0] + 2 * 256, ws + W.v1, ra))) return rc;
     }
-    {
-        const int grid = min((A + 7) / 8, 4 * nsm);
-        attn_aggregate_kernel<<<grid, 256, 0, st>>>(A, cap, use_tc ? nullptr : ws + W.g1, ws + W.msg, blob + I.a23, blob + I.c23, row_start,
-                                                    row_deg, ws + W.att, ws + W.ag);
-        count_launch();
-        if ((rc = check_launch("attn_aggregate_kernel"))) return rc;
-    }
-    if ((rc = gemm(EPI_BIAS_RELU, ws + W.ag, P + L.w[L_UPD0] + 3 * 256, I.t_u1, 128, 256, P + L.b[L_UPD0],
-                   P + L.w[L_UPD0] + 2 * 256, ws + W.v1, ra))) return rc;
     if (z_out != nullptr) {
         if (use_tc) {   // last hidden layer + output layer partial sums in the GEMM epilogue (h1 never leaves the SM)
             return tc::launch_gemm_tc(EPI_RELU_DOTN, false, ws + W.v1, blob + I.t_uh, blob + I.t_uh + 256 * 256, blob + I.buh,
