@@ -95,6 +95,22 @@ class GCBFPlus(MultiAgentController):
         """gcbf.py:209-212 -> [G, N, 1]."""
         return self.runner.forward(params or self.cbf_params, graph)
 
+    def get_qp_action(self, graph: SwarmGraph, relax_penalty: float = 1e3, cbf_params: Optional[NetParams] = None,
+                      qp_settings=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """gcbf_plus.py:299-352 for every graph of the batch: (u_opt [G, N, nu], relaxation r [G, N]).
+        relax_penalty is fixed at the reference's 1e3 in the kernel; qp_settings is accepted and ignored
+        (the device solver has its own iteration cap / tolerance, algo/train.py)."""
+        if relax_penalty != 1e3:
+            raise NotImplementedError("relax_penalty is compiled in (1e3, gcbf_plus.py:302)")
+        from .train import qp_labels
+        u, aux, _ = qp_labels(self, graph, params=cbf_params or self.cbf_params, with_aux=True)
+        return u, aux[..., 1]
+
+    def get_b_u_qp(self, b_graph: SwarmGraph, params: Optional[NetParams] = None) -> torch.Tensor:
+        """gcbf_plus.py:193-196."""
+        from .train import qp_labels
+        return qp_labels(self, b_graph, params=params or self.cbf_tgt_params)
+
     def update(self, rollout, step: int) -> dict:
         from .train import update as _update
         return _update(self, rollout, step)

@@ -182,9 +182,8 @@ def _cat(parts):
 
 def update(algo, rollout: Rollout, step: int) -> dict:
     """GCBFPlus.update (gcbf_plus.py:282-297) + sample_batch (:232-280) + update_nets (:198-230),
-    with the replay kept on the device.  QP action labels (get_qp_action, :299-352) are
-    a "next" row: until the batched QP solver lands, u_qp := u_ref(graph), the QP's
-    unconstrained minimiser."""
+    with the replay kept on the device.  Action labels: the CBF-QP of every graph in the
+    batch, solved on the device with the TARGET cbf (get_b_u_qp, :193-213) -- `batch_u_qp`."""
     env = algo._env
     if algo._trainer_state is None:
         algo._trainer_state = TrainState(algo)
@@ -205,8 +204,7 @@ def update(algo, rollout: Rollout, step: int) -> dict:
         algo.unsafe_buffer.append_graphs(new, new["unsafe"].any(dim=-1))
         batch = new
     n = batch["agent"].shape[0]
-    # u_qp labels (see docstring)
-    u_qp = batch_u_ref(algo, batch)
+    u_qp = batch_u_qp(algo, batch)
     n_mb = max(n // algo.batch_size, 1)
     info = {}
     for _ in range(algo.inner_epoch):
@@ -227,4 +225,57 @@ def batch_u_ref(algo, batch) -> torch.Tensor:
     d = env.desc(n, 0, edge_cap=1)
     _lib.check(env.lib.gcbf_act(C.byref(d), _lib.ptr(batch["agent"].contiguous()), _lib.ptr(batch["goal"].contiguous()),
                                 None, _lib.ptr(out), env._stream()), "gcbf_act")
+    return out
+
+
+# ------------------------------------------------------------------------------------ QP action labels
+QP_MAX_ITER = 4000      # accelerated dual iterations per graph (early exit on QP_TOL; typical 50-1000)
+QP_TOL = 1e-5           # projected dual-gradient residual
+
+
+def qp_labels(algo, graph: SwarmGraph, params=None, with_aux: bool = False, max_iter: int = QP_MAX_ITER,
+              tol: float = QP_TOL):
+    """get_qp_action vmapped over the graphs of `graph` (gcbf_plus.py:193-196, 299-352): u_qp [G, N, nu];
+    with_aux also returns (lam, r) [G, N, 2] and the iteration counts [G]."""
+    env = algo._env
+    lib = env.lib
+    G, N = graph.n_graphs, env.num_agents
+    d = env.desc(G, 0, edge_cap=graph.edge_recv.numel())
+    cache = algo.__dict__.setdefault("_qp_ws", {})
+    key = (G, d.edge_cap)
+    if cache.get("key") != key:
+        n = lib.gcbf_qp_workspace_floats(C.byref(d))
+        if n <= 0:
+            raise RuntimeError("gcbf_qp_workspace_floats failed")
+        cache["ws"] = None
+        cache["ws"] = torch.empty(int(n), dtype=torch.float32, device=env.device)
+        cache["key"] = key
+    ws = cache["ws"]
+    p = params if params is not None else algo.cbf_tgt_params
+    u_qp = torch.empty(G, N, env.action_dim, dtype=torch.float32, device=env.device)
+    aux = torch.empty(G, N, 2, dtype=torch.float32, device=env.device) if with_aux else None
+    iters = torch.empty(G, dtype=torch.int32, device=env.device) if with_aux else None
+    rc = lib.gcbf_qp_labels(C.byref(d), float(algo.alpha), 1 if _lib.USE_TC else 0, int(max_iter), float(tol),
+                            _lib.ptr(p.flat), _lib.ptr(graph.agent), _lib.ptr(graph.goal), _lib.ptr(graph.hits),
+                            _lib.ptr(graph.row_start), _lib.ptr(graph.row_deg), _lib.ptr(graph.edge_recv),
+                            _lib.ptr(graph.edge_src), _lib.ptr(graph.counters), _lib.ptr(u_qp), _lib.ptr(aux),
+                            _lib.ptr(iters), _lib.ptr(ws), ws.numel(), env._stream())
+    _lib.check(rc, "gcbf_qp_labels")
+    if with_aux:
+        return u_qp, aux, iters & 0x3FFFFFFF      # bit 30 flags the global-memory fallback of dense graphs
+    return u_qp
+
+
+def batch_u_qp(algo, batch, agents_per_chunk: int = 32768) -> torch.Tensor:
+    """update_nets' label pass (gcbf_plus.py:201-211): the reference cuts the batch into 8 chunks to bound the
+    dense QP memory; here the chunk only bounds the activation workspace."""
+    env = algo._env
+    n = batch["agent"].shape[0]
+    chunk = max(1, agents_per_chunk // env.num_agents)
+    out = torch.empty(n, env.num_agents, env.action_dim, dtype=torch.float32, device=env.device)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        g = env.get_graph(batch["agent"][lo:hi].contiguous(), batch["goal"][lo:hi].contiguous(), None,
+                          hits=batch["hits"][lo:hi].contiguous())
+        out[lo:hi] = qp_labels(algo, g)
     return out

@@ -273,6 +273,7 @@ head_out_bwd_kernel(const int A, const int nout, const float* __restrict__ H2, c
         dst[0] = make_float4(dh[0], dh[1], dh[2], dh[3]);
         dst[1] = make_float4(dh[4], dh[5], dh[6], dh[7]);
     }
+    if (!dW) return;   // data-only backward (QP labels): no parameter gradient
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         for (int j = 0; j < nout; ++j) atomicAdd(dW + (lane * 8 + k) * nout + j, wacc[k][j]);
@@ -325,6 +326,7 @@ attn_aggregate_bwd_kernel(const int A, const int edge_cap, const float* __restri
             accb += wd;
         }
     }
+    if (!da3) return;  // data-only backward
     atomicAdd(da3 + lane * 4 + 0, acc3.x);
     atomicAdd(da3 + lane * 4 + 1, acc3.y);
     atomicAdd(da3 + lane * 4 + 2, acc3.z);
@@ -375,7 +377,8 @@ __global__ void __launch_bounds__(256)
 edge_l1_bwd_x_kernel(const gcbf_env_desc d, const float* __restrict__ W1, const float* __restrict__ dY,
                      const float* __restrict__ agent, const float* __restrict__ goal, const float* __restrict__ hits,
                      const int32_t* __restrict__ edge_recv, const int32_t* __restrict__ edge_src,
-                     const int32_t* __restrict__ counters, const int clip_all, float* __restrict__ d_es) {
+                     const int32_t* __restrict__ counters, const int clip_all, float* __restrict__ d_es,
+                     float* __restrict__ je) {
     using T = EnvTraits<KIND>;
     constexpr int ED = T::ED, SD = T::SD, PD = T::PD;
     __shared__ __align__(16) float sW[ED][256];
@@ -413,6 +416,11 @@ edge_l1_bwd_x_kernel(const gcbf_env_desc d, const float* __restrict__ W1, const 
                 const float inv_n2 = 1.f / (nrm * nrm);
 #pragma unroll
                 for (int p = 0; p < PD; ++p) df[p] = coef * (df[p] - (er[p] - es[p]) * dotp * inv_n2);
+            }
+            if (je) {   // per-edge Jacobian block d out[recv] / d feat_e (QP labels): no reduction
+#pragma unroll
+                for (int c = 0; c < ED; ++c) je[(size_t)e * 8 + c] = df[c];
+                continue;
             }
 #pragma unroll
             for (int c = 0; c < ED; ++c) {
@@ -503,6 +511,7 @@ struct BwdArgs {
     const int32_t *row_start, *row_deg, *edge_recv, *edge_src, *counters;
     int clip_all;
     float* d_es;           // optional [A, ED] (accumulated) : gradient wrt the agents' edge states
+    float* je;             // optional [cap, 8]: per-edge d out[recv] / d feat_e instead of the d_es reduction
     int use_tc;            // 1: backward-data GEMMs on the tcgen05 path
 };
 
@@ -540,58 +549,61 @@ static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
     const float* fw = b.fw;
     float* gw = b.gw;
     int32_t rc;
+    const bool wgrad = b.G != nullptr;   // false: data-only backward (d network / d inputs), used by the QP labels
+    float* const Gz = b.G;
 #define RC(x) do { if ((rc = (x))) return rc; } while (0)
+#define WG(x) do { if (wgrad) RC(x); } while (0)
     // ---- output layer
     {
         const int grid = min((A + 7) / 8, 2 * nsm);
         head_out_bwd_kernel<<<grid, 256, 0, st>>>(A, b.out_dim, fw + W.h2, b.P + L.w[L_OUT], b.out, b.d_out, b.roww,
-                                                  gw + W.h2, b.G + L.w[L_OUT], b.G + L.b[L_OUT]);
+                                                  gw + W.h2, wgrad ? Gz + L.w[L_OUT] : nullptr, wgrad ? Gz + L.b[L_OUT] : nullptr);
         count_launch();
         RC(check_launch("head_out_bwd_kernel"));
     }
     // ---- head MLP
-    RC(dense_bwd_weight(b, fw + W.h1, 256, gw + W.h2, b.G + L.w[L_HEAD1], nullptr, ra, 256, 256, A, st));
-    RC(launch_colsum(gw + W.h2, b.G + L.b[L_HEAD1], b.roww, nullptr, ra, 256, A, st));
+    WG(dense_bwd_weight(b, fw + W.h1, 256, gw + W.h2, b.G + L.w[L_HEAD1], nullptr, ra, 256, 256, A, st));
+    WG(launch_colsum(gw + W.h2, b.G + L.b[L_HEAD1], b.roww, nullptr, ra, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_HEAD1, EPI_RELU_MASK, false, gw + W.h2, gw + W.h1, fw + W.h1, ra, st));
-    RC(dense_bwd_weight(b, fw + W.v3, 128, gw + W.h1, b.G + L.w[L_HEAD0], nullptr, ra, 128, 256, A, st));
-    RC(launch_colsum(gw + W.h1, b.G + L.b[L_HEAD0], b.roww, nullptr, ra, 256, A, st));
+    WG(dense_bwd_weight(b, fw + W.v3, 128, gw + W.h1, b.G + L.w[L_HEAD0], nullptr, ra, 128, 256, A, st));
+    WG(launch_colsum(gw + W.h1, b.G + L.b[L_HEAD0], b.roww, nullptr, ra, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_HEAD0, EPI_NONE, false, gw + W.h1, gw + W.v3, nullptr, ra, st));
     // ---- update MLP
-    RC(dense_bwd_weight(b, fw + W.v2, 256, gw + W.v3, b.G + L.w[L_UPDOUT], nullptr, ra, 256, 128, A, st));
-    RC(launch_colsum(gw + W.v3, b.G + L.b[L_UPDOUT], b.roww, nullptr, ra, 128, A, st));
+    WG(dense_bwd_weight(b, fw + W.v2, 256, gw + W.v3, b.G + L.w[L_UPDOUT], nullptr, ra, 256, 128, A, st));
+    WG(launch_colsum(gw + W.v3, b.G + L.b[L_UPDOUT], b.roww, nullptr, ra, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_UPDOUT, EPI_NONE, false, gw + W.v3, gw + W.v2, nullptr, ra, st));
-    RC(dense_bwd_weight(b, fw + W.v1, 256, gw + W.v2, b.G + L.w[L_UPD1], nullptr, ra, 256, 256, A, st));
-    RC(launch_colsum(gw + W.v2, b.G + L.b[L_UPD1], b.roww, nullptr, ra, 256, A, st));
+    WG(dense_bwd_weight(b, fw + W.v1, 256, gw + W.v2, b.G + L.w[L_UPD1], nullptr, ra, 256, 256, A, st));
+    WG(launch_colsum(gw + W.v2, b.G + L.b[L_UPD1], b.roww, nullptr, ra, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_UPD1, EPI_RELU_MASK, false, gw + W.v2, gw + W.v1, fw + W.v1, ra, st));
-    RC(dense_bwd_weight(b, fw + W.ag, 128, gw + W.v1, b.G + L.w[L_UPD0] + 3 * 256, nullptr, ra, 128, 256, A, st));
-    RC(launch_colsum(gw + W.v1, b.G + L.b[L_UPD0], b.roww, nullptr, ra, 256, A, st));
-    RC(launch_colsum(gw + W.v1, b.G + L.w[L_UPD0] + 2 * 256, b.roww, nullptr, ra, 256, A, st));  // agent one-hot row
+    WG(dense_bwd_weight(b, fw + W.ag, 128, gw + W.v1, b.G + L.w[L_UPD0] + 3 * 256, nullptr, ra, 128, 256, A, st));
+    WG(launch_colsum(gw + W.v1, b.G + L.b[L_UPD0], b.roww, nullptr, ra, 256, A, st));
+    WG(launch_colsum(gw + W.v1, b.G + L.w[L_UPD0] + 2 * 256, b.roww, nullptr, ra, 256, A, st));  // agent one-hot row
     RC(dense_bwd_data(b, L, TL, L_UPD0, EPI_NONE, false, gw + W.v1, gw + W.ag, nullptr, ra, st));
     // ---- attention + aggregation
     {
         const int grid = min((A + 7) / 8, 2 * nsm);
         attn_aggregate_bwd_kernel<<<grid, 256, 0, st>>>(A, cap, gw + W.ag, fw + W.msg, fw + W.g2, fw + W.att,
                                                         b.P + L.w[L_GATE], b.row_start, b.row_deg, b.roww, gw + W.msg,
-                                                        gw + W.g2, b.G + L.w[L_GATE], b.G + L.b[L_GATE]);
+                                                        gw + W.g2, wgrad ? Gz + L.w[L_GATE] : nullptr, wgrad ? Gz + L.b[L_GATE] : nullptr);
         count_launch();
         RC(check_launch("attn_aggregate_bwd_kernel"));
     }
     // ---- gate MLP (edge rows; dW weighted by the receiver's weight)
-    RC(dense_bwd_weight(b, fw + W.g1, 128, gw + W.g2, b.G + L.w[L_ATT1], b.edge_recv, re, 128, 128, A, st));
-    RC(launch_colsum(gw + W.g2, b.G + L.b[L_ATT1], b.roww, b.edge_recv, re, 128, A, st));
+    WG(dense_bwd_weight(b, fw + W.g1, 128, gw + W.g2, b.G + L.w[L_ATT1], b.edge_recv, re, 128, 128, A, st));
+    WG(launch_colsum(gw + W.g2, b.G + L.b[L_ATT1], b.roww, b.edge_recv, re, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_ATT1, EPI_RELU_MASK, false, gw + W.g2, gw + W.g1, fw + W.g1, re, st));
-    RC(dense_bwd_weight(b, fw + W.msg, 128, gw + W.g1, b.G + L.w[L_ATT0], b.edge_recv, re, 128, 128, A, st));
-    RC(launch_colsum(gw + W.g1, b.G + L.b[L_ATT0], b.roww, b.edge_recv, re, 128, A, st));
+    WG(dense_bwd_weight(b, fw + W.msg, 128, gw + W.g1, b.G + L.w[L_ATT0], b.edge_recv, re, 128, 128, A, st));
+    WG(launch_colsum(gw + W.g1, b.G + L.b[L_ATT0], b.roww, b.edge_recv, re, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_ATT0, EPI_NONE, true, gw + W.g1, gw + W.msg, nullptr, re, st));
     // ---- message MLP
-    RC(dense_bwd_weight(b, fw + W.x2, 256, gw + W.msg, b.G + L.w[L_MSGOUT], b.edge_recv, re, 256, 128, A, st));
-    RC(launch_colsum(gw + W.msg, b.G + L.b[L_MSGOUT], b.roww, b.edge_recv, re, 128, A, st));
+    WG(dense_bwd_weight(b, fw + W.x2, 256, gw + W.msg, b.G + L.w[L_MSGOUT], b.edge_recv, re, 256, 128, A, st));
+    WG(launch_colsum(gw + W.msg, b.G + L.b[L_MSGOUT], b.roww, b.edge_recv, re, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_MSGOUT, EPI_NONE, false, gw + W.msg, gw + W.x2, nullptr, re, st));
-    RC(dense_bwd_weight(b, fw + W.x1, 256, gw + W.x2, b.G + L.w[L_MSG1], b.edge_recv, re, 256, 256, A, st));
-    RC(launch_colsum(gw + W.x2, b.G + L.b[L_MSG1], b.roww, b.edge_recv, re, 256, A, st));
+    WG(dense_bwd_weight(b, fw + W.x1, 256, gw + W.x2, b.G + L.w[L_MSG1], b.edge_recv, re, 256, 256, A, st));
+    WG(launch_colsum(gw + W.x2, b.G + L.b[L_MSG1], b.roww, b.edge_recv, re, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_MSG1, EPI_RELU_MASK, false, gw + W.x2, gw + W.x1, fw + W.x1, re, st));
     // ---- edge layer 1
-    {
+    if (wgrad) {
         const int grid = min(max(cap / 64, 1), 4 * nsm);
         switch (ed) {
             case 2: edge_l1_bwd_w_kernel<2><<<grid, 256, 0, st>>>(cap, A, b.counters, gw + W.x1, fw + W.feat, b.edge_src, b.edge_recv, b.roww, b.G + L.w[L_MSG0], b.G + L.b[L_MSG0]); break;
@@ -601,15 +613,16 @@ static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
         count_launch();
         RC(check_launch("edge_l1_bwd_w_kernel"));
     }
-    if (b.d_es) {
+    if (b.d_es || b.je) {
         const int grid = min((cap + 7) / 8, 4 * nsm);
         GCBF_DISPATCH_ENV(d->env_kind, {
             edge_l1_bwd_x_kernel<KIND><<<grid, 256, 0, st>>>(*d, b.P + L.w[L_MSG0], gw + W.x1, b.agent, b.goal, b.hits,
-                                                             b.edge_recv, b.edge_src, b.counters, b.clip_all, b.d_es);
+                                                             b.edge_recv, b.edge_src, b.counters, b.clip_all, b.d_es, b.je);
         });
         count_launch();
         RC(check_launch("edge_l1_bwd_x_kernel"));
     }
+#undef WG
 #undef RC
     return 0;
 }
@@ -689,6 +702,42 @@ __global__ void adamw_advance_kernel(const float* __restrict__ norm_info, int32_
 __global__ void polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, const int n, const float tau) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         tgt[i] = tau * src[i] + (1.f - tau) * tgt[i];
+}
+
+}  // namespace gcbf
+#include "qp.cuh"
+namespace gcbf {
+
+// ------------------------------------------------------------------------------------ QP label workspace layout
+struct QpWs {
+    int64_t ws0, gws, pt_cbf, h, ones, je, qb, qs, qe, ur, qsc, rev, total;
+};
+static QpWs make_qp_ws(const gcbf_env_desc* d) {
+    const int ed = env_ed(d->env_kind);
+    const int64_t A = (int64_t)d->n_graphs * d->n_agents, cap = d->edge_cap;
+    const GnnWs W = make_ws(d->edge_cap, A);
+    const ParamLayout Lc = make_layout(ed, 1);
+    QpWs t;
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t r = o; o += (n + 3) & ~(int64_t)3; return r; };
+    t.ws0 = take(W.total);
+    t.gws = take(W.total);
+    t.pt_cbf = take(make_prepared_layout(Lc, make_trans_layout(Lc)).total);
+    t.h = take(A);
+    t.ones = take(A);
+    t.je = take(cap * 8);
+    t.qb = take(A);
+    t.qs = take(A * 4);
+    t.qe = take(cap * 4);
+    t.ur = take(A * 4);
+    t.qsc = take(A);
+    t.rev = take(cap);
+    t.total = o;
+    return t;
+}
+
+__global__ void fill_kernel(float* __restrict__ p, const int n, const float v) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
 }
 
 // ------------------------------------------------------------------------------------ train workspace layout
@@ -846,6 +895,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
     b.G = grad_cbf;
     b.clip_all = 1;
     b.d_es = ws + TW.d_es;
+    b.je = nullptr;
     b.use_tc = use_tc;
     RC(gnn_backward_impl(b, st));
     // ---- through the Euler step / clips into the policy output
@@ -915,4 +965,117 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_polyak(float* tgt
     polyak_kernel<<<min((n + 1023) / 1024, 2 * sm_count()), 256, 0, (cudaStream_t)stream>>>(tgt, src, n, tau);
     count_launch();
     return check_launch("polyak_kernel");
+}
+
+// ------------------------------------------------------------------------------------ QP action labels
+extern "C" __attribute__((visibility("default"))) int64_t gcbf_qp_workspace_floats(const gcbf_env_desc* desc) {
+    if (!desc || desc->edge_cap <= 0 || desc->n_graphs <= 0 || desc->n_agents <= 0 || desc->env_kind < 0 ||
+        desc->env_kind > 3)
+        return -1;
+    return make_qp_ws(desc).total;
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_qp_workspace_layout(const gcbf_env_desc* desc,
+                                                                                   int64_t* offsets8_host) {
+    GCBF_REQUIRE(desc && offsets8_host && desc->edge_cap > 0 && desc->n_graphs > 0 && desc->n_agents > 0 &&
+                     desc->env_kind >= 0 && desc->env_kind <= 3, "gcbf_qp_workspace_layout: bad argument");
+    const QpWs Q = make_qp_ws(desc);
+    const int64_t o[8] = {Q.h, Q.je, Q.qb, Q.qs, Q.qe, Q.ur, Q.qsc, Q.rev};
+    for (int i = 0; i < 8; ++i) offsets8_host[i] = o[i];
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_qp_labels(
+    const gcbf_env_desc* desc, float alpha, int32_t use_tensor_cores, int32_t max_iter, float tol,
+    const float* cbf_params, const float* agent, const float* goal, const float* hits, const int32_t* row_start,
+    const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src, const int32_t* counters, float* u_qp,
+    float* aux, int32_t* iters, float* workspace, int64_t workspace_floats, void* stream) {
+    GCBF_REQUIRE(desc && cbf_params && agent && goal && hits && row_start && row_deg && edge_recv && edge_src &&
+                     counters && u_qp && workspace, "gcbf_qp_labels: NULL pointer argument");
+    GCBF_REQUIRE(desc->env_kind >= 0 && desc->env_kind <= 3 && desc->edge_cap > 0 && desc->n_graphs > 0 &&
+                     desc->n_agents > 0, "gcbf_qp_labels: bad descriptor");
+    GCBF_REQUIRE(desc->n_agents <= QP_MAX_AGENTS, "gcbf_qp_labels: n_agents %d > %d not supported", desc->n_agents,
+                 QP_MAX_AGENTS);
+    GCBF_REQUIRE(max_iter > 0 && tol >= 0.f, "gcbf_qp_labels: bad solver settings");
+    const QpWs Q = make_qp_ws(desc);
+    GCBF_REQUIRE(workspace_floats >= Q.total, "qp workspace too small: %lld < %lld floats", (long long)workspace_floats,
+                 (long long)Q.total);
+    GCBF_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)cbf_params & 15) == 0, "buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const gcbf_env_desc* d = desc;
+    const int ed = env_ed(d->env_kind), nu = env_nu(d->env_kind);
+    const int A = d->n_graphs * d->n_agents, N = d->n_agents;
+    const ParamLayout Lc = make_layout(ed, 1);
+    float* ws = workspace;
+    int32_t rc;
+#define RC(x) do { if ((rc = (x))) return rc; } while (0)
+    if (use_tensor_cores) RC(build_prepared(Lc, cbf_params, ws + Q.pt_cbf, st));
+    else RC(build_transposes(Lc, make_trans_layout(Lc), cbf_params, ws + Q.pt_cbf, st));
+    // h = cbf(add_edge_feats(graph, x)): every edge feature norm-clipped (gcbf_plus.py:310-316)
+    RC(gnn_forward_impl(d, 1, cbf_params, use_tensor_cores ? ws + Q.pt_cbf : nullptr, agent, goal, hits, row_start, row_deg,
+                        edge_recv, edge_src, counters, 1, ws + Q.h, ws + Q.ws0, st));
+    fill_kernel<<<min((A + 255) / 256, 2 * sm_count()), 256, 0, st>>>(ws + Q.ones, A, 1.f);
+    count_launch();
+    RC(check_launch("fill_kernel"));
+    // Jacobian: data-only backward with upstream 1, kept per edge
+    BwdArgs b;
+    b.d = d;
+    b.out_dim = 1;
+    b.P = cbf_params;
+    b.PT = ws + Q.pt_cbf;
+    b.fw = ws + Q.ws0;
+    b.gw = ws + Q.gws;
+    b.out = ws + Q.h;
+    b.d_out = ws + Q.ones;
+    b.roww = nullptr;
+    b.G = nullptr;
+    b.agent = agent;
+    b.goal = goal;
+    b.hits = hits;
+    b.row_start = row_start;
+    b.row_deg = row_deg;
+    b.edge_recv = edge_recv;
+    b.edge_src = edge_src;
+    b.counters = counters;
+    b.clip_all = 1;
+    b.d_es = nullptr;
+    b.je = ws + Q.je;
+    b.use_tc = use_tensor_cores;
+    RC(gnn_backward_impl(b, st));
+    int32_t* rev = reinterpret_cast<int32_t*>(ws + Q.rev);
+    GCBF_DISPATCH_ENV(d->env_kind, {
+        qp_assemble_kernel<KIND><<<(A + 127) / 128, 128, 0, st>>>(*d, alpha, agent, goal, ws + Q.h, ws + Q.je, row_start,
+                                                                  row_deg, edge_src, ws + Q.qb, ws + Q.qs, ws + Q.qe,
+                                                                  ws + Q.ur, ws + Q.qsc, rev);
+    });
+    count_launch();
+    RC(check_launch("qp_assemble_kernel"));
+    const int nt = min(1024, (N + 31) / 32 * 32);
+    // compacted agent-agent blocks per graph kept in shared memory: N (N - 1) at most, 24 per agent is generous for
+    // radius graphs, and whatever fits under the 227 KB limit; denser graphs iterate on the global edge list.
+    int nbr_cap = (int)min((int64_t)N * (N - 1), (int64_t)24 * N);
+    const size_t smem_base = qp_solve_smem(N, nu, 0), entry = sizeof(int) + 2 * nu * sizeof(float);
+    const size_t smem_max = 200 * 1024;
+    if (smem_base + (size_t)nbr_cap * entry > smem_max) nbr_cap = (int)((smem_max - smem_base) / entry);
+    nbr_cap = max(nbr_cap, 1);
+    const size_t smem = qp_solve_smem(N, nu, nbr_cap);
+    cudaError_t e;
+#define QP_LAUNCH(NUv)                                                                                                  \
+    do {                                                                                                                \
+        if ((e = cudaFuncSetAttribute(qp_solve_kernel<NUv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=  \
+            cudaSuccess) {                                                                                              \
+            set_error("cudaFuncSetAttribute(qp_solve_kernel): %s", cudaGetErrorString(e));                              \
+            return (int32_t)e;                                                                                          \
+        }                                                                                                               \
+        qp_solve_kernel<NUv><<<d->n_graphs, nt, smem, st>>>(N, d->edge_cap, nbr_cap, d->u_lim, max_iter, tol, ws + Q.qb,  \
+                                                            ws + Q.qs, ws + Q.qe, ws + Q.ur, ws + Q.qsc, rev, row_start, \
+                                                            row_deg, edge_src, u_qp, aux, iters);                       \
+    } while (0)
+    if (nu == 2) QP_LAUNCH(2);
+    else QP_LAUNCH(3);
+#undef QP_LAUNCH
+    count_launch();
+    RC(check_launch("qp_solve_kernel"));
+#undef RC
+    return 0;
 }

@@ -233,6 +233,32 @@ int32_t gcbf_clip_adamw(float* params, const float* grad, float* m, float* v, in
 /* tgt <- tau * src + (1 - tau) * tgt  (GCBFPlus.update_tgt, gcbf_plus.py:188-191). */
 int32_t gcbf_polyak(float* tgt, const float* src, int32_t n, float tau, void* stream);
 
+/* ---------------------------------------------------------------- QP action labels (f1)
+ * gcbf_qp_labels replaces GCBFPlus.get_b_u_qp / get_qp_action (gcbfplus/algo/gcbf_plus.py:193-196,
+ * 299-352; the JaxProxQP solve at :341-346) for a batch of graphs: per graph
+ *   min_{u,r} 1/2|u|^2 - u_ref.u + 5|r|^2 + 1000 sum(r)
+ *   s.t.  -Lg_h u - r <= Lf_h + 0.1 alpha h,   -u_lim <= u <= u_lim,   r >= 0
+ * with h = cbf(add_edge_feats(graph, x)) (all edge features norm-clipped), h_x its Jacobian wrt the
+ * agent states (one data-only backward pass kept per edge: h is a one-layer GNN, so row i touches
+ * only agent i and its neighbours), f, g = env.control_affine_dyn.  Solved exactly (unique
+ * minimiser) by an accelerated projected-gradient ascent on the dual, one CTA per graph.
+ *   cbf_params: the parameters to label with (the reference passes the TARGET network, :210)
+ *   max_iter / tol: iteration cap and stopping threshold on the projected dual-gradient residual
+ *   u_qp [G, N, nu] (out);  aux [G, N, 2] = (multiplier lam, relaxation r) or NULL;  iters [G] or NULL
+ *     (iteration count; bit 30 set when the graph was too dense for the shared-memory path)
+ *   workspace: gcbf_qp_workspace_floats(desc) floats;  n_agents <= 2048.
+ * gcbf_qp_workspace_layout: float offsets inside the workspace of the assembled QP (test hook):
+ *   0 h[A]  1 JE[cap,8] (d h_recv / d feat_e)  2 b[A]  3 Lg_self[A,4]  4 Lg_edge[cap,4]  5 u_ref[A,4]
+ *   6 row scale[A]  7 mirror-edge index[cap] (int32). */
+int64_t gcbf_qp_workspace_floats(const gcbf_env_desc* desc);
+int32_t gcbf_qp_workspace_layout(const gcbf_env_desc* desc, int64_t* offsets8_host);
+int32_t gcbf_qp_labels(const gcbf_env_desc* desc, float alpha, int32_t use_tensor_cores, int32_t max_iter,
+                       float tol, const float* cbf_params, const float* agent, const float* goal,
+                       const float* hits, const int32_t* row_start, const int32_t* row_deg,
+                       const int32_t* edge_recv, const int32_t* edge_src, const int32_t* counters,
+                       float* u_qp, float* aux, int32_t* iters, float* workspace, int64_t workspace_floats,
+                       void* stream);
+
 /* ---------------------------------------------------------------- dense-layer building blocks
  * The fp32 GEMM family the MLPs are made of (flax nn.Dense, gcbfplus/nn/mlp.py:19-21, and its
  * autodiff transposes).  Exported so the kernels can be unit-tested against a plain fp32

@@ -195,3 +195,76 @@ def test_rollout_and_rates_smoke():
     assert out["states"].shape == (9, N, 4) and out["actions"].shape == (8, N, 2)
     s, f, ok = rates(out["collision"].numpy(), out["finish"].numpy())
     assert 0.0 <= s <= 1.0 and 0.0 <= f <= 1.0 and ok <= min(s, f) + 1e-9
+
+
+# ------------------------------------------------------------------------------------ QP action labels
+def _qp_case(env_id, N, area, seed, dtype=torch.float64):
+    from oracle import qp
+    agent, goal, obs = random_scene(env_id, N, 1, area, 4, seed)
+    oenv = oracle_env(env_id, N, area, 4, dtype=dtype)
+    from helpers import product_obstacles
+    pobs = product_obstacles(env_id, obs, device="cpu")
+    oobs = oracle_obstacles(pobs.packed.numpy()[0], dtype=dtype)
+    _, cp = oracle_params(env_id, dtype)
+    g = oenv.sparsify(oenv.get_graph(torch.tensor(agent[0], dtype=dtype), torch.tensor(goal[0], dtype=dtype), oobs))
+    return oenv, cp, g, qp.qp_data(oenv, cp, g, 1.0)
+
+
+@pytest.mark.parametrize("env_id,N,area", [("SingleIntegrator", 8, 0.8), ("DoubleIntegrator", 12, 1.2),
+                                           ("DubinsCar", 8, 1.0), ("LinearDrone", 8, 0.9)])
+def test_qp_dual_solver_matches_active_set_and_kkt(env_id, N, area):
+    """The dual solver (the algorithm the CUDA kernel runs) against SciPy's SLSQP on the primal, and against
+    the KKT conditions: the QP is strictly convex, so both pin the unique minimiser (oracle/qp.py header)."""
+    from oracle import qp
+    oenv, cp, g, d = _qp_case(env_id, N, area, seed=11)
+    u, r, lam, it = qp.solve_qp_dual(d["Lg_h"], d["b"], d["u_ref"], d["u_lim"])
+    assert it < 100000
+    kkt = qp.kkt_residual(d["Lg_h"], d["b"], d["u_ref"], d["u_lim"], u, r, lam)
+    assert max(kkt.values()) < 1e-6, kkt      # complementarity is lam * slack with lam up to ~1e3
+    us, rs, res = qp.solve_qp_slsqp(d["Lg_h"], d["b"], d["u_ref"], d["u_lim"])
+    np.testing.assert_allclose(u, us, atol=1e-6)
+    np.testing.assert_allclose(r, rs, atol=1e-6)
+    assert (lam > 0).sum() >= 1, "scene too easy: no CBF constraint active"
+    # the label differs from u_ref exactly where a constraint is active
+    assert np.abs(u - np.clip(d["u_ref"], -d["u_lim"], d["u_lim"])).max() > 1e-3
+
+
+def test_qp_jacobian_is_graph_sparse_and_matches_finite_differences():
+    """h is a one-layer GNN: d h_i / d x_j is non-zero only for j = i or an agent neighbour j -> i (the
+    structure the CUDA path stores on the edge list); central differences confirm the autograd Jacobian."""
+    from oracle import qp
+    from oracle.algo import get_cbf
+    oenv, cp, g, d = _qp_case("DoubleIntegrator", 10, 1.5, seed=5)
+    N = 10
+    hx = d["h_x"]
+    nbr = np.eye(N, dtype=bool)
+    for r_, s_ in zip(g.receivers.numpy(), g.senders.numpy()):
+        if s_ < N:
+            nbr[r_, s_] = True
+    assert np.abs(hx[~nbr]).max() == 0.0
+    assert np.abs(hx[nbr]).max() > 1e-3
+    rest = g.states[N:]
+    x0 = g.states[:N].clone()
+
+    def h_of(x):
+        with torch.no_grad():
+            return get_cbf(cp, oenv.add_edge_feats(g, torch.cat([x, rest], 0))).squeeze(-1).numpy()
+    eps = 1e-6
+    for (j, c) in [(0, 0), (3, 2), (7, 1), (9, 3)]:
+        xp, xm = x0.clone(), x0.clone()
+        xp[j, c] += eps
+        xm[j, c] -= eps
+        np.testing.assert_allclose((h_of(xp) - h_of(xm)) / (2 * eps), hx[:, j, c], atol=1e-6)
+
+
+def test_qp_relaxation_engages_when_infeasible():
+    """A constraint no admissible u can satisfy is relaxed: lam sits above the 1e3 penalty and r > 0 makes the
+    row feasible with equality (gcbf_plus.py:329-339)."""
+    from oracle import qp
+    Lg = np.array([[1.0, 0.0], [0.0, 0.5]])
+    b = np.array([-5.0, 0.3])            # row 0 needs u0 >= 5 with |u| <= 1
+    u_ref = np.array([0.2, -0.1])
+    u, r, lam, _ = qp.solve_qp_dual(Lg, b, u_ref, 1.0)
+    assert u[0] == 1.0 and abs(r[0] - 4.0) < 1e-9 and abs(lam[0] - (1000 + 10 * 4.0)) < 1e-6
+    assert r[1] == 0.0 and lam[1] == 0.0 and abs(u[1] + 0.1) < 1e-12
+    assert max(qp.kkt_residual(Lg, b, u_ref, 1.0, u, r, lam).values()) < 1e-8
