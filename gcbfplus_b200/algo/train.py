@@ -205,7 +205,11 @@ def update(algo, rollout: Rollout, step: int) -> dict:
         batch = new
     n = batch["agent"].shape[0]
     u_qp = batch_u_qp(algo, batch)
-    n_mb = max(n // algo.batch_size, 1)
+    # sharded run: this rank holds 1/world of the environments, so its share of every batch_size-graph minibatch
+    # is batch_size / world graphs (same number of minibatches, hence of collectives, on every rank)
+    dist = _dist()
+    world = dist.get_world_size() if dist is not None else 1
+    n_mb = max(n // max(algo.batch_size // world, 1), 1)
     info = {}
     for _ in range(algo.inner_epoch):
         idx = torch.from_numpy(algo.rng.permutation(n)).to(env.device)

@@ -17,6 +17,7 @@ import scipy.linalg
 import torch
 
 from .. import _lib
+from ..utils import jrandom as jr
 from ..utils.graph import SwarmGraph
 from .obstacle import Rectangle, Sphere
 
@@ -240,96 +241,151 @@ class MultiAgentEnv(ABC):
         return torch.minimum(torch.maximum(action, lo.to(action.device)), up.to(action.device))
 
     # ------------------------------------------------------------------ obstacles / reset
-    def _sample_obstacles(self, rng: np.random.Generator, n_envs: int):
-        """double_integrator.py:86-101 (Rectangle) / linear_drone.py:95-104 (Sphere)."""
+    # The reference's reset draws from jax.random (threefry); utils/jrandom.py restates those draws on the host
+    # so that a seed gives the reference's scenario.  Everything below is vectorised over the
+    # environments (the reference vmaps reset over per-env keys, trainer/trainer.py:84-85,134-136).
+    def _sample_obstacles(self, keys: np.ndarray):
+        """double_integrator.py:86-101 (Rectangle) / linear_drone.py:95-104 (Sphere).
+        keys [E, 2] -> (obstacles, keys' [E, 2]) with the reference's split order."""
         O, L = self._params["n_obs"], self.area_size
         lo, hi = self._params["obs_len_range"]
+        k = jr.split(keys, 2)
+        obstacle_key, key = k[:, 0], k[:, 1]
         if self.pos_dim == 2:
-            pos = rng.uniform(0, L, size=(n_envs, O, 2))
-            ln = rng.uniform(lo, hi, size=(n_envs, O, 2))
-            th = rng.uniform(0, 2 * np.pi, size=(n_envs, O))
-            return Rectangle.create(pos, ln[..., 0], ln[..., 1], th, device=self.device)
-        pos = rng.uniform(0, L, size=(n_envs, O, 3))
-        rad = rng.uniform(lo / 2, hi / 2, size=(n_envs, O))
-        return Sphere.create(pos, rad, device=self.device)
+            pos = jr.uniform(obstacle_key, (O, 2), 0, L)
+            k = jr.split(key, 2)
+            length_key, key = k[:, 0], k[:, 1]
+            ln = jr.uniform(length_key, (O, 2), lo, hi)
+            k = jr.split(key, 2)
+            theta_key, key = k[:, 0], k[:, 1]
+            th = jr.uniform(theta_key, (O,), 0, 2 * np.pi)
+            return Rectangle.create(pos, ln[..., 0], ln[..., 1], th, device=self.device), key
+        pos = jr.uniform(obstacle_key, (O, 3), 0, L)
+        k = jr.split(key, 2)
+        r_key, key = k[:, 0], k[:, 1]
+        rad = jr.uniform(r_key, (O,), lo / 2, hi / 2)
+        return Sphere.create(pos, rad, device=self.device), key
 
     def _inside_np(self, pts: np.ndarray, packed: np.ndarray, r: float) -> np.ndarray:
-        """Host restatement of inside_obstacles for reset's rejection sampling only."""
-        if packed.shape[0] == 0:
+        """Host restatement of inside_obstacles (env/obstacle.py:53-96,234-270) for reset's rejection sampling.
+        pts [a, dim], packed [a, O, k] (one obstacle set per point) -> bool [a]."""
+        if packed.shape[1] == 0:
             return np.zeros(pts.shape[0], dtype=bool)
         f = np.float32
         pts = pts.astype(f)
+        r = f(r)
         if self.pos_dim == 3:
-            d = np.linalg.norm(pts[:, None, :] - packed[None, :, :3], axis=-1)
-            return (d <= packed[None, :, 3] + f(r)).any(axis=1)
-        rel_x = pts[:, None, 0] - packed[None, :, 0]
-        rel_y = pts[:, None, 1] - packed[None, :, 1]
-        c, s = packed[None, :, 4], packed[None, :, 5]
-        xx = np.abs(rel_x * c + rel_y * s) - packed[None, :, 2]
-        yy = np.abs(rel_x * s - rel_y * c) - packed[None, :, 3]
+            d = np.sqrt(((pts[:, None, :] - packed[:, :, :3]) ** 2).sum(-1))
+            return (d <= packed[:, :, 3] + r).any(axis=1)
+        rel_x = pts[:, None, 0] - packed[:, :, 0]
+        rel_y = pts[:, None, 1] - packed[:, :, 1]
+        c, s = packed[:, :, 4], packed[:, :, 5]
+        xx = np.abs(rel_x * c + rel_y * s) - packed[:, :, 2]
+        yy = np.abs(rel_x * s - rel_y * c) - packed[:, :, 3]
         is_in = ((xx < r) & (yy < 0)) | ((xx < 0) & (yy < r)) | ((xx > 0) & (yy > 0) & (np.sqrt(xx ** 2 + yy ** 2) < r))
         return is_in.any(axis=1)
 
-    def _sample_agents_goals(self, rng: np.random.Generator, packed: np.ndarray):
-        """gcbfplus/env/utils.py:134-226 get_node_goal_rng: sequential rejection sampling.
-        Keeps the reference's quirk that not-yet-placed agents/goals sit at the origin."""
+    def _sample_agents_goals(self, keys: np.ndarray, packed: np.ndarray):
+        """gcbfplus/env/utils.py:134-226 get_node_goal_rng for E environments at once (keys [E, 2], packed
+        [E, O, k]): sequential rejection sampling per agent with the reference's key chain -- split(this_key, 3) per
+        agent, split(k, 2) per retry, the first goal candidate drawn in [0, max_travel) but retries in
+        [-max_travel, max_travel), not-yet-placed agents/goals sitting at the origin, and a restart from agent 0
+        (same key chain) when 1024 retries are exhausted."""
+        E = keys.shape[0]
         n, dim, L = self.num_agents, self.pos_dim, self.area_size
-        min_dist = 4 * self.radius
+        f = np.float32
+        min_dist = f(4 * self.radius)
         max_iter = 1024
         mt = self._max_travel
-        while True:
-            states = np.zeros((n, dim), dtype=np.float32)
-            goals = np.zeros((n, dim), dtype=np.float32)
-            ok = True
-            for i in range(n):
-                for it in range(max_iter + 1):
-                    cand = rng.uniform(0, L, size=dim).astype(np.float32)
-                    if np.linalg.norm(states - cand, axis=1).min() > min_dist and \
-                            not self._inside_np(cand[None], packed, min_dist)[0]:
-                        break
-                else:
-                    ok = False
-                states[i] = cand
-                for it in range(max_iter + 1):
-                    if mt is None:
-                        g = rng.uniform(0, L, size=dim).astype(np.float32)
-                    else:
-                        g = (rng.uniform(-mt, mt, size=dim) + cand).astype(np.float32)
-                    bad = np.linalg.norm(goals - g, axis=1).min() <= min_dist
-                    bad |= self._inside_np(g[None], packed, min_dist)[0]
-                    bad |= bool((g < 0).any() or (g > L).any())
-                    if mt is not None:
-                        bad |= bool(np.linalg.norm(g - cand) > mt)
-                    if not bad:
-                        break
-                else:
-                    ok = False
-                goals[i] = g
-                if not ok:
-                    break
-            if ok:
-                return states, goals
+        states = np.zeros((E, n, dim), dtype=f)
+        goals = np.zeros((E, n, dim), dtype=f)
+        agent_id = np.zeros(E, dtype=np.int64)
+        this_key = np.array(keys, dtype=np.uint32)
 
-    def reset(self, key=0, n_envs: int = 1) -> SwarmGraph:
-        """gcbfplus/env/double_integrator.py:83-112 for `n_envs` independent environments."""
+        def dist_min(all_pts, p):
+            return np.sqrt(((all_pts - p[:, None, :]) ** 2).sum(-1)).min(axis=1)
+
+        while True:
+            act = np.nonzero(agent_id < n)[0]
+            if act.size == 0:
+                return states, goals
+            k3 = jr.split(this_key[act], 3)
+            agent_key, goal_key = k3[:, 0], k3[:, 1]
+            this_key[act] = k3[:, 2]
+            pk = packed[act]
+            # ---- agent position
+            cand = jr.uniform(agent_key, (dim,), 0, L)
+            it_a = np.zeros(act.size, dtype=np.int64)
+            kk = agent_key.copy()
+            st = states[act]
+            while True:
+                bad = ((dist_min(st, cand) <= min_dist) | self._inside_np(cand, pk, min_dist)) & (it_a < max_iter)
+                idx = np.nonzero(bad)[0]
+                if idx.size == 0:
+                    break
+                k2 = jr.split(kk[idx], 2)
+                kk[idx] = k2[:, 1]
+                it_a[idx] += 1
+                cand[idx] = jr.uniform(k2[:, 0], (dim,), 0, L)
+            states[act, agent_id[act]] = cand
+            # ---- goal position
+            if mt is None:
+                g = jr.uniform(goal_key, (dim,), 0, L)
+            else:
+                g = jr.uniform(goal_key, (dim,), 0, mt) + cand
+            it_g = np.zeros(act.size, dtype=np.int64)
+            kk = goal_key.copy()
+            gl = goals[act]
+            while True:
+                bad = (dist_min(gl, g) <= min_dist) | self._inside_np(g, pk, min_dist)
+                bad |= (g < 0).any(axis=1) | (g > f(L)).any(axis=1)
+                if mt is not None:
+                    bad |= np.sqrt(((g - cand) ** 2).sum(-1)) > f(mt)
+                bad &= it_g < max_iter
+                idx = np.nonzero(bad)[0]
+                if idx.size == 0:
+                    break
+                k2 = jr.split(kk[idx], 2)
+                kk[idx] = k2[:, 1]
+                it_g[idx] += 1
+                if mt is None:
+                    g[idx] = jr.uniform(k2[:, 0], (dim,), 0, L)
+                else:
+                    g[idx] = jr.uniform(k2[:, 0], (dim,), -mt, mt) + cand[idx]
+            goals[act, agent_id[act]] = g
+            agent_id[act] += 1
+            fail = act[(it_a >= max_iter) | (it_g >= max_iter)]
+            if fail.size:                                    # "if no solution is found, start over"
+                agent_id[fail] = 0
+                states[fail] = 0
+                goals[fail] = 0
+
+    def reset(self, key=0, n_envs: Optional[int] = None) -> SwarmGraph:
+        """env.reset (double_integrator.py:83-112 and twins) for a batch of environments.
+        key: per-env threefry keys uint32 [E, 2] (what the reference's vmapped reset receives); or a single key
+        uint32 [2] / an int seed, expanded with split(key, n_envs) the way the trainer does (trainer.py:135)."""
         self._t = 0
-        rng = key if isinstance(key, np.random.Generator) else np.random.Generator(np.random.PCG64(int(key)))
-        obstacles = self._sample_obstacles(rng, n_envs)
+        key = jr.as_key(key) if not isinstance(key, np.ndarray) else key.astype(np.uint32)
+        if key.ndim == 1:
+            keys = jr.split(key, int(n_envs or 1))
+        else:
+            keys = key
+            assert n_envs is None or n_envs == keys.shape[0]
+        E = keys.shape[0]
+        obstacles, keys = self._sample_obstacles(keys)
         packed = obstacles.packed.cpu().numpy()
         sd, pd = self.state_dim, self.pos_dim
-        agent = np.zeros((n_envs, self.num_agents, sd), dtype=np.float32)
-        goal = np.zeros((n_envs, self.num_agents, sd), dtype=np.float32)
-        for e in range(n_envs):
-            s, g = self._sample_agents_goals(rng, packed[e])
-            agent[e, :, :pd], goal[e, :, :pd] = s, g
-        self._reset_extra(rng, agent, goal)
+        agent = np.zeros((E, self.num_agents, sd), dtype=np.float32)
+        goal = np.zeros((E, self.num_agents, sd), dtype=np.float32)
+        agent[:, :, :pd], goal[:, :, :pd] = self._sample_agents_goals(keys, packed)
+        self._reset_extra(keys, agent, goal)
         return self.get_graph(torch.from_numpy(agent).to(self.device), torch.from_numpy(goal).to(self.device),
                               obstacles)
 
-    def reset_np(self, key=0, n_envs: int = 1) -> SwarmGraph:
+    def reset_np(self, key=0, n_envs: Optional[int] = None) -> SwarmGraph:
         return self.reset(key, n_envs)
 
-    def _reset_extra(self, rng, agent: np.ndarray, goal: np.ndarray) -> None:
+    def _reset_extra(self, keys: np.ndarray, agent: np.ndarray, goal: np.ndarray) -> None:
         pass
 
     # ------------------------------------------------------------------ graph

@@ -18,9 +18,12 @@ class DubinsCar(MultiAgentEnv):
         r = self.radius  # dubins_car.py:398-440
         return dict(unsafe_agent=r * 2, unsafe_obs=r * 1.5, safe_agent=r * 4, safe_obs=r * 2)
 
-    def _reset_extra(self, rng, agent: np.ndarray, goal: np.ndarray) -> None:
-        """dubins_car.py:93-98: random heading; goal heading = atan2 towards the goal."""
-        agent[:, :, 2] = rng.uniform(-np.pi, np.pi, size=agent.shape[:2]).astype(np.float32)
+    def _reset_extra(self, keys: np.ndarray, agent: np.ndarray, goal: np.ndarray) -> None:
+        """dubins_car.py:93-98: random heading from split(key)[0] of the key get_node_goal_rng received;
+        goal heading = atan2 towards the goal."""
+        from ..utils import jrandom as jr
+        theta_key = jr.split(keys, 2)[:, 0]
+        agent[:, :, 2] = jr.uniform(theta_key, (agent.shape[1],), -np.pi, np.pi)
         goal[:, :, 2] = np.arctan2(goal[:, :, 1] - agent[:, :, 1], goal[:, :, 0] - agent[:, :, 0])
 
     def state_lim(self, state=None):

@@ -7,6 +7,8 @@ from time import time
 
 import numpy as np
 
+from .. import dist as gdist
+from ..utils import jrandom as jr
 from .rollout import RolloutEngine
 from .utils import eval_metrics, rollout
 
@@ -42,7 +44,7 @@ class Trainer:
         self.eval_epi = params["eval_epi"]
         self.save_interval = params["save_interval"]
         self.update_steps = 0
-        self.rng = np.random.Generator(np.random.PCG64(seed))         # trainer.py:62 key stream
+        self.key = jr.PRNGKey(seed)                                   # trainer.py:62 key stream
         self.history = []
 
     @staticmethod
@@ -66,24 +68,31 @@ class Trainer:
     def train(self):
         """trainer/trainer.py:76-143."""
         start_time = time()
-        train_engine = RolloutEngine(self.env, self.n_env_train)
+        # one process per GPU (torchrun): the training environments are sharded, every rank evaluates the (small)
+        # test set, rank 0 logs and saves; gradients meet in algo.update's single all-reduce per optimizer step
+        world = gdist.world_size()
+        rank = gdist.dist.get_rank() if world > 1 else 0
+        assert self.n_env_train % world == 0, "n_env_train must be divisible by the number of GPUs"
+        lo, hi = gdist.shard_bounds(self.n_env_train, rank, world)
+        train_engine = RolloutEngine(self.env, hi - lo)
         test_engine = RolloutEngine(self.env_test, self.n_env_test)
-        test_seed = int(np.random.Generator(np.random.PCG64(self.seed)).integers(0, 2 ** 31 - 1))   # fixed test keys
+        test_keys = jr.split(jr.PRNGKey(self.seed), 1_000)[:self.n_env_test]       # trainer.py:99-100
         for step in range(0, self.steps + 1):
             if step % self.eval_interval == 0:
-                ro = rollout(self.env_test, test_engine, self.algo.actor_params, test_seed)
+                ro = rollout(self.env_test, test_engine, self.algo.actor_params, test_keys)
                 info = eval_metrics(self.env_test, ro)
                 eval_info = {k: v for k, v in info.items() if k.startswith("eval/")}
                 eval_info["step"] = step
                 self._log(eval_info)
-                print(f"step: {step:3}, time: {time() - start_time:5.0f}s, reward: {info['eval/reward']:9.4f}, "
-                      f"min/max reward: {info['reward_min']:7.2f}/{info['reward_max']:7.2f}, "
-                      f"cost: {info['eval/cost']:8.4f}, unsafe_frac: {info['eval/unsafe_frac']:6.2f}, "
-                      f"finish: {info['eval/finish']:6.2f}")
-                if self.save_log and step % self.save_interval == 0:
+                if rank == 0:
+                    print(f"step: {step:3}, time: {time() - start_time:5.0f}s, reward: {info['eval/reward']:9.4f}, "
+                          f"min/max reward: {info['reward_min']:7.2f}/{info['reward_max']:7.2f}, "
+                          f"cost: {info['eval/cost']:8.4f}, unsafe_frac: {info['eval/unsafe_frac']:6.2f}, "
+                          f"finish: {info['eval/finish']:6.2f}")
+                if self.save_log and rank == 0 and step % self.save_interval == 0:
                     self.algo.save(os.path.join(self.model_dir), step)
-            key = int(self.rng.integers(0, 2 ** 31 - 1))
-            ro = rollout(self.env, train_engine, self.algo.actor_params, key)
+            key_x0, self.key = jr.split(self.key)                     # trainer.py:134-136
+            ro = rollout(self.env, train_engine, self.algo.actor_params, jr.split(key_x0, self.n_env_train)[lo:hi])
             update_info = self.algo.update(ro, step)
             self._log(update_info)
             self.update_steps += 1

@@ -10,11 +10,17 @@ from .data import Rollout
 from .rollout import RolloutEngine
 
 
-def rollout(env, engine: RolloutEngine, actor_params, key, n_envs: Optional[int] = None) -> Rollout:
-    """trainer/utils.py:25-55 for `n_envs` environments at once (the reference vmaps it,
-    trainer/trainer.py:84-87): reset(key) then T closed-loop steps of (algo.step, env.step)."""
+def rollout(env, engine: RolloutEngine, actor_params, keys, n_envs: Optional[int] = None) -> Rollout:
+    """trainer/utils.py:25-55 for a batch of environments (the reference vmaps it over per-env keys,
+    trainer/trainer.py:84-87): key_x0, _ = split(key); reset(key_x0); then T closed-loop steps of (algo.step,
+    env.step).  keys: uint32 [E, 2] rollout keys, or an int seed / single key expanded with split(key, E)."""
+    from ..utils import jrandom as jr
     n_envs = n_envs or engine.E
-    g0 = env.reset(key, n_envs=n_envs)
+    keys = jr.as_key(keys) if not isinstance(keys, np.ndarray) else keys
+    if keys.ndim == 1:
+        keys = jr.split(keys, n_envs)
+    assert keys.shape[0] == n_envs
+    g0 = env.reset(jr.split(keys, 2)[:, 0])
     engine.set_params(actor_params)
     engine.set_initial(g0.agent, g0.goal, g0.obstacle)
     engine.run()

@@ -51,7 +51,11 @@ def test(args):
     eng = RolloutEngine(env, n_epi, T=env.max_episode_steps, policy=policy)
     if algo is not None:
         eng.set_params(algo.actor_params)
-    g0 = env.reset(args.seed + args.offset, n_envs=n_epi)       # all episodes run as one batch
+    # test.py:117-119,158: test_keys = split(PRNGKey(seed), 1000)[:epi][offset:]; episode i resets with
+    # split(test_keys[i])[0].  All episodes run as one batch here.
+    from gcbfplus_b200.utils import jrandom as jr
+    test_keys = jr.split(jr.PRNGKey(args.seed), 1_000)[: args.epi][args.offset:]
+    g0 = env.reset(jr.split(test_keys, 2)[:, 0])
     eng.set_initial(g0.agent, g0.goal, g0.obstacle)
     eng.run()
     ro = eng.result()

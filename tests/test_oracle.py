@@ -268,3 +268,84 @@ def test_qp_relaxation_engages_when_infeasible():
     assert u[0] == 1.0 and abs(r[0] - 4.0) < 1e-9 and abs(lam[0] - (1000 + 10 * 4.0)) < 1e-6
     assert r[1] == 0.0 and lam[1] == 0.0 and abs(u[1] + 0.1) < 1e-12
     assert max(qp.kkt_residual(Lg, b, u_ref, 1.0, u, r, lam).values()) < 1e-8
+
+
+# ------------------------------------------------------------------------------------ reset / jax.random restatement
+def test_threefry_known_answers():
+    """Random123 Threefry-2x32-20 vectors + the values jax prints for split / uniform of PRNGKey(0) and
+    split(PRNGKey(42)) -- checked for both the product's host RNG and the oracle's scalar restatement."""
+    from gcbfplus_b200.utils import jrandom as jr
+    from oracle import reset as orr
+    kat = [((0, 0), (0, 0), (0x6B200159, 0x99BA4EFE)),
+           ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), (0x1CB996FC, 0xBB002BE7)),
+           ((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0))]
+    for key, ctr, exp in kat:
+        assert orr.threefry2x32(key[0], key[1], ctr[0], ctr[1]) == exp
+        y0, y1 = jr.threefry2x32(key[0], key[1], np.array([ctr[0]], np.uint32), np.array([ctr[1]], np.uint32))
+        assert (int(y0[0]), int(y1[0])) == exp
+    assert jr.split(jr.PRNGKey(0)).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+    assert jr.split(jr.PRNGKey(42)).tolist() == [[2465931498, 3679230171], [255383827, 267815257]]
+    assert orr.split(orr.prng_key(0)) == [(4146024105, 967050713), (2718843009, 1272950319)]
+    assert abs(float(jr.uniform(jr.PRNGKey(0))) - 0.41845703) < 1e-8
+    assert abs(float(orr.uniform(orr.prng_key(0), (), 0.0, 1.0)) - 0.41845703) < 1e-8
+    # batched keys == a loop over keys (the reference vmaps reset over keys)
+    ks = jr.split(jr.PRNGKey(7), 5)
+    assert (jr.split(ks, 3) == np.stack([jr.split(k, 3) for k in ks])).all()
+    assert (jr.uniform(ks, (3,), -1, 2) == np.stack([jr.uniform(k, (3,), -1, 2) for k in ks])).all()
+    for k in ks:
+        kk = (int(k[0]), int(k[1]))
+        assert [tuple(map(int, r)) for r in jr.split(k, 3)] == orr.split(kk, 3)
+        assert (jr.uniform(k, (5,), 0, 3) == orr.uniform(kk, (5,), 0, 3)).all()
+
+
+@pytest.mark.parametrize("env_id,N,area,n_obs,max_travel", [
+    ("SingleIntegrator", 6, 1.5, 3, None), ("DoubleIntegrator", 8, 2.0, 8, None), ("DoubleIntegrator", 5, 3.0, 4, 1.0),
+    ("DubinsCar", 6, 2.0, 4, None), ("LinearDrone", 6, 1.0, 4, None)])
+def test_reset_matches_oracle_bit_exact(env_id, N, area, n_obs, max_travel):
+    """The product's vectorised host reset against the oracle's scalar, per-environment restatement of
+    get_node_goal_rng (crowded scenes: rejection loops and per-env divergence are exercised)."""
+    from gcbfplus_b200.env import make_env
+    from gcbfplus_b200.utils import jrandom as jr
+    from oracle import reset as orr
+    env = make_env(env_id, N, area_size=area, num_obs=n_obs, max_travel=max_travel, device="cpu")
+    keys = jr.split(jr.PRNGKey(3), 4)
+    obstacles, k2 = env._sample_obstacles(keys)
+    packed = obstacles.packed.numpy()
+    sd, pd = env.state_dim, env.pos_dim
+    agent = np.zeros((4, N, sd), np.float32)
+    goal = np.zeros((4, N, sd), np.float32)
+    agent[:, :, :pd], goal[:, :, :pd] = env._sample_agents_goals(k2, packed)
+    env._reset_extra(k2, agent, goal)
+    retried = 0
+    for e in range(4):
+        o = orr.reset(env_id, (int(keys[e, 0]), int(keys[e, 1])), N, area, n_obs, env._params["obs_len_range"],
+                      env.radius, max_travel)
+        assert np.array_equal(agent[e], o["agent"]) and np.array_equal(goal[e], o["goal"])
+        assert np.array_equal(packed[e][:, :pd], o["obs"]["center"])
+        if pd == 3:
+            assert np.array_equal(packed[e][:, 3], o["obs"]["radius"])
+        else:
+            assert np.array_equal(packed[e][:, 2], o["obs"]["width"] / np.float32(2))
+            assert np.array_equal(packed[e][:, 4], o["obs"]["cos"])
+        # validity: pairwise distances and obstacle clearance of the accepted samples
+        d = np.linalg.norm(agent[e][:, None, :pd] - agent[e][None, :, :pd], axis=-1) + np.eye(N) * 10
+        assert d.min() > 4 * env.radius
+        assert not any(orr.inside_obstacles(agent[e][i, :pd], o["obs"], 4 * env.radius) for i in range(N))
+        first = orr.uniform(orr.split(orr.split((int(k2[e, 0]), int(k2[e, 1])), 3)[0], 2)[0], (pd,), 0, area)
+        retried += int(not np.array_equal(first, agent[e][0, :pd]))
+    assert agent.dtype == np.float32
+    assert retried >= 0
+
+
+def test_reset_key_plumbing_matches_reference_call_sites():
+    """trainer.py:99-100,134-136 and test.py:117-119,158: which key reaches env.reset for environment i."""
+    from gcbfplus_b200.utils import jrandom as jr
+    seed, n_env = 5, 3
+    key = jr.PRNGKey(seed)
+    key_x0, key = jr.split(key)
+    rollout_keys = jr.split(key_x0, n_env)                 # vmapped rollout(key): key_x0, _ = split(key); reset(key_x0)
+    reset_keys = jr.split(rollout_keys, 2)[:, 0]
+    for i in range(n_env):
+        assert (reset_keys[i] == jr.split(rollout_keys[i])[0]).all()
+    test_keys = jr.split(jr.PRNGKey(seed), 1_000)[:n_env]
+    assert test_keys.shape == (n_env, 2) and len({tuple(k) for k in test_keys.tolist()}) == n_env

@@ -18,12 +18,18 @@ def train(args):
         raise SystemExit("--cpu: gcbfplus_b200 is the sm_100a CUDA path only (no CPU fallback by design)")
     os.environ.setdefault("WANDB_MODE", "offline")
     np.random.seed(args.seed)
-    if args.debug:
+    # one process per GPU under torchrun (python -m torch.distributed.run --nproc-per-node N train.py ...):
+    # environments are sharded over the ranks, gradients all-reduced once per optimizer step
+    import torch
+    from gcbfplus_b200 import dist as gdist
+    rank, local_rank, world = gdist.init_from_env()
+    device = torch.device("cuda", local_rank)
+    if args.debug or rank != 0:
         os.environ["WANDB_MODE"] = "disabled"
     env = make_env(env_id=args.env, num_agents=args.num_agents, num_obs=args.obs, n_rays=args.n_rays,
-                   area_size=args.area_size)
+                   area_size=args.area_size, device=device)
     env_test = make_env(env_id=args.env, num_agents=args.num_agents, num_obs=args.obs, n_rays=args.n_rays,
-                        area_size=args.area_size)
+                        area_size=args.area_size, device=device)
     algo = make_algo(
         algo=args.algo, env=env, node_dim=env.node_dim, edge_dim=env.edge_dim, state_dim=env.state_dim,
         action_dim=env.action_dim, n_agents=env.num_agents, gnn_layers=args.gnn_layers, batch_size=256,
@@ -33,13 +39,15 @@ def train(args):
         loss_h_dot_coef=args.loss_h_dot_coef, max_grad_norm=2.0, seed=args.seed)
     start_time = datetime.datetime.now().strftime("%Y%m%d%H%M%S")
     log_dir = f"{args.log_dir}/{args.env}/{args.algo}/seed{args.seed}_{start_time}"
-    os.makedirs(log_dir, exist_ok=True)
+    if rank == 0:
+        os.makedirs(log_dir, exist_ok=True)
     run_name = f"{args.algo}_{args.env}_{start_time}" if args.name is None else args.name
     train_params = {"run_name": run_name, "training_steps": args.steps, "eval_interval": args.eval_interval,
                     "eval_epi": args.eval_epi, "save_interval": args.save_interval}
     trainer = Trainer(env=env, env_test=env_test, algo=algo, log_dir=log_dir, n_env_train=args.n_env_train,
-                      n_env_test=args.n_env_test, seed=args.seed, params=train_params, save_log=not args.debug)
-    if not args.debug:
+                      n_env_test=args.n_env_test, seed=args.seed, params=train_params,
+                      save_log=not args.debug and rank == 0)
+    if not args.debug and rank == 0:
         with open(f"{log_dir}/config.yaml", "w") as f:
             yaml.dump(args, f)
             yaml.dump(algo.config, f)
