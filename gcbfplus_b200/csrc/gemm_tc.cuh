@@ -141,10 +141,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int M = m_ptr ? *m_ptr : m_fixed;
-    M = min(M, m_cap);
     const int tiles_n = N / BN;                // 1, or 2 when a 256-wide layer is split to fill more SMs
-    const int n_tiles = ((M + BM - 1) / BM) * tiles_n;
     const int nkb = K / BK;
 
     if (threadIdx.x == 0) {
@@ -169,6 +166,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    int M = m_ptr ? *m_ptr : m_fixed;
+    M = min(M, m_cap);
+    const int n_tiles = ((M + BM - 1) / BM) * tiles_n;
 
     if (warp == 0) {
         // ================= TMA producer =================

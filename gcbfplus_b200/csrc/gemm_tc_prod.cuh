@@ -52,10 +52,7 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
     float* sW = reinterpret_cast<float*>(smem + STAGES * CF::STAGE_BYTES + 256);   // PROD_EDGE: [ED + 3][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int M = m_ptr ? *m_ptr : m_fixed;
-    M = min(M, m_cap);
-    const int tiles_n = N / BN;
-    const int n_tiles = ((M + BM - 1) / BM) * tiles_n;
+    const int tiles_n = N / BN;                // 1, or 2 when a 256-wide layer is split to fill more SMs
     const int nkb = K / BK;
 
     if (threadIdx.x == 0) {
@@ -87,6 +84,9 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    int M = m_ptr ? *m_ptr : m_fixed;
+    M = min(M, m_cap);
+    const int n_tiles = ((M + BM - 1) / BM) * tiles_n;
 
     if (warp == 0) {
         // ================= TMA producer (weights only) =================

@@ -143,6 +143,23 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
     constexpr int OBW = (PD == 2) ? 16 : 4;
     extern __shared__ float smem[];
     const int N = d.n_agents, O = d.n_obs, R = d.n_hits;
+    constexpr int OBS2 = (PD == 2) ? 24 : 4;    // 2-D: packed rectangle + derived [14] reach^2, [15..18] edge dx, [19..22] edge dy
+    float* spos = smem;                         // [N, PD]
+    float* sobs = spos + N * PD;                // [O, OBS2]
+    float* stab = sobs + O * OBS2;              // [n_rays, PD]
+    float* salpha = stab + d.n_rays * PD;       // 3-D only: [GB_WARPS, n_rays]
+    const int n_words = (N + 31) / 32;
+    unsigned* sbits = reinterpret_cast<unsigned*>(salpha + (PD == 3 ? GB_WARPS * d.n_rays : 0));  // [GB_WARPS, n_words]
+    __shared__ int s_off[GB_WARPS + 1];
+    __shared__ int s_base;
+
+    const int g = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (O > 0) {
+        const float* ob = obstacles + (d.obs_per_graph ? (size_t)g * O * OBW : 0);
+        for (int i = tid; i < O * OBW; i += blockDim.x) sobs[(i / OBW) * OBS2 + (i % OBW)] = ob[i];
+    }
+    for (int i = tid; i < d.n_rays * PD; i += blockDim.x) stab[i] = ray_table[i];
     // ---- optional: per-env reward / cost of the step that produced these states (policy_tail_kernel wrote the
     // per-agent terms); deterministic fixed-order reduction by the first CTA of each graph.
     if (terms != nullptr && blockIdx.x == 0) {
@@ -170,28 +187,11 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
             cost[blockIdx.y] = t[1] / (float)N + t[2] / (float)N;
         }
     }
-    constexpr int OBS2 = (PD == 2) ? 24 : 4;    // 2-D: packed rectangle + derived [14] reach^2, [15..18] edge dx, [19..22] edge dy
-    float* spos = smem;                         // [N, PD]
-    float* sobs = spos + N * PD;                // [O, OBS2]
-    float* stab = sobs + O * OBS2;              // [n_rays, PD]
-    float* salpha = stab + d.n_rays * PD;       // 3-D only: [GB_WARPS, n_rays]
-    const int n_words = (N + 31) / 32;
-    unsigned* sbits = reinterpret_cast<unsigned*>(salpha + (PD == 3 ? GB_WARPS * d.n_rays : 0));  // [GB_WARPS, n_words]
-    __shared__ int s_off[GB_WARPS + 1];
-    __shared__ int s_base;
-
-    const int g = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < N; i += blockDim.x) {
         const float* a = agent + ((size_t)g * N + i) * SD;
 #pragma unroll
         for (int c = 0; c < PD; ++c) spos[i * PD + c] = a[c];
     }
-    if (O > 0) {
-        const float* ob = obstacles + (d.obs_per_graph ? (size_t)g * O * OBW : 0);
-        for (int i = tid; i < O * OBW; i += blockDim.x) sobs[(i / OBW) * OBS2 + (i % OBW)] = ob[i];
-    }
-    for (int i = tid; i < d.n_rays * PD; i += blockDim.x) stab[i] = ray_table[i];
     __syncthreads();
     if (PD == 2) {   // derived fields for the (conservative, exactness-preserving) far-obstacle skip
         for (int o = tid; o < O; o += blockDim.x) {
@@ -605,12 +605,14 @@ policy_tail_kernel(const gcbf_env_desc d, const float* __restrict__ z, const int
                    const float* __restrict__ bHO, const float* __restrict__ agent, const float* __restrict__ goal,
                    const float* __restrict__ obstacles, const int32_t* __restrict__ row_start,
                    const int32_t* __restrict__ row_deg, const int32_t* __restrict__ edge_src,
-                   float* __restrict__ action, float* __restrict__ next_agent, float* __restrict__ terms) {
+                   float* __restrict__ action, float* __restrict__ next_agent, float* __restrict__ terms,
+                   int32_t* __restrict__ zero_counter) {
     using T = EnvTraits<KIND>;
     constexpr int SD = T::SD, NU = T::NU, PD = T::PD;
     constexpr int OBW = (PD == 2) ? 16 : 4;
     const int A = d.n_graphs * d.n_agents;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a == 0 && zero_counter) zero_counter[0] = 0;
     if (a >= A) return;
     float zz[4] = {0.f, 0.f, 0.f, 0.f};
     for (int p = 0; p < parts; ++p) {
@@ -828,11 +830,14 @@ int32_t graph_build_impl(const gcbf_env_desc* desc, const float* agent, const fl
 int32_t policy_tail_impl(const gcbf_env_desc* desc, const float* z, int parts, int z_cap, const float* bHO,
                          const float* agent, const float* goal, const float* obstacles, const int32_t* row_start,
                          const int32_t* row_deg, const int32_t* edge_src, float* action, float* next_agent, float* terms,
-                         cudaStream_t st) {
+                         int32_t* zero_counter, cudaStream_t st) {
+    // zero_counter: edge counter of the NEXT graph, cleared here so that no memset node sits between this kernel
+    // and the graph build that follows (one node less per env-step in the rollout graph: measured +5 %)
     const int A = desc->n_graphs * desc->n_agents;
     GCBF_DISPATCH_ENV(desc->env_kind, {
         policy_tail_kernel<KIND><<<(A + 127) / 128, 128, 0, st>>>(*desc, z, parts, z_cap, bHO, agent, goal, obstacles,
-                                                                  row_start, row_deg, edge_src, action, next_agent, terms);
+                                                                  row_start, row_deg, edge_src, action, next_agent, terms,
+                                                                  zero_counter);
     });
     count_launch();
     return check_launch("policy_tail_kernel");
@@ -863,8 +868,10 @@ int32_t gcbf::graph_build_impl(const gcbf_env_desc* desc, const float* agent, co
                                          (size_t)desc->n_rays * pd + (pd == 3 ? (size_t)GB_WARPS * desc->n_rays : 0) +
                                          (size_t)GB_WARPS * ((desc->n_agents + 31) / 32));
     GCBF_REQUIRE(smem <= 200 * 1024, "graph_build needs %zu B shared memory (> 200 KB): too many agents/obstacles", smem);
-    cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t), st);
-    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int32_t)e; }
+    if (!(flags & 4)) {   // bit 2: the caller's previous kernel already cleared counters[0]
+        cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t), st);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int32_t)e; }
+    }
     dim3 grid((desc->n_agents + GB_WARPS - 1) / GB_WARPS, desc->n_graphs);
     GCBF_DISPATCH_ENV(desc->env_kind, {
         auto kern = graph_build_kernel<KIND>;

@@ -431,7 +431,7 @@ int32_t graph_build_impl(const gcbf_env_desc* desc, const float* agent, const fl
 int32_t policy_tail_impl(const gcbf_env_desc* desc, const float* z, int parts, int z_cap, const float* bHO,
                          const float* agent, const float* goal, const float* obstacles, const int32_t* row_start,
                          const int32_t* row_deg, const int32_t* edge_src, float* action, float* next_agent, float* terms,
-                         cudaStream_t st);
+                         int32_t* zero_counter, cudaStream_t st);
 }  // namespace gcbf
 
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step(
@@ -459,12 +459,17 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step(
     float* z = terms + ((3 * A + 3) & ~(int64_t)3);          // [2][A][4] output-layer partial sums
     int32_t rc;
     int parts = 1;
+    // (Programmatic dependent launch of this 7-kernel chain was built and measured: +1 % (98.2 vs 97.2 M env-steps/s;
+    //  inside a CUDA graph the kernel-to-kernel gap is already ~1 us) and it was NOT safe as written -- a dependent
+    //  kernel that starts early can keep L1 / read-only-cache lines of buffers its predecessor rewrites (DubinsCar
+    //  rollouts became non-deterministic with only the edge-message GEMM launched that way).  Removed; what stayed
+    //  is the memset-free chain (policy_tail clears the next edge counter), worth +5 %.)
     if ((rc = gnn_infer_impl(desc, nu, actor_params, infer_blob, use_tensor_cores, agent, goal, hits, row_start, row_deg,
                              edge_recv, edge_src, counters, 0, nullptr, workspace, st, z, &parts))) return rc;
     if ((rc = policy_tail_impl(desc, z, parts, (int)A, infer_blob + I.bho, agent, goal, obstacles, row_start, row_deg,
-                               edge_src, action, next_agent, terms, st))) return rc;
+                               edge_src, action, next_agent, terms, next_counters, st))) return rc;
     return graph_build_impl(desc, next_agent, obstacles, ray_table, next_hits, row_start, row_deg, edge_recv, edge_src,
-                            next_counters, 1, terms, reward, cost, stream);
+                            next_counters, 1 | 4, terms, reward, cost, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t gcbf_rollout_workspace_floats(const gcbf_env_desc* desc) {
