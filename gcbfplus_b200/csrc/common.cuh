@@ -23,6 +23,20 @@ int sm_count();
         }                                  \
     } while (0)
 
+// ---- fused policy tail of the rollout step (z == nullptr: plain graph build from `agent`).
+struct TailArgs {
+    const float* z;            // [parts][z_cap][4] output-layer partial sums (no bias / tanh)
+    int parts, z_cap;
+    const float* bHO;          // output-layer bias
+    const float* agent_prev;   // states the action is computed for
+    const float* goal;
+    const int32_t* row_start_prev;   // previous graph (cost: any neighbour within 2r)
+    const int32_t* row_deg_prev;
+    const int32_t* edge_src_prev;
+    float* action;             // out [A, nu] (unclipped 2 pi + u_ref)
+    float* next_agent;         // out [A, sd]
+};
+
 // ---- per-environment compile-time traits -------------------------------------------
 template <int KIND> struct EnvTraits;
 template <> struct EnvTraits<GCBF_ENV_SINGLE_INTEGRATOR> { static constexpr int SD = 2, ED = 2, NU = 2, PD = 2; };

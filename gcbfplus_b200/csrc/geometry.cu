@@ -127,6 +127,12 @@ __device__ __forceinline__ SortKey warp_sort32(SortKey k, int lane) {
     return k;
 }
 
+template <int KIND>
+__device__ __forceinline__ void u_ref_dev(const gcbf_env_desc& d, const float* x, const float* gl, float* u);
+template <int KIND>
+__device__ __forceinline__ void euler_dev(const gcbf_env_desc& d, const float* x, const float* gl, const float* u,
+                                          float* xn);
+
 // ------------------------------------------------------------------------------------
 // graph build: one warp per agent, GB_WARPS agents per CTA, grid = (ceil(N/GB_WARPS), G)
 // smem: positions of all N agents of the graph, its obstacles, 3-D alpha scratch.
@@ -136,10 +142,10 @@ __global__ void __launch_bounds__(GB_WARPS * 32)
 graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const float* __restrict__ obstacles,
                    const float* __restrict__ ray_table, float* __restrict__ hits, int32_t* __restrict__ row_start,
                    int32_t* __restrict__ row_deg, int32_t* __restrict__ edge_recv, int32_t* __restrict__ edge_src,
-                   int32_t* __restrict__ counters, const int do_cast, const float* __restrict__ terms,
+                   int32_t* __restrict__ counters, const int do_cast, const TailArgs tl,
                    float* __restrict__ reward, float* __restrict__ cost) {
     using T = EnvTraits<KIND>;
-    constexpr int SD = T::SD, PD = T::PD;
+    constexpr int SD = T::SD, PD = T::PD, NU = T::NU;
     constexpr int OBW = (PD == 2) ? 16 : 4;
     extern __shared__ float smem[];
     const int N = d.n_agents, O = d.n_obs, R = d.n_hits;
@@ -160,37 +166,96 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
         for (int i = tid; i < O * OBW; i += blockDim.x) sobs[(i / OBW) * OBS2 + (i % OBW)] = ob[i];
     }
     for (int i = tid; i < d.n_rays * PD; i += blockDim.x) stab[i] = ray_table[i];
-    // ---- optional: per-env reward / cost of the step that produced these states (policy_tail_kernel wrote the
-    // per-agent terms); deterministic fixed-order reduction by the first CTA of each graph.
-    if (terms != nullptr && blockIdx.x == 0) {
+    if (tl.z == nullptr) {
+        for (int i = tid; i < N; i += blockDim.x) {
+            const float* a = agent + ((size_t)g * N + i) * SD;
+#pragma unroll
+            for (int c = 0; c < PD; ++c) spos[i * PD + c] = a[c];
+        }
+    } else {
+        // ---- fused policy tail (rollout step): pi = tanh(sum_parts z + bHO) (policy.py:72), a = 2 pi + u_ref
+        // (gcbf_plus.py:182-186), clip_action, agent_step_euler (double_integrator.py:128-143).  Every CTA of graph g
+        // recomputes the next state of all N agents (thread per agent, a few hundred instructions) straight into its
+        // position table -- that replaces a separate kernel and a round trip through HBM; the graph's first CTA also
+        // records actions / next states and reduces the reward / cost terms of the step (double_integrator.py:145-198)
+        // in a fixed order.  The cost reads the PREVIOUS edge lists (the new ones are being written by this kernel
+        // into the other half of the caller's double buffer).
         __shared__ float s_red[3][GB_WARPS];
+        const bool rec = blockIdx.x == 0;
         const int A_tot = d.n_graphs * N;
         float acc[3] = {0.f, 0.f, 0.f};
-        for (int i = threadIdx.x; i < N; i += blockDim.x) {
-#pragma unroll
-            for (int q = 0; q < 3; ++q) acc[q] += terms[(size_t)q * A_tot + (size_t)blockIdx.y * N + i];
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const float v = warp_sum(acc[q]);
-            if ((threadIdx.x & 31) == 0) s_red[q][threadIdx.x >> 5] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float t[3] = {0.f, 0.f, 0.f};
-            for (int w = 0; w < GB_WARPS; ++w) {
-                t[0] += s_red[0][w];
-                t[1] += s_red[1][w];
-                t[2] += s_red[2][w];
+        for (int i = tid; i < N; i += blockDim.x) {
+            const size_t a = (size_t)g * N + i;
+            float zz[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int p = 0; p < tl.parts; ++p) {
+                const float4 v = *reinterpret_cast<const float4*>(tl.z + ((size_t)p * tl.z_cap + a) * 4);
+                zz[0] += v.x; zz[1] += v.y; zz[2] += v.z; zz[3] += v.w;
             }
-            reward[blockIdx.y] = -(t[0] / (float)N);
-            cost[blockIdx.y] = t[1] / (float)N + t[2] / (float)N;
-        }
-    }
-    for (int i = tid; i < N; i += blockDim.x) {
-        const float* a = agent + ((size_t)g * N + i) * SD;
+            float x[SD], gl[SD], ur[NU], u[NU], xn[SD];
 #pragma unroll
-        for (int c = 0; c < PD; ++c) spos[i * PD + c] = a[c];
+            for (int c = 0; c < SD; ++c) {
+                x[c] = tl.agent_prev[a * SD + c];
+                gl[c] = tl.goal[a * SD + c];
+            }
+            u_ref_dev<KIND>(d, x, gl, ur);
+            float sq = 0.f;
+#pragma unroll
+            for (int c = 0; c < NU; ++c) {
+                const float act = 2.f * tanhf(zz[c] + tl.bHO[c]) + ur[c];
+                if (rec) tl.action[a * NU + c] = act;
+                u[c] = isnan(act) ? act : fminf(fmaxf(act, -d.u_lim), d.u_lim);
+                const float df = u[c] - ur[c];
+                sq = (c == 0) ? df * df : sq + df * df;
+            }
+            euler_dev<KIND>(d, x, gl, u, xn);
+#pragma unroll
+            for (int c = 0; c < PD; ++c) spos[i * PD + c] = xn[c];
+            if (rec) {
+#pragma unroll
+                for (int c = 0; c < SD; ++c) tl.next_agent[a * SD + c] = xn[c];
+                const float nr = sqrtf(sq);
+                bool col = false;
+                const int rs = tl.row_start_prev[a], rd = tl.row_deg_prev[a];
+                for (int e = rs + 1; e < rs + rd; ++e) {
+                    const int sidx = tl.edge_src_prev[e];
+                    if (sidx < 0) break;
+                    float dd = 0.f;
+#pragma unroll
+                    for (int c = 0; c < PD; ++c) {
+                        const float dlt = x[c] - tl.agent_prev[(size_t)sidx * SD + c];
+                        dd = (c == 0) ? dlt * dlt : dd + dlt * dlt;
+                    }
+                    col = col || (d.two_r > sqrtf(dd));
+                }
+                bool in_obs = false;
+                if (O > 0) {
+                    const float* ob = obstacles + (d.obs_per_graph ? (size_t)g * O * OBW : 0);
+                    in_obs = inside_any<PD>(ob, O, x, d.radius);
+                }
+                acc[0] += nr * nr;
+                acc[1] += col ? 1.f : 0.f;
+                acc[2] += in_obs ? 1.f : 0.f;
+            }
+        }
+        (void)A_tot;
+        if (rec) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float v = warp_sum(acc[q]);
+                if (lane == 0) s_red[q][warp] = v;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float t[3] = {0.f, 0.f, 0.f};
+                for (int w = 0; w < GB_WARPS; ++w) {
+                    t[0] += s_red[0][w];
+                    t[1] += s_red[1][w];
+                    t[2] += s_red[2][w];
+                }
+                reward[g] = -(t[0] / (float)N);
+                cost[g] = t[1] / (float)N + t[2] / (float)N;
+            }
+        }
     }
     __syncthreads();
     if (PD == 2) {   // derived fields for the (conservative, exactness-preserving) far-obstacle skip
@@ -595,75 +660,6 @@ env_step_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const fl
 }
 
 // ------------------------------------------------------------------------------------
-// policy tail, thread per agent: pi = tanh(sum_parts z[part] + bHO) (policy.py:72; z = partial sums of the output
-// layer written by the EPI_RELU_DOTN GEMM epilogue or by head_z_kernel), a = 2 pi + u_ref (gcbf_plus.py:182-186),
-// clip_action, agent_step_euler, per-agent reward / cost terms (double_integrator.py:145-198).
-// ------------------------------------------------------------------------------------
-template <int KIND>
-__global__ void __launch_bounds__(128)
-policy_tail_kernel(const gcbf_env_desc d, const float* __restrict__ z, const int parts, const int z_cap,
-                   const float* __restrict__ bHO, const float* __restrict__ agent, const float* __restrict__ goal,
-                   const float* __restrict__ obstacles, const int32_t* __restrict__ row_start,
-                   const int32_t* __restrict__ row_deg, const int32_t* __restrict__ edge_src,
-                   float* __restrict__ action, float* __restrict__ next_agent, float* __restrict__ terms,
-                   int32_t* __restrict__ zero_counter) {
-    using T = EnvTraits<KIND>;
-    constexpr int SD = T::SD, NU = T::NU, PD = T::PD;
-    constexpr int OBW = (PD == 2) ? 16 : 4;
-    const int A = d.n_graphs * d.n_agents;
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a == 0 && zero_counter) zero_counter[0] = 0;
-    if (a >= A) return;
-    float zz[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int p = 0; p < parts; ++p) {
-        const float4 v = *reinterpret_cast<const float4*>(z + ((size_t)p * z_cap + a) * 4);
-        zz[0] += v.x; zz[1] += v.y; zz[2] += v.z; zz[3] += v.w;
-    }
-    const int g = a / d.n_agents;
-    float x[SD], gl[SD], ur[NU], u[NU], xn[SD];
-#pragma unroll
-    for (int c = 0; c < SD; ++c) {
-        x[c] = agent[(size_t)a * SD + c];
-        gl[c] = goal[(size_t)a * SD + c];
-    }
-    u_ref_dev<KIND>(d, x, gl, ur);
-    float sq = 0.f;
-#pragma unroll
-    for (int c = 0; c < NU; ++c) {
-        const float act = 2.f * tanhf(zz[c] + bHO[c]) + ur[c];
-        action[(size_t)a * NU + c] = act;
-        u[c] = isnan(act) ? act : fminf(fmaxf(act, -d.u_lim), d.u_lim);
-        const float df = u[c] - ur[c];
-        sq = (c == 0) ? df * df : sq + df * df;
-    }
-    euler_dev<KIND>(d, x, gl, u, xn);
-#pragma unroll
-    for (int c = 0; c < SD; ++c) next_agent[(size_t)a * SD + c] = xn[c];
-    const float nr = sqrtf(sq);
-    bool col = false;
-    const int rs = row_start[a], rd = row_deg[a];
-    for (int e = rs + 1; e < rs + rd; ++e) {
-        const int s = edge_src[e];
-        if (s < 0) break;
-        float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < PD; ++c) {
-            const float dlt = x[c] - agent[(size_t)s * SD + c];
-            acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
-        }
-        col = col || (d.two_r > sqrtf(acc));
-    }
-    bool in_obs = false;
-    if (d.n_obs > 0) {
-        const float* ob = obstacles + (d.obs_per_graph ? (size_t)g * d.n_obs * OBW : 0);
-        in_obs = inside_any<PD>(ob, d.n_obs, x, d.radius);
-    }
-    terms[a] = nr * nr;
-    terms[(size_t)A + a] = col ? 1.f : 0.f;
-    terms[(size_t)2 * A + a] = in_obs ? 1.f : 0.f;
-}
-
-// ------------------------------------------------------------------------------------
 // masks: warp per agent; brute force over the graph's agents + own hit nodes.
 // ------------------------------------------------------------------------------------
 template <int KIND>
@@ -824,40 +820,31 @@ static int32_t check_desc(const gcbf_env_desc* d) {
 namespace gcbf {
 int32_t graph_build_impl(const gcbf_env_desc* desc, const float* agent, const float* obstacles, const float* ray_table,
                          float* hits, int32_t* row_start, int32_t* row_deg, int32_t* edge_recv, int32_t* edge_src,
-                         int32_t* counters, int32_t flags, const float* terms, float* reward, float* cost, void* stream);
+                         int32_t* counters, int32_t flags, const TailArgs& tail, float* reward, float* cost, void* stream);
 
-// policy tail launcher (used by gcbf_rollout_step in gnn.cu)
-int32_t policy_tail_impl(const gcbf_env_desc* desc, const float* z, int parts, int z_cap, const float* bHO,
-                         const float* agent, const float* goal, const float* obstacles, const int32_t* row_start,
-                         const int32_t* row_deg, const int32_t* edge_src, float* action, float* next_agent, float* terms,
-                         int32_t* zero_counter, cudaStream_t st) {
-    // zero_counter: edge counter of the NEXT graph, cleared here so that no memset node sits between this kernel
-    // and the graph build that follows (one node less per env-step in the rollout graph: measured +5 %)
-    const int A = desc->n_graphs * desc->n_agents;
-    GCBF_DISPATCH_ENV(desc->env_kind, {
-        policy_tail_kernel<KIND><<<(A + 127) / 128, 128, 0, st>>>(*desc, z, parts, z_cap, bHO, agent, goal, obstacles,
-                                                                  row_start, row_deg, edge_src, action, next_agent, terms,
-                                                                  zero_counter);
-    });
-    count_launch();
-    return check_launch("policy_tail_kernel");
-}
 }  // namespace gcbf
 
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_graph_build(const gcbf_env_desc* desc, const float* agent, const float* obstacles,
                                     const float* ray_table, float* hits, int32_t* row_start, int32_t* row_deg,
                                     int32_t* edge_recv, int32_t* edge_src, int32_t* counters, int32_t flags,
                                     void* stream) {
+    TailArgs none;
+    memset(&none, 0, sizeof(none));
     return graph_build_impl(desc, agent, obstacles, ray_table, hits, row_start, row_deg, edge_recv, edge_src, counters,
-                            flags, nullptr, nullptr, nullptr, stream);
+                            flags, none, nullptr, nullptr, stream);
 }
 
 int32_t gcbf::graph_build_impl(const gcbf_env_desc* desc, const float* agent, const float* obstacles,
                                const float* ray_table, float* hits, int32_t* row_start, int32_t* row_deg,
                                int32_t* edge_recv, int32_t* edge_src, int32_t* counters, int32_t flags,
-                               const float* terms, float* reward, float* cost, void* stream) {
+                               const TailArgs& tail, float* reward, float* cost, void* stream) {
     if (int32_t rc = check_desc(desc)) return rc;
-    GCBF_REQUIRE(agent && hits && row_start && row_deg && edge_recv && edge_src && counters, "NULL pointer argument");
+    GCBF_REQUIRE((agent || tail.z) && hits && row_start && row_deg && edge_recv && edge_src && counters,
+                 "NULL pointer argument");
+    GCBF_REQUIRE(!tail.z || (tail.bHO && tail.agent_prev && tail.goal && tail.row_start_prev && tail.row_deg_prev &&
+                             tail.edge_src_prev && tail.action && tail.next_agent && reward && cost &&
+                             tail.row_start_prev != row_start && tail.edge_src_prev != edge_src),
+                 "fused policy tail: NULL argument or edge lists not double-buffered");
     GCBF_REQUIRE(desc->n_obs == 0 || obstacles, "obstacles is NULL but n_obs > 0");
     GCBF_REQUIRE(!(flags & 1) || ray_table, "ray_table is NULL");
     GCBF_REQUIRE(desc->edge_cap > 0, "edge_cap must be positive");
@@ -877,7 +864,7 @@ int32_t gcbf::graph_build_impl(const gcbf_env_desc* desc, const float* agent, co
         auto kern = graph_build_kernel<KIND>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, GB_WARPS * 32, smem, st>>>(*desc, agent, obstacles, ray_table, hits, row_start, row_deg,
-                                                edge_recv, edge_src, counters, flags & 1, terms, reward, cost);
+                                                edge_recv, edge_src, counters, flags & 1, tail, reward, cost);
     });
     count_launch();
     return check_launch("graph_build_kernel");

@@ -302,7 +302,7 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
                               const float* agent, const float* goal, const float* hits, const int32_t* row_start,
                               const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src,
                               const int32_t* counters, int clip_all, float* out, float* ws, cudaStream_t st,
-                              float* z_out = nullptr, int* z_parts = nullptr) {
+                              float* z_out = nullptr, int* z_parts = nullptr, int32_t* zero_counter = nullptr) {
     // z_out != nullptr (rollout step): instead of `out`, write the output layer's pre-activation partial sums
     // z[part][A][4] (no bias, no tanh) for policy_tail_kernel
     const int ed = env_ed(d->env_kind);
@@ -333,7 +333,7 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
         {
             const int grid = min((A + 7) / 8, 4 * nsm);
             attn_aggregate_kernel<<<grid, 256, 0, st>>>(A, cap, nullptr, ws + W.msg, blob + I.a23, blob + I.c23, row_start,
-                                                        row_deg, ws + W.att, ws + W.ag);
+                                                        row_deg, ws + W.att, ws + W.ag, zero_counter);
             count_launch();
             if ((rc = check_launch("attn_aggregate_kernel"))) return rc;
         }
@@ -354,7 +354,7 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
         {
             const int grid = min((A + 7) / 8, 4 * nsm);
             attn_aggregate_kernel<<<grid, 256, 0, st>>>(A, cap, ws + W.g1, ws + W.msg, blob + I.a23, blob + I.c23, row_start,
-                                                        row_deg, ws + W.att, ws + W.ag);
+                                                        row_deg, ws + W.att, ws + W.ag, zero_counter);
             count_launch();
             if ((rc = check_launch("attn_aggregate_kernel"))) return rc;
         }
@@ -427,53 +427,64 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_gnn_infer(
 namespace gcbf {
 int32_t graph_build_impl(const gcbf_env_desc* desc, const float* agent, const float* obstacles, const float* ray_table,
                          float* hits, int32_t* row_start, int32_t* row_deg, int32_t* edge_recv, int32_t* edge_src,
-                         int32_t* counters, int32_t flags, const float* terms, float* reward, float* cost, void* stream);
-int32_t policy_tail_impl(const gcbf_env_desc* desc, const float* z, int parts, int z_cap, const float* bHO,
-                         const float* agent, const float* goal, const float* obstacles, const int32_t* row_start,
-                         const int32_t* row_deg, const int32_t* edge_src, float* action, float* next_agent, float* terms,
-                         int32_t* zero_counter, cudaStream_t st);
+                         int32_t* counters, int32_t flags, const TailArgs& tail, float* reward, float* cost, void* stream);
 }  // namespace gcbf
 
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step(
     const gcbf_env_desc* desc, const float* actor_params, const float* infer_blob, int32_t use_tensor_cores,
     const float* agent, const float* goal, const float* obstacles, const float* ray_table, const float* hits,
-    int32_t* row_start, int32_t* row_deg, int32_t* edge_recv, int32_t* edge_src, const int32_t* counters,
-    float* action, float* next_agent, float* next_hits, int32_t* next_counters, float* reward, float* cost,
-    float* workspace, int64_t workspace_floats, void* stream) {
+    const int32_t* row_start, const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src,
+    const int32_t* counters, float* action, float* next_agent, float* next_hits, int32_t* next_row_start,
+    int32_t* next_row_deg, int32_t* next_edge_recv, int32_t* next_edge_src, int32_t* next_counters, float* reward,
+    float* cost, float* workspace, int64_t workspace_floats, void* stream) {
     GCBF_REQUIRE(desc && actor_params && infer_blob && agent && goal && ray_table && hits && row_start && row_deg &&
-                     edge_recv && edge_src && counters && action && next_agent && next_hits && next_counters && reward &&
-                     cost && workspace, "gcbf_rollout_step: NULL pointer argument");
+                     edge_recv && edge_src && counters && action && next_agent && next_hits && next_row_start &&
+                     next_row_deg && next_edge_recv && next_edge_src && next_counters && reward && cost && workspace,
+                 "gcbf_rollout_step: NULL pointer argument");
+    GCBF_REQUIRE(next_row_start != row_start && next_row_deg != row_deg && next_edge_recv != edge_recv &&
+                     next_edge_src != edge_src && next_counters != counters,
+                 "gcbf_rollout_step: the next graph must not alias the current one (double-buffer the edge lists)");
     GCBF_REQUIRE(desc->env_kind >= 0 && desc->env_kind <= 3 && desc->edge_cap > 0, "gcbf_rollout_step: bad descriptor");
     GCBF_REQUIRE(desc->n_obs == 0 || obstacles, "obstacles is NULL but n_obs > 0");
     const int nu = env_nu(desc->env_kind);
     const int64_t A = (int64_t)desc->n_graphs * desc->n_agents;
     const GnnWs W = make_ws(desc->edge_cap, A);
-    const int64_t need = W.total + 3 * A + 8 * A + 8;
+    const int64_t need = W.total + 8 * A + 8;
     GCBF_REQUIRE(workspace_floats >= need, "workspace too small: %lld < %lld floats", (long long)workspace_floats,
                  (long long)need);
-    GCBF_REQUIRE((((uintptr_t)actor_params | (uintptr_t)workspace | (uintptr_t)infer_blob) & 15) == 0,
-                 "params/infer_blob/workspace must be 16-byte aligned");
+    GCBF_REQUIRE(((uintptr_t)workspace & 15) == 0, "workspace must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const InferLayout I = make_infer_layout(nu);
-    float* terms = workspace + ((W.total + 3) & ~(int64_t)3);
-    float* z = terms + ((3 * A + 3) & ~(int64_t)3);          // [2][A][4] output-layer partial sums
+    float* z = workspace + ((W.total + 3) & ~(int64_t)3);    // [2][A][4] output-layer partial sums
     int32_t rc;
     int parts = 1;
-    // (Programmatic dependent launch of this 7-kernel chain was built and measured: +1 % (98.2 vs 97.2 M env-steps/s;
-    //  inside a CUDA graph the kernel-to-kernel gap is already ~1 us) and it was NOT safe as written -- a dependent
-    //  kernel that starts early can keep L1 / read-only-cache lines of buffers its predecessor rewrites (DubinsCar
-    //  rollouts became non-deterministic with only the edge-message GEMM launched that way).  Removed; what stayed
-    //  is the memset-free chain (policy_tail clears the next edge counter), worth +5 %.)
+    // 6 launches, no memset / copy node in between: {edge features + message layer}, {gate layer -> logits},
+    // {segment softmax + aggregate; clears the next edge counter}, {update layer}, {folded update/head layer + output
+    // layer partial sums}, {policy tail fused into the graph build of the next state}.
+    // (Programmatic dependent launch of this chain was built and measured: +1 % (inside a CUDA graph the
+    //  kernel-to-kernel gap is already ~1 us) and it was NOT safe as written -- a dependent kernel that starts early
+    //  can keep L1 / read-only-cache lines of buffers its predecessor rewrites (DubinsCar rollouts became
+    //  non-deterministic with only the edge-message GEMM launched that way).  Removed.)
     if ((rc = gnn_infer_impl(desc, nu, actor_params, infer_blob, use_tensor_cores, agent, goal, hits, row_start, row_deg,
-                             edge_recv, edge_src, counters, 0, nullptr, workspace, st, z, &parts))) return rc;
-    if ((rc = policy_tail_impl(desc, z, parts, (int)A, infer_blob + I.bho, agent, goal, obstacles, row_start, row_deg,
-                               edge_src, action, next_agent, terms, next_counters, st))) return rc;
-    return graph_build_impl(desc, next_agent, obstacles, ray_table, next_hits, row_start, row_deg, edge_recv, edge_src,
-                            next_counters, 1 | 4, terms, reward, cost, stream);
+                             edge_recv, edge_src, counters, 0, nullptr, workspace, st, z, &parts, next_counters))) return rc;
+    TailArgs tl;
+    tl.z = z;
+    tl.parts = parts;
+    tl.z_cap = (int)A;
+    tl.bHO = infer_blob + I.bho;
+    tl.agent_prev = agent;
+    tl.goal = goal;
+    tl.row_start_prev = row_start;
+    tl.row_deg_prev = row_deg;
+    tl.edge_src_prev = edge_src;
+    tl.action = action;
+    tl.next_agent = next_agent;
+    return graph_build_impl(desc, nullptr, obstacles, ray_table, next_hits, next_row_start, next_row_deg, next_edge_recv,
+                            next_edge_src, next_counters, 1 | 4, tl, reward, cost, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t gcbf_rollout_workspace_floats(const gcbf_env_desc* desc) {
     if (!desc || desc->edge_cap <= 0 || desc->n_graphs <= 0 || desc->n_agents <= 0) return -1;
     const int64_t A = (int64_t)desc->n_graphs * desc->n_agents;
-    return make_ws(desc->edge_cap, A).total + 3 * A + 8 * A + 16;
+    return make_ws(desc->edge_cap, A).total + 8 * A + 16;
 }

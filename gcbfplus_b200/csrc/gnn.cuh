@@ -146,8 +146,11 @@ static __global__ void __launch_bounds__(256)
 attn_aggregate_kernel(const int A, const int edge_cap, const float* __restrict__ G2, const float* __restrict__ MSG,
                       const float* __restrict__ a3, const float* __restrict__ ba3,
                       const int32_t* __restrict__ row_start, const int32_t* __restrict__ row_deg,
-                      float* __restrict__ ATT, float* __restrict__ AG) {
+                      float* __restrict__ ATT, float* __restrict__ AG, int32_t* __restrict__ zero_counter = nullptr) {
     // G2 == nullptr: ATT already holds the gate logits (written by the EPI_RELU_DOT GEMM epilogue)
+    // zero_counter (rollout step): edge counter of the NEXT graph, cleared here so that no memset node sits in the
+    // per-step kernel chain (the graph build two kernels later accumulates into it)
+    if (zero_counter && blockIdx.x == 0 && threadIdx.x == 0) zero_counter[0] = 0;
     const int lane = threadIdx.x & 31;
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
     const float4 w = G2 ? *reinterpret_cast<const float4*>(a3 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);

@@ -28,10 +28,12 @@ class _Chain:
         self.desc = env.desc(E, eng.O)
         cap = self.desc.edge_cap
         self.pi = torch.zeros(E, N, nu, dtype=f32, device=dev)
-        self.row_start = torch.zeros(E * N, dtype=i32, device=dev)
-        self.row_deg = torch.zeros(E * N, dtype=i32, device=dev)
-        self.edge_recv = torch.zeros(cap, dtype=i32, device=dev)
-        self.edge_src = torch.zeros(cap, dtype=i32, device=dev)
+        # edge lists are double-buffered: step t reads half t % 2 while the graph of state t+1 is written into the
+        # other half (gcbf_rollout_step's fused tail + graph build reads the old lists for the step cost)
+        self.row_start = torch.zeros(2, E * N, dtype=i32, device=dev)
+        self.row_deg = torch.zeros(2, E * N, dtype=i32, device=dev)
+        self.edge_recv = torch.zeros(2, cap, dtype=i32, device=dev)
+        self.edge_src = torch.zeros(2, cap, dtype=i32, device=dev)
         self.counters = torch.zeros(eng.T + 1, 4, dtype=i32, device=dev)
         n_ws = env.lib.gcbf_rollout_workspace_floats(C.byref(self.desc))
         self.ws = torch.empty(int(n_ws), dtype=f32, device=dev)
@@ -91,26 +93,30 @@ class RolloutEngine:
         rc = env.lib.gcbf_graph_build(C.byref(d), self.agent[t, ch.e0].data_ptr(),
                                       self.obstacles[ch.e0].data_ptr() if self.O > 0 else None,
                                       env.ray_table.data_ptr(), self.hits[t, ch.e0].data_ptr(),
-                                      ch.row_start.data_ptr(), ch.row_deg.data_ptr(), ch.edge_recv.data_ptr(),
-                                      ch.edge_src.data_ptr(), ch.counters[t].data_ptr(), 1, stream)
+                                      ch.row_start[t % 2].data_ptr(), ch.row_deg[t % 2].data_ptr(),
+                                      ch.edge_recv[t % 2].data_ptr(), ch.edge_src[t % 2].data_ptr(),
+                                      ch.counters[t].data_ptr(), 1, stream)
         _lib.check(rc, "gcbf_graph_build")
 
     def _step(self, ch: _Chain, t: int, stream: int) -> None:
         env, d = self.env, ch.desc
         obs = self.obstacles[ch.e0].data_ptr() if self.O > 0 else None
-        if self.policy == "actor":      # algo.step + env.step + get_graph(next) in one call (8 launches)
+        b = t % 2
+        if self.policy == "actor":      # algo.step + env.step + get_graph(next) in one call (6 launches)
             rc = env.lib.gcbf_rollout_step(
                 C.byref(d), self.params_buf.data_ptr(), self.infer_blob.data_ptr(), self.use_tc,
                 self.agent[t, ch.e0].data_ptr(), self.goal[ch.e0].data_ptr(), obs, env.ray_table.data_ptr(),
-                self.hits[t, ch.e0].data_ptr(), ch.row_start.data_ptr(), ch.row_deg.data_ptr(), ch.edge_recv.data_ptr(),
-                ch.edge_src.data_ptr(), ch.counters[t].data_ptr(), self.actions[t, ch.e0].data_ptr(),
-                self.agent[t + 1, ch.e0].data_ptr(), self.hits[t + 1, ch.e0].data_ptr(), ch.counters[t + 1].data_ptr(),
+                self.hits[t, ch.e0].data_ptr(), ch.row_start[b].data_ptr(), ch.row_deg[b].data_ptr(),
+                ch.edge_recv[b].data_ptr(), ch.edge_src[b].data_ptr(), ch.counters[t].data_ptr(),
+                self.actions[t, ch.e0].data_ptr(), self.agent[t + 1, ch.e0].data_ptr(),
+                self.hits[t + 1, ch.e0].data_ptr(), ch.row_start[1 - b].data_ptr(), ch.row_deg[1 - b].data_ptr(),
+                ch.edge_recv[1 - b].data_ptr(), ch.edge_src[1 - b].data_ptr(), ch.counters[t + 1].data_ptr(),
                 self.rewards[t, ch.e0:].data_ptr(), self.costs[t, ch.e0:].data_ptr(), ch.ws.data_ptr(), ch.ws.numel(),
                 stream)
             _lib.check(rc, "gcbf_rollout_step")
             return
         rc = env.lib.gcbf_env_step(C.byref(d), self.agent[t, ch.e0].data_ptr(), self.goal[ch.e0].data_ptr(), obs,
-                                   None, ch.row_start.data_ptr(), ch.row_deg.data_ptr(), ch.edge_src.data_ptr(),
+                                   None, ch.row_start[b].data_ptr(), ch.row_deg[b].data_ptr(), ch.edge_src[b].data_ptr(),
                                    self.actions[t, ch.e0].data_ptr(), self.agent[t + 1, ch.e0].data_ptr(),
                                    self.rewards[t, ch.e0:].data_ptr(), self.costs[t, ch.e0:].data_ptr(), 2, stream)
         _lib.check(rc, "gcbf_env_step")

@@ -167,17 +167,24 @@ int32_t gcbf_act(const gcbf_env_desc* desc, const float* agent, const float* goa
 /* ---------------------------------------------------------------- fused rollout step (a8 body)
  * One iteration of the scan body of rollout() (gcbfplus/trainer/utils.py:46-49): algo.step
  * (algo/gcbf_plus.py:182-186) + env.step incl. get_graph of the next state
- * (env/double_integrator.py:145-181) for the G envs of the batch, 8 kernel launches:
- * policy forward with folded weights -> {tanh head, a = 2 pi + u_ref, clip, Euler, per-agent
- * reward / cost terms} -> {LiDAR, neighbour lists of the next state, per-env reward / cost}.
- * The edge lists are rebuilt in place for the next state; counters / next_counters are the
- * 4-int counter blocks of the current / next graph.  workspace: gcbf_rollout_workspace_floats(). */
+ * (env/double_integrator.py:145-181) for the G envs of the batch, 6 kernel launches and no
+ * memset / copy in between: policy forward with folded weights (5 launches: edge features + message
+ * layer, gate logits, segment softmax + aggregate, update layer, folded update/head layer with the
+ * output layer's partial sums in its epilogue) -> one kernel that applies the policy tail
+ * {tanh head, a = 2 pi + u_ref, clip, Euler} for the whole graph in every CTA, records actions /
+ * next states / per-env reward and cost, and builds LiDAR hits + neighbour lists of the next state.
+ * The NEXT graph (next_row_start ... next_counters) must not alias the current one: callers
+ * double-buffer the edge lists (the cost of the step reads the current lists while the next ones are
+ * written).  counters / next_counters are the 4-int counter blocks of the current / next graph.
+ * workspace: gcbf_rollout_workspace_floats(). */
 int64_t gcbf_rollout_workspace_floats(const gcbf_env_desc* desc);
 int32_t gcbf_rollout_step(const gcbf_env_desc* desc, const float* actor_params, const float* infer_blob,
                           int32_t use_tensor_cores, const float* agent, const float* goal,
                           const float* obstacles, const float* ray_table, const float* hits,
-                          int32_t* row_start, int32_t* row_deg, int32_t* edge_recv, int32_t* edge_src,
-                          const int32_t* counters, float* action, float* next_agent, float* next_hits,
+                          const int32_t* row_start, const int32_t* row_deg, const int32_t* edge_recv,
+                          const int32_t* edge_src, const int32_t* counters, float* action,
+                          float* next_agent, float* next_hits, int32_t* next_row_start,
+                          int32_t* next_row_deg, int32_t* next_edge_recv, int32_t* next_edge_src,
                           int32_t* next_counters, float* reward, float* cost, float* workspace,
                           int64_t workspace_floats, void* stream);
 
