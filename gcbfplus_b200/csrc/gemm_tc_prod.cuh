@@ -29,13 +29,27 @@ struct ProdArgs {
     int edge_cap;
 };
 
-template <int BN, int EPI, int PROD, int KIND>
+// CHAIN (PROD_EDGE, BN = 128 only): a second GEMM is chained onto the tile while it is still on the SM --
+//   logit[m] = relu(MSG[m, :128] @ A1 + b_g) . avec + c            (gate layer + folded gate vector, gnn.py:64-67)
+// The epilogue warps hand the message tile over in shared memory (tf32 hi / lo planes in the K-major SWIZZLE_128B
+// layout, 4 k-blocks of 32 = 128 KB over the drained pipeline stages 0-1), the gate weights stream through the third
+// stage (two 32 KB slots), the accumulator lives in the second half of the CTA's TMEM.  One launch (and one
+// round trip of MSG through L2) less per env-step; the fixed ~6 us of a GEMM launch is paid once for both layers.
+struct ChainArgs {
+    const float* bias_g;   // [128] gate hidden-layer bias
+    const float* avec;     // [128] folded gate vector
+    const float* cst;      // [1]   folded gate constant
+    float* logits;         // [M]   out
+};
+
+template <int BN, int EPI, int PROD, int KIND, bool CHAIN>
 __global__ void __launch_bounds__(THREADS_NN, 1)
 gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                     const __grid_constant__ ProdArgs pa, const float* __restrict__ bias,
                     const float* __restrict__ bias2, float* __restrict__ C, const float* __restrict__ aux,
                     const int32_t* __restrict__ m_ptr, const int m_fixed, const int m_cap, const int K, const int N,
-                    const int ndot) {
+                    const int ndot, const __grid_constant__ CUtensorMap tmB2h, const __grid_constant__ CUtensorMap tmB2l,
+                    const ChainArgs ch) {
     using CF = Cfg<BN>;
     using T = EnvTraits<KIND>;
     constexpr int ED = T::ED, SD = T::SD;
@@ -49,7 +63,13 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
     uint64_t* tmem_full = bars + 3 * STAGES;
     uint64_t* tmem_empty = bars + 3 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+    uint64_t* b2_full = bars + 16;             // [2] CHAIN: gate-weight slot landed
+    uint64_t* b2_empty = bars + 18;            // [2] CHAIN: gate-weight slot consumed
+    uint64_t* a2_ready = bars + 20;            // CHAIN: message tile written to shared memory (128 arrivals)
+    uint64_t* tmem2_full = bars + 21;          // CHAIN: gate accumulator ready / chained GEMM retired
     float* sW = reinterpret_cast<float*>(smem + STAGES * CF::STAGE_BYTES + 256);   // PROD_EDGE: [ED + 3][256]
+    static_assert(!CHAIN || (BN == 128 && PROD == PROD_EDGE && STAGES == 3 && CF::STAGE_BYTES == 65536),
+                  "chained gate GEMM: 128-wide message tile over three 64 KB stages");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = N / BN;                // 1, or 2 when a 256-wide layer is split to fill more SMs
@@ -64,6 +84,14 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 128);
+        }
+        if (CHAIN) {
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&b2_full[i], 1);
+                mbar_init(&b2_empty[i], 1);
+            }
+            mbar_init(a2_ready, 128);
+            mbar_init(tmem2_full, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -91,9 +119,11 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
     if (warp == 0) {
         // ================= TMA producer (weights only) =================
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
                 const int n0 = (tile % tiles_n) * BN;
+                // CHAIN: the previous tile's chained GEMM still reads stages 0-2 until it retires
+                if (CHAIN && tcount > 0) mbar_wait(tmem2_full, (tcount - 1) & 1);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -103,6 +133,17 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                     tma_load_2d(st + 2 * CF::A_BYTES, &tmBh, &full[s], kb * BK, n0);
                     tma_load_2d(st + 2 * CF::A_BYTES + CF::B_BYTES, &tmBl, &full[s], kb * BK, n0);
                 }
+                if (CHAIN) {
+                    mbar_wait(&tmem_full[0], tcount & 1);      // every main-loop MMA retired: stage 2 is free
+                    for (int kb2 = 0; kb2 < 4; ++kb2) {
+                        const uint32_t j2 = tcount * 4 + kb2, slot = j2 & 1, use = j2 >> 1;
+                        mbar_wait(&b2_empty[slot], (use & 1) ^ 1);
+                        uint8_t* sl = smem + 2 * CF::STAGE_BYTES + slot * 32768;
+                        mbar_expect_tx(&b2_full[slot], 32768);
+                        tma_load_2d(sl, &tmB2h, &b2_full[slot], kb2 * BK, 0);
+                        tma_load_2d(sl + 16384, &tmB2l, &b2_full[slot], kb2 * BK, 0);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -111,9 +152,9 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
             constexpr uint32_t idesc = make_idesc(BM, BN);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t acc = tcount & 1;
+                const uint32_t acc = CHAIN ? 0u : (tcount & 1);
                 const uint32_t tmem_d = tmem_base + acc * BN;
-                mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+                mbar_wait(&tmem_empty[acc], (CHAIN ? (tcount & 1) : ((tcount >> 1) & 1)) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -137,16 +178,43 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                     umma_commit(&empty[s]);
                 }
                 umma_commit(&tmem_full[acc]);
+                if (CHAIN) {
+                    // ---- chained gate GEMM: D2[128 x 128] = MSG tile (shared memory) x A1, accumulator in columns BN..
+                    mbar_wait(&tmem_empty[1], (tcount & 1) ^ 1);
+                    mbar_wait(a2_ready, tcount & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int kb2 = 0; kb2 < 4; ++kb2) {
+                        const uint32_t j2 = tcount * 4 + kb2, slot = j2 & 1, use = j2 >> 1;
+                        mbar_wait(&b2_full[slot], use & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_hi = smem_u32(smem + kb2 * 32768);
+                        const uint32_t a_lo = a_hi + 16384;
+                        const uint32_t b_hi = smem_u32(smem + 2 * CF::STAGE_BYTES + slot * 32768);
+                        const uint32_t b_lo = b_hi + 16384;
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint32_t koff = k * UMMA_K * 4;
+                            const uint64_t dah = make_desc(a_hi + koff), dal = make_desc(a_lo + koff);
+                            const uint64_t dbh = make_desc(b_hi + koff), dbl = make_desc(b_lo + koff);
+                            umma_tf32(tmem_base + BN, dal, dbh, idesc, (kb2 | k) != 0);
+                            umma_tf32(tmem_base + BN, dah, dbl, idesc, 1u);
+                            umma_tf32(tmem_base + BN, dah, dbh, idesc, 1u);
+                        }
+                        umma_commit(&b2_empty[slot]);
+                    }
+                    umma_commit(tmem2_full);
+                }
             }
         }
     } else if (warp < 6) {
         // ================= operand warps: produce the A tile (thread = row) =================
         const int r = threadIdx.x - 64;           // row inside the tile, 0..127
         const int A_tot = pa.d.n_graphs * pa.d.n_agents;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t it = 0, tcount_p = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount_p) {
             const int m = (tile / tiles_n) * BM + r;
             const bool row_ok = m < M;
+            if (CHAIN && tcount_p > 0) mbar_wait(tmem2_full, (tcount_p - 1) & 1);   // stages still feed the chained GEMM
             // ---- per-row setup
             float f[ED];
             int stype = 0;
@@ -237,8 +305,8 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-            const uint32_t acc = tcount & 1;
-            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+            const uint32_t acc = CHAIN ? 0u : (tcount & 1);
+            mbar_wait(&tmem_full[acc], CHAIN ? (tcount & 1) : ((tcount >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = quarter * 32 + lane;
             const int m = m0 + row;
@@ -246,6 +314,29 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                if (CHAIN) {
+                    // message tile -> global (the aggregation kernel reads it) and -> shared memory as the A operand
+                    // of the chained GEMM: k-block c0 / 32, row `row`, 16-byte chunks XOR-swizzled like the TMA does
+                    uint8_t* hi_row = smem + (c0 >> 5) * 32768 + row * 128;
+                    uint8_t* lo_row = hi_row + 16384;
+                    float* crow = C + (size_t)m * N + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
+                        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                        if (m < M) *reinterpret_cast<float4*>(crow + j) = o;
+                        float4 h, l;
+                        h.x = rn_tf32(o.x); h.y = rn_tf32(o.y); h.z = rn_tf32(o.z); h.w = rn_tf32(o.w);
+                        l.x = rn_tf32(o.x - h.x); l.y = rn_tf32(o.y - h.y);
+                        l.z = rn_tf32(o.z - h.z); l.w = rn_tf32(o.w - h.w);
+                        const int off = (((j >> 2) ^ (row & 7)) << 4);
+                        *reinterpret_cast<float4*>(hi_row + off) = h;
+                        *reinterpret_cast<float4*>(lo_row + off) = l;
+                    }
+                    continue;
+                }
                 if (m < M) {
                     const int n = n0 + c0;
                     float* crow = C + (size_t)m * N + n;
@@ -267,6 +358,27 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (CHAIN) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> MMA (async proxy)
+                mbar_arrive(a2_ready);
+                mbar_arrive(&tmem_empty[0]);
+                // ---- gate logit from the chained accumulator: relu(acc2 + b_g) . avec + c
+                mbar_wait(tmem2_full, tcount & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float dot = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        dot = fmaf(fmaxf(__uint_as_float(v[j]) + ch.bias_g[c0 + j], 0.f), ch.avec[c0 + j], dot);
+                }
+                if (m < M) ch.logits[m] = dot + ch.cst[0];
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&tmem_empty[1]);
+                continue;
+            }
             mbar_arrive(&tmem_empty[acc]);
         }
     }
@@ -279,17 +391,23 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
     (void)ndot;
 }
 
-template <int BN, int EPI, int PROD, int KIND>
+template <int BN, int EPI, int PROD, int KIND, bool CHAIN = false>
 inline int32_t launch_prod_inst(const CUtensorMap& tmB, const CUtensorMap& tmBl, const ProdArgs& pa, const float* bias,
-                                const float* bias2, float* C, RowCount rc, int K, int N, int grid, cudaStream_t st) {
+                                const float* bias2, float* C, RowCount rc, int K, int N, int grid, cudaStream_t st,
+                                const CUtensorMap* tmB2h = nullptr, const CUtensorMap* tmB2l = nullptr,
+                                const ChainArgs* chain = nullptr) {
     constexpr int smem = Cfg<BN>::SMEM_BYTES + 9 * 256 * 4;
-    auto kern = gemm_tc_prod_kernel<BN, EPI, PROD, KIND>;
+    auto kern = gemm_tc_prod_kernel<BN, EPI, PROD, KIND, CHAIN>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
-    kern<<<grid, THREADS_NN, smem, st>>>(tmB, tmBl, pa, bias, bias2, C, nullptr, rc.ptr, rc.fixed, rc.cap, K, N, 0);
+    ChainArgs ch;
+    memset(&ch, 0, sizeof(ch));
+    if (chain) ch = *chain;
+    kern<<<grid, THREADS_NN, smem, st>>>(tmB, tmBl, pa, bias, bias2, C, nullptr, rc.ptr, rc.fixed, rc.cap, K, N, 0,
+                                         tmB2h ? *tmB2h : tmB, tmB2l ? *tmB2l : tmBl, ch);
     count_launch();
     return check_launch("gemm_tc_prod_kernel");
 }
@@ -298,7 +416,11 @@ inline int32_t launch_prod_inst(const CUtensorMap& tmB, const CUtensorMap& tmBl,
 inline int32_t launch_edge_msg(const gcbf_env_desc* d, const float* W1, const float* b1, const float* agent,
                                const float* goal, const float* hits, const int32_t* edge_recv,
                                const int32_t* edge_src, const int32_t* counters, int clip_all, const float* Bt_hi,
-                               const float* Bt_lo, const float* bias, float* msg, cudaStream_t st) {
+                               const float* Bt_lo, const float* bias, float* msg, cudaStream_t st,
+                               const float* gate_Bt_hi = nullptr, const float* gate_Bt_lo = nullptr,
+                               const ChainArgs* chain = nullptr) {
+    // chain != nullptr: the gate layer (K = N = 128, weights gate_Bt_*) and its folded gate vector run inside the same
+    // kernel and the logits are written to chain->logits
     ProdArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.d = *d;
@@ -310,6 +432,16 @@ inline int32_t launch_edge_msg(const gcbf_env_desc* d, const float* W1, const fl
     if (int32_t r = make_map(&tmBl, Bt_lo, N, K, N)) return r;
     const RowCount rc{counters, 0, d->edge_cap};
     const int grid = min((d->edge_cap + BM - 1) / BM, sm_count());
+    if (chain) {
+        CUtensorMap tmG, tmGl;
+        if (int32_t r = make_map(&tmG, gate_Bt_hi, 128, 128, 128)) return r;
+        if (int32_t r = make_map(&tmGl, gate_Bt_lo, 128, 128, 128)) return r;
+        GCBF_DISPATCH_ENV(d->env_kind, {
+            return launch_prod_inst<128, EPI_BIAS, PROD_EDGE, KIND, true>(tmB, tmBl, pa, bias, nullptr, msg, rc, K, N, grid, st,
+                                                                          &tmG, &tmGl, chain);
+        });
+        return -1;
+    }
     GCBF_DISPATCH_ENV(d->env_kind, {
         return launch_prod_inst<128, EPI_BIAS, PROD_EDGE, KIND>(tmB, tmBl, pa, bias, nullptr, msg, rc, K, N, grid, st);
     });

@@ -1,4 +1,6 @@
 // gnn.cu -- GNN forward for one network (CBF h(x) or policy pi(x)) over a swarm batch.
+#include <stdlib.h>
+
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
 #include "gnn.cuh"
@@ -323,15 +325,29 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
         // tensor-core path, 4 launches: {edge features + layer 1 produced in-kernel -> folded message GEMM},
         // {gate layer + folded gate vector -> logits}, {softmax-aggregate produced in-kernel -> update layer 1},
         // {update/head folded layer (+ output layer) below}
-        if ((rc = tc::launch_edge_msg(d, P + L.w[L_MSG0], P + L.b[L_MSG0], agent, goal, hits, edge_recv, edge_src, counters,
-                                      clip_all, blob + I.t_w23, blob + I.t_w23 + 256 * 128, blob + I.b23, ws + W.msg, st))) return rc;
-        if ((rc = tc::launch_gemm_tc(EPI_RELU_DOT, false, ws + W.msg, blob + I.t_a1, blob + I.t_a1 + 128 * 128,
-                                     P + L.b[L_ATT0], blob + I.c23, ws + W.att, blob + I.a23, re, 128, 128, st))) return rc;
+        // GCBF_CHAIN=0: gate layer as its own GEMM launch (A/B measurements)
+        static const bool chain_on = [] { const char* e = getenv("GCBF_CHAIN"); return !(e && e[0] == '0'); }();
+        if (chain_on) {
+            tc::ChainArgs ch;
+            ch.bias_g = P + L.b[L_ATT0];
+            ch.avec = blob + I.a23;
+            ch.cst = blob + I.c23;
+            ch.logits = ws + W.att;
+            if ((rc = tc::launch_edge_msg(d, P + L.w[L_MSG0], P + L.b[L_MSG0], agent, goal, hits, edge_recv, edge_src,
+                                          counters, clip_all, blob + I.t_w23, blob + I.t_w23 + 256 * 128, blob + I.b23,
+                                          ws + W.msg, st, blob + I.t_a1, blob + I.t_a1 + 128 * 128, &ch))) return rc;
+        } else {
+            if ((rc = tc::launch_edge_msg(d, P + L.w[L_MSG0], P + L.b[L_MSG0], agent, goal, hits, edge_recv, edge_src,
+                                          counters, clip_all, blob + I.t_w23, blob + I.t_w23 + 256 * 128, blob + I.b23,
+                                          ws + W.msg, st))) return rc;
+            if ((rc = tc::launch_gemm_tc(EPI_RELU_DOT, false, ws + W.msg, blob + I.t_a1, blob + I.t_a1 + 128 * 128,
+                                         P + L.b[L_ATT0], blob + I.c23, ws + W.att, blob + I.a23, re, 128, 128, st))) return rc;
+        }
         // (measured: producing the aggregate inside the update GEMM (tc::launch_attn_upd) is slower than the
         //  separate warp-per-receiver kernel + TMA-fed GEMM: 36.6 us vs 13.2 + 11.7 us -- its N-split repeats
         //  the aggregation and the per-thread MSG gathers are latency-bound; the edge producer above is a win)
         {
-            const int grid = min((A + 7) / 8, 4 * nsm);
+            const int grid = min((A + 7) / 8, 8 * nsm);   // 8 x 256 threads per SM: one receiver per warp in flight (latency-bound kernel)
             attn_aggregate_kernel<<<grid, 256, 0, st>>>(A, cap, nullptr, ws + W.msg, blob + I.a23, blob + I.c23, row_start,
                                                         row_deg, ws + W.att, ws + W.ag, zero_counter);
             count_launch();
