@@ -143,7 +143,7 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
                    const float* __restrict__ ray_table, float* __restrict__ hits, int32_t* __restrict__ row_start,
                    int32_t* __restrict__ row_deg, int32_t* __restrict__ edge_recv, int32_t* __restrict__ edge_src,
                    int32_t* __restrict__ counters, const int do_cast, const TailArgs tl,
-                   float* __restrict__ reward, float* __restrict__ cost) {
+                   float* __restrict__ reward, float* __restrict__ cost, const int rounds) {
     using T = EnvTraits<KIND>;
     constexpr int SD = T::SD, PD = T::PD, NU = T::NU;
     constexpr int OBW = (PD == 2) ? 16 : 4;
@@ -273,7 +273,10 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
         __syncthreads();
     }
 
-    const int i = blockIdx.x * GB_WARPS + warp;
+    // A CTA serves `rounds` groups of GB_WARPS agents: at ~60 registers per thread one 1024-thread CTA fills an SM, so
+    // the grid is sized to one wave (graph_build_impl) instead of paying the prologue (and the fused tail) per wave.
+    for (int round = 0; round < rounds; ++round) {
+    const int i = (blockIdx.x * rounds + round) * GB_WARPS + warp;
     const bool valid = i < N;
     const int ii = valid ? i : 0;
     float p[PD];
@@ -436,39 +439,40 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
         s_base = (s_off[GB_WARPS] > 0) ? atomicAdd(&counters[0], s_off[GB_WARPS]) : 0;
     }
     __syncthreads();
-    if (!valid) return;
     const int base = s_base + s_off[warp];
     const int a_id = (int)a_glob;
-    if (base + deg > d.edge_cap) {
+    if (valid && base + deg > d.edge_cap) {
         if (lane == 0) {
             atomicOr(&counters[1], 1);
             row_start[a_id] = 0;
             row_deg[a_id] = 0;
         }
-        return;
-    }
-    if (lane == 0) {
-        row_start[a_id] = base;
-        row_deg[a_id] = deg;
-        edge_recv[base] = a_id;
-        edge_src[base] = -1;
-    }
-    int pos = base + 1;
-    const unsigned lt = (1u << lane) - 1u;
-    __syncwarp();
-    for (int w = 0; w < n_words; ++w) {
-        const unsigned bits = my_bits[w];
-        if ((bits >> lane) & 1u) {
-            const int e = pos + __popc(bits & lt);
-            edge_recv[e] = a_id;
-            edge_src[e] = g * N + (w << 5) + lane;
+    } else if (valid) {
+        if (lane == 0) {
+            row_start[a_id] = base;
+            row_deg[a_id] = deg;
+            edge_recv[base] = a_id;
+            edge_src[base] = -1;
         }
-        pos += __popc(bits);
+        int pos = base + 1;
+        const unsigned lt = (1u << lane) - 1u;
+        __syncwarp();
+        for (int w = 0; w < n_words; ++w) {
+            const unsigned bits = my_bits[w];
+            if ((bits >> lane) & 1u) {
+                const int e = pos + __popc(bits & lt);
+                edge_recv[e] = a_id;
+                edge_src[e] = g * N + (w << 5) + lane;
+            }
+            pos += __popc(bits);
+        }
+        if ((hit_bits >> lane) & 1u) {
+            const int e = pos + __popc(hit_bits & lt);
+            edge_recv[e] = a_id;
+            edge_src[e] = -2 - lane;
+        }
     }
-    if ((hit_bits >> lane) & 1u) {
-        const int e = pos + __popc(hit_bits & lt);
-        edge_recv[e] = a_id;
-        edge_src[e] = -2 - lane;
+    __syncthreads();   // s_off / s_base / the per-warp scratch are reused by the next round
     }
 }
 
@@ -859,12 +863,16 @@ int32_t gcbf::graph_build_impl(const gcbf_env_desc* desc, const float* agent, co
         cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t), st);
         if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int32_t)e; }
     }
-    dim3 grid((desc->n_agents + GB_WARPS - 1) / GB_WARPS, desc->n_graphs);
+    // one wave: a 1024-thread CTA owns an SM (register-bound), so each CTA takes `rounds` groups of GB_WARPS agents
+    const int groups = (desc->n_agents + GB_WARPS - 1) / GB_WARPS;
+    int rounds = 1;
+    while (rounds < groups && (int64_t)((groups + rounds - 1) / rounds) * desc->n_graphs > sm_count()) ++rounds;
+    dim3 grid((groups + rounds - 1) / rounds, desc->n_graphs);
     GCBF_DISPATCH_ENV(desc->env_kind, {
         auto kern = graph_build_kernel<KIND>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, GB_WARPS * 32, smem, st>>>(*desc, agent, obstacles, ray_table, hits, row_start, row_deg,
-                                                edge_recv, edge_src, counters, flags & 1, tail, reward, cost);
+                                                edge_recv, edge_src, counters, flags & 1, tail, reward, cost, rounds);
     });
     count_launch();
     return check_launch("graph_build_kernel");

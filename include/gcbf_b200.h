@@ -167,10 +167,11 @@ int32_t gcbf_act(const gcbf_env_desc* desc, const float* agent, const float* goa
 /* ---------------------------------------------------------------- fused rollout step (a8 body)
  * One iteration of the scan body of rollout() (gcbfplus/trainer/utils.py:46-49): algo.step
  * (algo/gcbf_plus.py:182-186) + env.step incl. get_graph of the next state
- * (env/double_integrator.py:145-181) for the G envs of the batch, 6 kernel launches and no
- * memset / copy in between: policy forward with folded weights (5 launches: edge features + message
- * layer, gate logits, segment softmax + aggregate, update layer, folded update/head layer with the
- * output layer's partial sums in its epilogue) -> one kernel that applies the policy tail
+ * (env/double_integrator.py:145-181) for the G envs of the batch, 5 kernel launches and no
+ * memset / copy in between: policy forward with folded weights (4 launches: edge features + message
+ * layer with the gate layer chained onto the tile -> logits, segment softmax + aggregate, update
+ * layer, folded update/head layer with the output layer's partial sums in its epilogue) -> one
+ * kernel that applies the policy tail
  * {tanh head, a = 2 pi + u_ref, clip, Euler} for the whole graph in every CTA, records actions /
  * next states / per-env reward and cost, and builds LiDAR hits + neighbour lists of the next state.
  * The NEXT graph (next_row_start ... next_counters) must not alias the current one: callers
