@@ -88,3 +88,36 @@ def test_parallel_chains_give_identical_results():
         outs[-1]["n_edges"] = eng.counters[:, 0].clone()
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def _rollout_digest():
+    """Small DoubleIntegrator rollout -> sha256 of the recorded states / actions (run in this or a child process)."""
+    import hashlib
+    from gcbfplus_b200.trainer.rollout import RolloutEngine
+    env, g0 = _reset_scene("DoubleIntegrator", 48, 3, 3.0, 6, seed=5)
+    algo = product_algo(env, "DoubleIntegrator")
+    eng = RolloutEngine(env, 3, T=16, n_obs=6)
+    eng.set_params(algo.actor_params)
+    eng.set_initial(g0.agent, g0.goal, g0.obstacle)
+    eng.run()
+    torch.cuda.synchronize()
+    h = hashlib.sha256()
+    for t in (eng.agent, eng.actions, eng.rewards, eng.costs):
+        h.update(t.cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def test_chained_gate_gemm_is_bit_identical_to_separate_launch():
+    """The gate layer chained onto the message tile (shared-memory hand-over, second TMEM accumulator) must give the
+    bits of the two-launch path (GCBF_CHAIN=0): same operand split, same MMA order, same epilogue."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_rollout as t; "
+            "print('DIGEST', t._rollout_digest())" % (here, os.path.dirname(here)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GCBF_CHAIN="0"), capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    other = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0].split()[1]
+    assert other == _rollout_digest()
