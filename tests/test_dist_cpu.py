@@ -86,3 +86,29 @@ def test_two_rank_sharded_gradient_equals_full_batch(tmp_path):
     assert got["counts"].tolist() == [float(unsafe.sum()), float(safe.sum()), float(safe.numel())]
     torch.testing.assert_close(got["packed"], want, atol=1e-12, rtol=1e-9)
     assert float(want[:-1].abs().max()) > 0
+
+
+def test_env_sharded_reset_keys_reproduce_the_unsharded_batch():
+    """rank r of W rolls out environments [lo, hi) of the global batch with the same per-env threefry
+    keys the single-process run uses (trainer.py:134-136), so the union of the shards is the unsharded batch."""
+    import numpy as np
+    from gcbfplus_b200.dist import shard_bounds
+    from gcbfplus_b200.env import make_env
+    from gcbfplus_b200.utils import jrandom as jr
+    env = make_env("DoubleIntegrator", 6, area_size=2.5, num_obs=3, device="cpu")
+    key_x0, _ = jr.split(jr.PRNGKey(3))
+    keys = jr.split(key_x0, 6)
+    reset_keys = jr.split(keys, 2)[:, 0]
+
+    def sample(k):
+        obstacles, k2 = env._sample_obstacles(k)
+        s, g = env._sample_agents_goals(k2, obstacles.packed.numpy())
+        return obstacles.packed.numpy(), s, g
+    full = sample(reset_keys)
+    for world in (2, 3):
+        parts = []
+        for rank in range(world):
+            lo, hi = shard_bounds(6, rank, world)
+            parts.append(sample(reset_keys[lo:hi]))
+        for q in range(3):
+            assert np.array_equal(np.concatenate([p[q] for p in parts], axis=0), full[q])
