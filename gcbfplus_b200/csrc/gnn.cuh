@@ -159,6 +159,39 @@ attn_aggregate_kernel(const int A, const int edge_cap, const float* __restrict__
         const int rs = row_start[a];
         int rd = row_deg[a];
         if (rs < 0 || rs + rd > edge_cap) rd = 0;
+        if (!G2 && rd <= 4) {
+            // inference fast path (typical degree: goal + 0..3 neighbours / hits): every logit and message row is
+            // requested before anything is consumed, so the warp waits for ONE round trip to L2 instead of three
+            float lg[4];
+            float4 mv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = rs + min(q, max(rd - 1, 0));
+                lg[q] = (q < rd) ? ATT[e] : -INFINITY;
+                mv[q] = (q < rd) ? *reinterpret_cast<const float4*>(MSG + (size_t)e * 128 + lane * 4)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mx = fmaxf(mx, lg[q]);      // same left-to-right order as the general path
+            float den = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < rd) den += expf(lg[q] - mx);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < rd) {
+                    const float att = expf(lg[q] - mx) / den;
+                    acc.x = fmaf(att, mv[q].x, acc.x);
+                    acc.y = fmaf(att, mv[q].y, acc.y);
+                    acc.z = fmaf(att, mv[q].z, acc.z);
+                    acc.w = fmaf(att, mv[q].w, acc.w);
+                }
+            }
+            *reinterpret_cast<float4*>(AG + (size_t)a * 128 + lane * 4) = acc;
+            continue;
+        }
         float mx = -INFINITY;
         if (G2) {
             for (int e = rs; e < rs + rd; ++e) {
