@@ -50,6 +50,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// 256-bit global store (sm_100: STG.E.ENL2.256): one full 32-byte sector per lane.  The epilogue owns one output row
+// per lane, so a 128-bit store touches half a sector and the row needs twice the LSU instructions.
+__device__ __forceinline__ void st_global_v8(float* p, const float4& a, const float4& b) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+                 "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ void ld_global_v8(const float* p, float4& a, float4& b) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -288,31 +303,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (m < M) {
                     const int n = n0 + c0;
                     float* crow = C + (size_t)m * N + n;
+                    const float* mrow = (EPI == EPI_RELU_MASK) ? aux + (size_t)m * N + n : nullptr;
+                    // 256-bit accesses when the row is 32-byte aligned (warp-uniform: N % 8 == 0)
+                    const bool wide = ((reinterpret_cast<uintptr_t>(crow) | reinterpret_cast<uintptr_t>(mrow)) & 31) == 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    for (int j = 0; j < 32; j += 8) {
+                        float4 o[2];
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh)
+                            o[hh] = make_float4(__uint_as_float(v[j + 4 * hh]), __uint_as_float(v[j + 4 * hh + 1]),
+                                                __uint_as_float(v[j + 4 * hh + 2]), __uint_as_float(v[j + 4 * hh + 3]));
                         if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) {
-                            const float4 bb = *reinterpret_cast<const float4*>(bias + n + j);
-                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                            if (bias2) {
-                                const float4 b2 = *reinterpret_cast<const float4*>(bias2 + n + j);
-                                o.x += b2.x; o.y += b2.y; o.z += b2.z; o.w += b2.w;
-                            }
-                            if (EPI == EPI_BIAS_RELU) {
-                                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const float4 bb = *reinterpret_cast<const float4*>(bias + n + j + 4 * hh);
+                                o[hh].x += bb.x; o[hh].y += bb.y; o[hh].z += bb.z; o[hh].w += bb.w;
+                                if (bias2) {
+                                    const float4 b2 = *reinterpret_cast<const float4*>(bias2 + n + j + 4 * hh);
+                                    o[hh].x += b2.x; o[hh].y += b2.y; o[hh].z += b2.z; o[hh].w += b2.w;
+                                }
+                                if (EPI == EPI_BIAS_RELU) {
+                                    o[hh].x = fmaxf(o[hh].x, 0.f); o[hh].y = fmaxf(o[hh].y, 0.f);
+                                    o[hh].z = fmaxf(o[hh].z, 0.f); o[hh].w = fmaxf(o[hh].w, 0.f);
+                                }
                             }
                         } else if (EPI == EPI_RELU_MASK) {
-                            const float4 mk = *reinterpret_cast<const float4*>(aux + (size_t)m * N + n + j);
-                            o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
-                            o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+                            float4 mk[2];
+                            if (wide) {
+                                ld_global_v8(mrow + j, mk[0], mk[1]);
+                            } else {
+                                mk[0] = *reinterpret_cast<const float4*>(mrow + j);
+                                mk[1] = *reinterpret_cast<const float4*>(mrow + j + 4);
+                            }
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                o[hh].x = mk[hh].x > 0.f ? o[hh].x : 0.f; o[hh].y = mk[hh].y > 0.f ? o[hh].y : 0.f;
+                                o[hh].z = mk[hh].z > 0.f ? o[hh].z : 0.f; o[hh].w = mk[hh].w > 0.f ? o[hh].w : 0.f;
+                            }
                         }
-                        float4* dst = reinterpret_cast<float4*>(crow + j);
                         if (ACCUM) {
-                            const float4 old = *dst;
-                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            float4 old[2];
+                            if (wide) {
+                                ld_global_v8(crow + j, old[0], old[1]);
+                            } else {
+                                old[0] = *reinterpret_cast<const float4*>(crow + j);
+                                old[1] = *reinterpret_cast<const float4*>(crow + j + 4);
+                            }
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                o[hh].x += old[hh].x; o[hh].y += old[hh].y; o[hh].z += old[hh].z; o[hh].w += old[hh].w;
+                            }
                         }
-                        *dst = o;
+                        if (wide) {
+                            st_global_v8(crow + j, o[0], o[1]);
+                        } else {
+                            *reinterpret_cast<float4*>(crow + j) = o[0];
+                            *reinterpret_cast<float4*>(crow + j + 4) = o[1];
+                        }
                     }
                 }
             }

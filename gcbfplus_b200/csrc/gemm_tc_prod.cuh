@@ -320,13 +320,19 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
                     uint8_t* hi_row = smem + (c0 >> 5) * 32768 + row * 128;
                     uint8_t* lo_row = hi_row + 16384;
                     float* crow = C + (size_t)m * N + n0 + c0;
+                    const bool wide = (reinterpret_cast<uintptr_t>(crow) & 31) == 0;
+                    float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                         const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
                         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                        if (m < M) *reinterpret_cast<float4*>(crow + j) = o;
+                        if (m < M) {
+                            if (!wide) *reinterpret_cast<float4*>(crow + j) = o;
+                            else if (j & 4) st_global_v8(crow + j - 4, prev, o);
+                            else prev = o;
+                        }
                         float4 h, l;
                         h.x = rn_tf32(o.x); h.y = rn_tf32(o.y); h.z = rn_tf32(o.z); h.w = rn_tf32(o.w);
                         l.x = rn_tf32(o.x - h.x); l.y = rn_tf32(o.y - h.y);

@@ -18,7 +18,7 @@ struct GnnWs {
 inline GnnWs make_ws(int64_t cap, int64_t A) {
     GnnWs w;
     int64_t o = 0;
-    auto take = [&](int64_t n) { int64_t r = o; o += (n + 3) & ~(int64_t)3; return r; };
+    auto take = [&](int64_t n) { int64_t r = o; o += (n + 7) & ~(int64_t)7; return r; };   // 32-byte slots: 256-bit epilogue stores
     w.feat = take(cap * FEAT_LD);
     w.x1 = take(cap * 256);
     w.x2 = take(cap * 256);

@@ -719,7 +719,7 @@ static QpWs make_qp_ws(const gcbf_env_desc* d) {
     const ParamLayout Lc = make_layout(ed, 1);
     QpWs t;
     int64_t o = 0;
-    auto take = [&](int64_t n) { int64_t r = o; o += (n + 3) & ~(int64_t)3; return r; };
+    auto take = [&](int64_t n) { int64_t r = o; o += (n + 7) & ~(int64_t)7; return r; };   // 32-byte slots: 256-bit epilogue stores
     t.ws0 = take(W.total);
     t.gws = take(W.total);
     t.pt_cbf = take(make_prepared_layout(Lc, make_trans_layout(Lc)).total);
@@ -751,7 +751,7 @@ static TrainWs make_train_ws(const gcbf_env_desc* d) {
     const TransLayout Tc = make_trans_layout(make_layout(ed, 1)), Ta = make_trans_layout(make_layout(ed, nu));
     TrainWs t;
     int64_t o = 0;
-    auto take = [&](int64_t n) { int64_t r = o; o += (n + 3) & ~(int64_t)3; return r; };
+    auto take = [&](int64_t n) { int64_t r = o; o += (n + 7) & ~(int64_t)7; return r; };   // 32-byte slots: 256-bit epilogue stores
     t.ws0 = take(W.total);
     t.ws1 = take(W.total);
     t.ws2 = take(W.total);
