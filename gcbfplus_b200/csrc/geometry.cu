@@ -905,6 +905,201 @@ int32_t gcbf::graph_build_impl(const gcbf_env_desc* desc, const float* agent, co
     return check_launch("graph_build_kernel");
 }
 
+// ------------------------------------------------------------------------------------
+// reset: start / goal positions of every environment (env/utils.py:134-226 get_node_goal_rng), one warp per
+// environment, with jax.random's threefry key chain (gcbfplus_b200/utils/jrandom.py describes the algorithm; the host
+// restatement there is the cross-check, tests/test_gpu_reset.py).  Sequential rejection sampling per agent: the lanes
+// share the key arithmetic and split the distance scan over the already placed agents.
+// ------------------------------------------------------------------------------------
+namespace gcbf {
+struct TfKey { uint32_t a, b; };
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+__device__ __forceinline__ void threefry2x32(TfKey k, uint32_t c0, uint32_t c1, uint32_t& y0, uint32_t& y1) {
+    const uint32_t ks[3] = {k.a, k.b, k.a ^ k.b ^ 0x1BD11BDAu};
+    uint32_t x0 = c0 + ks[0], x1 = c1 + ks[1];
+#pragma unroll
+    for (int g = 0; g < 5; ++g) {
+        const int* rot = (g & 1) ? (const int[4]){17, 29, 16, 24} : (const int[4]){13, 15, 26, 6};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            x0 += x1;
+            x1 = rotl32(x1, rot[r]);
+            x1 ^= x0;
+        }
+        x0 += ks[(g + 1) % 3];
+        x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+    }
+    y0 = x0;
+    y1 = x1;
+}
+// jr.split(key, 2) / jr.split(key, 3): threefry over iota(2 num) split in halves
+__device__ __forceinline__ void tf_split2(TfKey k, TfKey& k0, TfKey& k1) {
+    uint32_t a0, a1, b0, b1;
+    threefry2x32(k, 0u, 2u, a0, a1);
+    threefry2x32(k, 1u, 3u, b0, b1);
+    k0 = {a0, b0};
+    k1 = {a1, b1};
+}
+__device__ __forceinline__ void tf_split3(TfKey k, TfKey& k0, TfKey& k1, TfKey& k2) {
+    uint32_t a0, a1, b0, b1, c0, c1;
+    threefry2x32(k, 0u, 3u, a0, a1);
+    threefry2x32(k, 1u, 4u, b0, b1);
+    threefry2x32(k, 2u, 5u, c0, c1);
+    k0 = {a0, b0};
+    k1 = {c0, a1};
+    k2 = {b1, c1};
+}
+__device__ __forceinline__ float tf_unit(uint32_t bits) { return __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f; }
+// jr.uniform(key, (PD,), minval, maxval): max(minval, f * (maxval - minval) + minval), fp32 (this TU has no FMA)
+template <int PD>
+__device__ __forceinline__ void tf_uniform(TfKey k, float lo, float hi, float* out) {
+    uint32_t y0, y1;
+    if (PD == 2) {
+        threefry2x32(k, 0u, 1u, y0, y1);
+        out[0] = fmaxf(lo, tf_unit(y0) * (hi - lo) + lo);
+        out[1] = fmaxf(lo, tf_unit(y1) * (hi - lo) + lo);
+    } else {   // iota(3) zero-padded to 4: halves [0, 1] and [2, 0]
+        uint32_t z0, z1;
+        threefry2x32(k, 0u, 2u, y0, y1);
+        threefry2x32(k, 1u, 0u, z0, z1);
+        out[0] = fmaxf(lo, tf_unit(y0) * (hi - lo) + lo);
+        out[1] = fmaxf(lo, tf_unit(z0) * (hi - lo) + lo);
+        out[PD - 1] = fmaxf(lo, tf_unit(y1) * (hi - lo) + lo);
+    }
+}
+
+template <int PD>
+__global__ void __launch_bounds__(32)
+reset_kernel(const int N, const int O, const int sd, const uint32_t* __restrict__ keys,
+             const float* __restrict__ obstacles, const float L, const float min_dist, const float max_travel,
+             float* __restrict__ agent, float* __restrict__ goal) {
+    constexpr int OBW = (PD == 2) ? 16 : 4;
+    extern __shared__ float rsm[];
+    float* st = rsm;                 // [N, PD] placed start positions (zeros until placed: reference quirk)
+    float* gl = st + (size_t)N * PD; // [N, PD]
+    const int g = blockIdx.x, lane = threadIdx.x;
+    const float* ob = obstacles + (size_t)g * O * OBW;
+    const bool has_mt = max_travel >= 0.f;
+    const int max_iter = 1024;
+    for (int i = lane; i < N * PD; i += 32) { st[i] = 0.f; gl[i] = 0.f; }
+    __syncwarp();
+    // any slot within min_dist (sqrt of the fp32 sum, like jnp.linalg.norm)
+    auto too_close = [&](const float* tab, const float* p) {
+        bool hit = false;
+        for (int j = lane; j < N; j += 32) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < PD; ++c) {
+                const float dlt = tab[j * PD + c] - p[c];
+                acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
+            }
+            hit = hit || (sqrtf(acc) <= min_dist);
+        }
+        return __any_sync(0xffffffffu, hit);
+    };
+    TfKey this_key = {keys[2 * g], keys[2 * g + 1]};
+    int agent_id = 0;
+    while (agent_id < N) {
+        TfKey agent_key, goal_key;
+        tf_split3(this_key, agent_key, goal_key, this_key);
+        // ---- start position
+        float cand[PD];
+        tf_uniform<PD>(agent_key, 0.f, L, cand);
+        int it_a = 0;
+        TfKey k = agent_key;
+        while ((too_close(st, cand) || inside_any<PD>(ob, O, cand, min_dist)) && it_a < max_iter) {
+            TfKey use;
+            tf_split2(k, use, k);
+            ++it_a;
+            tf_uniform<PD>(use, 0.f, L, cand);
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < PD; ++c) st[agent_id * PD + c] = cand[c];
+        }
+        // ---- goal position
+        float gp[PD];
+        if (!has_mt) {
+            tf_uniform<PD>(goal_key, 0.f, L, gp);
+        } else {
+            tf_uniform<PD>(goal_key, 0.f, max_travel, gp);
+#pragma unroll
+            for (int c = 0; c < PD; ++c) gp[c] = gp[c] + cand[c];
+        }
+        int it_g = 0;
+        k = goal_key;
+        while (true) {
+            bool bad = too_close(gl, gp) || inside_any<PD>(ob, O, gp, min_dist);
+#pragma unroll
+            for (int c = 0; c < PD; ++c) bad = bad || (gp[c] < 0.f) || (gp[c] > L);
+            if (has_mt) {
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < PD; ++c) {
+                    const float dlt = gp[c] - cand[c];
+                    acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
+                }
+                bad = bad || (sqrtf(acc) > max_travel);
+            }
+            if (!bad || it_g >= max_iter) break;
+            TfKey use;
+            tf_split2(k, use, k);
+            ++it_g;
+            if (!has_mt) {
+                tf_uniform<PD>(use, 0.f, L, gp);
+            } else {
+                tf_uniform<PD>(use, -max_travel, max_travel, gp);
+#pragma unroll
+                for (int c = 0; c < PD; ++c) gp[c] = gp[c] + cand[c];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < PD; ++c) gl[agent_id * PD + c] = gp[c];
+        }
+        ++agent_id;
+        if (it_a >= max_iter || it_g >= max_iter) {   // "if no solution is found, start over" (same key chain)
+            agent_id = 0;
+            __syncwarp();
+            for (int i = lane; i < N * PD; i += 32) { st[i] = 0.f; gl[i] = 0.f; }
+        }
+        __syncwarp();
+    }
+    for (int i = lane; i < N * PD; i += 32) {
+        const int a = i / PD, c = i % PD;
+        agent[((size_t)g * N + a) * sd + c] = st[i];
+        goal[((size_t)g * N + a) * sd + c] = gl[i];
+    }
+}
+}  // namespace gcbf
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_reset_positions(
+    const gcbf_env_desc* desc, const uint32_t* keys, const float* obstacles, float area_size, float min_dist,
+    float max_travel, float* agent, float* goal, void* stream) {
+    GCBF_REQUIRE(desc && keys && agent && goal, "gcbf_reset_positions: NULL pointer argument");
+    GCBF_REQUIRE(desc->env_kind >= 0 && desc->env_kind <= 3 && desc->n_graphs > 0 && desc->n_agents > 0,
+                 "gcbf_reset_positions: bad descriptor");
+    GCBF_REQUIRE(desc->n_obs == 0 || obstacles, "obstacles is NULL but n_obs > 0");
+    GCBF_REQUIRE(desc->obs_per_graph == 1 || desc->n_obs == 0, "gcbf_reset_positions: one obstacle set per environment");
+    const int pd = env_pd(desc->env_kind), sd = env_sd(desc->env_kind);
+    const size_t smem = sizeof(float) * 2 * (size_t)desc->n_agents * pd;
+    GCBF_REQUIRE(smem <= 200 * 1024, "gcbf_reset_positions: too many agents (%d)", desc->n_agents);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pd == 2) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(gcbf::reset_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gcbf::reset_kernel<2><<<desc->n_graphs, 32, smem, st>>>(desc->n_agents, desc->n_obs, sd, keys, obstacles, area_size,
+                                                              min_dist, max_travel, agent, goal);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(gcbf::reset_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gcbf::reset_kernel<3><<<desc->n_graphs, 32, smem, st>>>(desc->n_agents, desc->n_obs, sd, keys, obstacles, area_size,
+                                                              min_dist, max_travel, agent, goal);
+    }
+    count_launch();
+    return check_launch("reset_kernel");
+}
+
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_env_step(const gcbf_env_desc* desc, const float* agent, const float* goal,
                                  const float* obstacles, const float* pi, const int32_t* row_start,
                                  const int32_t* row_deg, const int32_t* edge_src, float* action, float* next_agent,

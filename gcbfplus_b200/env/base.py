@@ -90,6 +90,7 @@ class MultiAgentEnv(ABC):
         #: average edge budget per agent for the receiver-grouped edge lists (overflow is
         #: detected on the device and raised by SwarmGraph.check_overflow()).
         self.edge_cap_per_agent = 16
+        self.host_reset = False   # True: sample start / goal positions with the NumPy restatement instead of the kernel
         self._K = None
         self._A = None
         self._B = None
@@ -373,8 +374,25 @@ class MultiAgentEnv(ABC):
             assert n_envs is None or n_envs == keys.shape[0]
         E = keys.shape[0]
         obstacles, keys = self._sample_obstacles(keys)
-        packed = obstacles.packed.cpu().numpy()
         sd, pd = self.state_dim, self.pos_dim
+        if torch.device(self.device).type == "cuda" and not self.host_reset:
+            # device path: one warp per environment runs the reference's rejection sampler with the same key chain
+            # (csrc/geometry.cu reset_kernel; the host sampler below is its cross-check, tests/test_gpu_reset.py)
+            agent_t = torch.zeros(E, self.num_agents, sd, dtype=torch.float32, device=self.device)
+            goal_t = torch.zeros_like(agent_t)
+            keys_t = torch.from_numpy(np.ascontiguousarray(keys).view(np.int32)).to(self.device)
+            d = self.desc(E, obstacles.n_obs, edge_cap=1)
+            mt = -1.0 if self._max_travel is None else float(self._max_travel)
+            rc = self.lib.gcbf_reset_positions(C.byref(d), _lib.ptr(keys_t), _lib.ptr(obstacles.packed) if obstacles.n_obs else None,
+                                               float(self.area_size), float(np.float32(4 * self.radius)), mt,
+                                               _lib.ptr(agent_t), _lib.ptr(goal_t), self._stream())
+            _lib.check(rc, "gcbf_reset_positions")
+            if type(self)._reset_extra is not MultiAgentEnv._reset_extra:      # DubinsCar headings (tiny, host)
+                agent, goal = agent_t.cpu().numpy(), goal_t.cpu().numpy()
+                self._reset_extra(keys, agent, goal)
+                agent_t, goal_t = torch.from_numpy(agent).to(self.device), torch.from_numpy(goal).to(self.device)
+            return self.get_graph(agent_t, goal_t, obstacles)
+        packed = obstacles.packed.cpu().numpy()
         agent = np.zeros((E, self.num_agents, sd), dtype=np.float32)
         goal = np.zeros((E, self.num_agents, sd), dtype=np.float32)
         agent[:, :, :pd], goal[:, :, :pd] = self._sample_agents_goals(keys, packed)

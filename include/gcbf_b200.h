@@ -164,6 +164,17 @@ int32_t gcbf_env_step(const gcbf_env_desc* desc, const float* agent, const float
 int32_t gcbf_act(const gcbf_env_desc* desc, const float* agent, const float* goal, const float* pi,
                  float* action, void* stream);
 
+/* ---------------------------------------------------------------- reset (f3)
+ * Start / goal positions of every environment: get_node_goal_rng (gcbfplus/env/utils.py:134-226) with
+ * jax.random's threefry key chain, one warp per environment.
+ *   keys [G, 2] uint32 (device): the key get_node_goal_rng receives (after the obstacle draws of env.reset,
+ *     env/double_integrator.py:89-104); obstacles: packed, one set per environment
+ *   area_size, min_dist (= 4 * radius), max_travel (< 0: none)
+ *   agent / goal [G, N, sd] (device): the position components are written, the rest is left untouched. */
+int32_t gcbf_reset_positions(const gcbf_env_desc* desc, const uint32_t* keys, const float* obstacles,
+                             float area_size, float min_dist, float max_travel, float* agent, float* goal,
+                             void* stream);
+
 /* ---------------------------------------------------------------- fused rollout step (a8 body)
  * One iteration of the scan body of rollout() (gcbfplus/trainer/utils.py:46-49): algo.step
  * (algo/gcbf_plus.py:182-186) + env.step incl. get_graph of the next state
