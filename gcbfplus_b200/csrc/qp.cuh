@@ -236,11 +236,11 @@ __device__ __forceinline__ int qp_iterate(const QpRows<NU, SM>& R, const int N, 
                                           double* red) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const double step = 1.0 / lip;
-    double t = 1.0;
+    float t = 1.f;                                  // momentum schedule: fp32 is ample (only beta depends on it)
     int it;
-    for (it = 1; it <= max_iter; ++it) {
-        for (int i = tid; i < N; i += nt) lam[i] = (double)sc[i] * y[i];
-        __syncthreads();
+    for (int i = tid; i < N; i += nt) lam[i] = (double)sc[i] * y[i];
+    __syncthreads();
+    for (it = 1; it <= max_iter; ++it) {            // 4 block barriers per iteration
         qp_primal_u<NU, SM>(R, N, u_lim, lam, ls, ur, u);
         __syncthreads();
         // dual gradient s (-Lg u - r - b), projected step, restart test
@@ -267,12 +267,14 @@ __device__ __forceinline__ int qp_iterate(const QpRows<NU, SM>& R, const int N, 
         }
         qp_block_max_sum(res, dotp, red);
         const bool restart = dotp < 0.0;
-        const double t_new = restart ? 1.0 : 0.5 * (1.0 + sqrt(1.0 + 4.0 * t * t));
-        const double beta = restart ? 0.0 : (t - 1.0) / t_new;
+        const float t_new = restart ? 1.f : 0.5f * (1.f + sqrtf(1.f + 4.f * t * t));
+        const double beta = restart ? 0.0 : (double)((t - 1.f) / t_new);
         for (int i = tid; i < N; i += nt) {
             const double mn = lam[i];
-            y[i] = fma(beta, mn - mu[i], mn);
+            const double yn = fma(beta, mn - mu[i], mn);
+            y[i] = yn;
             mu[i] = mn;
+            lam[i] = (double)sc[i] * yn;            // multipliers of the next iterate (read by every thread after the barrier)
         }
         t = t_new;
         __syncthreads();
