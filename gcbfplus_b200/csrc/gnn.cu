@@ -306,7 +306,7 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
                               const int32_t* counters, int clip_all, float* out, float* ws, cudaStream_t st,
                               float* z_out = nullptr, int* z_parts = nullptr, int32_t* zero_counter = nullptr) {
     // z_out != nullptr (rollout step): instead of `out`, write the output layer's pre-activation partial sums
-    // z[part][A][4] (no bias, no tanh) for policy_tail_kernel
+    // z[part][A][4] (no bias, no tanh) for the policy tail fused into graph_build_kernel
     const int ed = env_ed(d->env_kind);
     const ParamLayout L = make_layout(ed, out_dim);
     const InferLayout I = make_infer_layout(out_dim);
@@ -438,7 +438,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_gnn_infer(
 // ---------------------------------------------------------------------------------------------------
 // One closed-loop rollout step in a single call: policy forward (folded weights) -> a = 2 pi + u_ref,
 // clip, Euler, reward / cost terms -> LiDAR + neighbour lists of the next state (+ reward / cost reduction).
-// 8 kernel launches.
+// 5 kernel launches (tensor-core path).
 // ---------------------------------------------------------------------------------------------------
 namespace gcbf {
 int32_t graph_build_impl(const gcbf_env_desc* desc, const float* agent, const float* obstacles, const float* ray_table,
