@@ -1,64 +1,48 @@
-"""MultiAgentController ABC -- gcbfplus/algo/base.py:10-68."""
-from abc import ABC, abstractmethod
-from typing import Optional, Tuple
+"""Controller interface of the B200 path.
 
-import torch
-
+Same attribute and method names as the reference's abstract controller (gcbfplus/algo/base.py:10-68), because
+train.py / test.py / Trainer are written against them: `node_dim`, `edge_dim`, `action_dim`, `n_agents`, `config`,
+`actor_params`, `act`, `step`, `update`, `save`, `load`.  Tensors are torch CUDA fp32 with a leading graph-batch
+dimension where the reference vmaps over single graphs."""
 from ..env.base import MultiAgentEnv
-from ..utils.graph import SwarmGraph
+
+_DIMS = ("node_dim", "edge_dim", "action_dim", "n_agents")
 
 
-class MultiAgentController(ABC):
+def _abstract(name: str):
+    def method(self, *args, **kwargs):
+        raise NotImplementedError(f"{type(self).__name__} must implement {name}()")
+    method.__name__ = name
+    return method
+
+
+class MultiAgentController:
+    """Holds the environment and the four sizes; everything else is the subclass's job."""
 
     def __init__(self, env: MultiAgentEnv, node_dim: int, edge_dim: int, action_dim: int, n_agents: int):
         self._env = env
-        self._node_dim = node_dim
-        self._edge_dim = edge_dim
-        self._action_dim = action_dim
-        self._n_agents = n_agents
+        self._sizes = dict(zip(_DIMS, (int(node_dim), int(edge_dim), int(action_dim), int(n_agents))))
+
+    # node_dim / edge_dim / action_dim / n_agents: read-only views of the constructor arguments
+    def __getattr__(self, name):
+        sizes = self.__dict__.get("_sizes", {})
+        if name in sizes:
+            return sizes[name]
+        raise AttributeError(f"{type(self).__name__!s} has no attribute {name!r}")
 
     @property
-    def node_dim(self) -> int:
-        return self._node_dim
+    def config(self) -> dict:                     # hyper-parameters written next to the checkpoints (config.yaml)
+        raise NotImplementedError
 
     @property
-    def edge_dim(self) -> int:
-        return self._edge_dim
+    def actor_params(self):                       # what rollout / test code hands back to act() / step()
+        raise NotImplementedError
 
-    @property
-    def action_dim(self) -> int:
-        return self._action_dim
+    # act(graph, params=None) -> action [G, N, nu];  step(graph, key, params=None) -> (action, log_pi)
+    act = _abstract("act")
+    step = _abstract("step")
+    # update(rollout, step) -> info dict;  save / load(dir, step): <dir>/<step>/{actor,cbf}.pkl
+    update = _abstract("update")
+    save = _abstract("save")
+    load = _abstract("load")
 
-    @property
-    def n_agents(self) -> int:
-        return self._n_agents
-
-    @property
-    @abstractmethod
-    def config(self) -> dict:
-        pass
-
-    @property
-    @abstractmethod
-    def actor_params(self):
-        pass
-
-    @abstractmethod
-    def act(self, graph: SwarmGraph, params=None) -> torch.Tensor:
-        pass
-
-    @abstractmethod
-    def step(self, graph: SwarmGraph, key, params=None) -> Tuple[torch.Tensor, torch.Tensor]:
-        pass
-
-    @abstractmethod
-    def update(self, rollout, step: int) -> dict:
-        pass
-
-    @abstractmethod
-    def save(self, save_dir: str, step: int):
-        pass
-
-    @abstractmethod
-    def load(self, load_dir: str, step: int):
-        pass

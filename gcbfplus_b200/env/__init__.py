@@ -1,4 +1,5 @@
-"""gcbfplus.env surface (gcbfplus/env/__init__.py:1-46)."""
+"""Environment registry and factory with the reference's names (gcbfplus/env/__init__.py): `ENV`, `DEFAULT_MAX_STEP`,
+`make_env(env_id, num_agents, area_size, max_step, max_travel, num_obs, n_rays)` plus a `device` argument."""
 from typing import Optional
 
 from .base import MultiAgentEnv, RolloutResult, StepResult
@@ -7,36 +8,30 @@ from .dubins_car import DubinsCar
 from .linear_drone import LinearDrone
 from .single_integrator import SingleIntegrator
 
+DEFAULT_MAX_STEP = 256     # episode length T of train.py / test.py
+_DT = 0.03                 # integration step every environment is created with
 
-class CrazyFlie:  # gcbfplus/env/crazyflie.py -- out of scope
+
+class CrazyFlie:
+    """Placeholder: the CrazyFlie dynamics need the `control` package and are outside the hot path."""
     PARAMS: dict = {}
 
-    def __init__(self, *a, **k):
+    def __init__(self, *unused, **also_unused):
         raise NotImplementedError("CrazyFlie is outside the B200 hot-path scope (SURVEY.md section 2, row 16)")
 
 
-ENV = {
-    "SingleIntegrator": SingleIntegrator,
-    "DoubleIntegrator": DoubleIntegrator,
-    "LinearDrone": LinearDrone,
-    "DubinsCar": DubinsCar,
-    "CrazyFlie": CrazyFlie,
-}
-
-DEFAULT_MAX_STEP = 256
+ENV = {cls.__name__: cls for cls in (SingleIntegrator, DoubleIntegrator, LinearDrone, DubinsCar, CrazyFlie)}
 
 
 def make_env(env_id: str, num_agents: int, area_size: float = None, max_step: int = None,
              max_travel: Optional[float] = None, num_obs: Optional[int] = None, n_rays: Optional[int] = None,
              device: str = "cuda") -> MultiAgentEnv:
-    """gcbfplus/env/__init__.py:23-46 (same kwargs; dt fixed to 0.03).  Unlike the reference the
-    class-level PARAMS dict is copied, not mutated (documented deviation)."""
-    assert env_id in ENV.keys(), f"Environment {env_id} not implemented."
-    params = dict(ENV[env_id].PARAMS)
-    max_step = DEFAULT_MAX_STEP if max_step is None else max_step
-    if num_obs is not None:
-        params["n_obs"] = num_obs
-    if n_rays is not None:
-        params["n_rays"] = n_rays
-    return ENV[env_id](num_agents=num_agents, area_size=area_size, max_step=max_step, max_travel=max_travel, dt=0.03,
-                       params=params, device=device)
+    """Build `env_id` with per-call overrides of the obstacle count and ray count.  The class-level PARAMS dict is
+    copied, never mutated (the reference mutates it, gcbfplus/env/__init__.py:36-40: documented deviation)."""
+    if env_id not in ENV:
+        raise AssertionError(f"Environment {env_id} not implemented.")
+    cls = ENV[env_id]
+    overrides = {"n_obs": num_obs, "n_rays": n_rays}
+    params = {**cls.PARAMS, **{k: v for k, v in overrides.items() if v is not None}}
+    return cls(num_agents=num_agents, area_size=area_size, max_step=max_step or DEFAULT_MAX_STEP,
+               max_travel=max_travel, dt=_DT, params=params, device=device)

@@ -81,32 +81,20 @@ def test(args):
         print("video rendering is out of scope of the B200 hot path (SURVEY.md section 2, row 17); skipped")
 
 
+# the reference's command line (test.py:239-266), table-driven like train.py
+FLAGS = [
+    (("-n", "--num-agents"), int, None), (("--obs",), int, 0), (("--area-size",), float, "required"),
+    (("--max-step",), int, None), (("--path",), str, None), (("--n-rays",), int, 32), (("--alpha",), float, 1.0),
+    (("--max-travel",), float, None), (("--cbf",), int, None), (("--seed",), int, 1234), (("--debug",), "flag", False),
+    (("--cpu",), "flag", False), (("--u-ref",), "flag", False), (("--env",), str, None), (("--algo",), str, None),
+    (("--step",), int, None), (("--epi",), int, 5), (("--offset",), int, 0), (("--no-video",), "flag", False),
+    (("--nojit-rollout",), "flag", False), (("--log",), "flag", False), (("--dpi",), int, 100),
+]
+
+
 def main():
-    parser = argparse.ArgumentParser()
-    parser.add_argument("-n", "--num-agents", type=int, default=None)
-    parser.add_argument("--obs", type=int, default=0)
-    parser.add_argument("--area-size", type=float, required=True)
-    parser.add_argument("--max-step", type=int, default=None)
-    parser.add_argument("--path", type=str, default=None)
-    parser.add_argument("--n-rays", type=int, default=32)
-    parser.add_argument("--alpha", type=float, default=1.0)
-    parser.add_argument("--max-travel", type=float, default=None)
-    parser.add_argument("--cbf", type=int, default=None)
-    parser.add_argument("--seed", type=int, default=1234)
-    parser.add_argument("--debug", action="store_true", default=False)
-    parser.add_argument("--cpu", action="store_true", default=False)
-    parser.add_argument("--u-ref", action="store_true", default=False)
-    parser.add_argument("--env", type=str, default=None)
-    parser.add_argument("--algo", type=str, default=None)
-    parser.add_argument("--step", type=int, default=None)
-    parser.add_argument("--epi", type=int, default=5)
-    parser.add_argument("--offset", type=int, default=0)
-    parser.add_argument("--no-video", action="store_true", default=False)
-    parser.add_argument("--nojit-rollout", action="store_true", default=False)
-    parser.add_argument("--log", action="store_true", default=False)
-    parser.add_argument("--dpi", type=int, default=100)
-    args = parser.parse_args()
-    test(args)
+    from train import build_parser
+    test(build_parser(FLAGS).parse_args())
 
 
 if __name__ == "__main__":

@@ -54,40 +54,35 @@ def train(args):
     trainer.train()
 
 
-def main():
+# (flags, type or "flag", default) -- the reference's command line (train.py:115-151), table-driven
+FLAGS = [
+    (("-n", "--num-agents"), int, 8), (("--algo",), str, "gcbf+"), (("--env",), str, "SimpleCar"), (("--seed",), int, 0),
+    (("--steps",), int, 1000), (("--name",), str, None), (("--debug",), "flag", False), (("--obs",), int, None),
+    (("--n-rays",), int, 32), (("--area-size",), float, "required"),
+    # GCBF / GCBF+ hyper-parameters
+    (("--gnn-layers",), int, 1), (("--alpha",), float, 1.0), (("--horizon",), int, 32), (("--lr-actor",), float, 3e-5),
+    (("--lr-cbf",), float, 3e-5), (("--loss-action-coef",), float, 1e-4), (("--loss-unsafe-coef",), float, 1.0),
+    (("--loss-safe-coef",), float, 1.0), (("--loss-h-dot-coef",), float, 0.01), (("--buffer-size",), int, 512),
+    # run control
+    (("--n-env-train",), int, 16), (("--n-env-test",), int, 32), (("--log-dir",), str, "./logs"),
+    (("--eval-interval",), int, 1), (("--eval-epi",), int, 1), (("--save-interval",), int, 10), (("--cpu",), "flag", False),
+]
+
+
+def build_parser(flags) -> argparse.ArgumentParser:
     parser = argparse.ArgumentParser()
-    # custom arguments (train.py:119-128)
-    parser.add_argument("-n", "--num-agents", type=int, default=8)
-    parser.add_argument("--algo", type=str, default="gcbf+")
-    parser.add_argument("--env", type=str, default="SimpleCar")
-    parser.add_argument("--seed", type=int, default=0)
-    parser.add_argument("--steps", type=int, default=1000)
-    parser.add_argument("--name", type=str, default=None)
-    parser.add_argument("--debug", action="store_true", default=False)
-    parser.add_argument("--obs", type=int, default=None)
-    parser.add_argument("--n-rays", type=int, default=32)
-    parser.add_argument("--area-size", type=float, required=True)
-    # gcbf / gcbf+ arguments (train.py:131-140)
-    parser.add_argument("--gnn-layers", type=int, default=1)
-    parser.add_argument("--alpha", type=float, default=1.0)
-    parser.add_argument("--horizon", type=int, default=32)
-    parser.add_argument("--lr-actor", type=float, default=3e-5)
-    parser.add_argument("--lr-cbf", type=float, default=3e-5)
-    parser.add_argument("--loss-action-coef", type=float, default=0.0001)
-    parser.add_argument("--loss-unsafe-coef", type=float, default=1.0)
-    parser.add_argument("--loss-safe-coef", type=float, default=1.0)
-    parser.add_argument("--loss-h-dot-coef", type=float, default=0.01)
-    parser.add_argument("--buffer-size", type=int, default=512)
-    # default arguments (train.py:143-148)
-    parser.add_argument("--n-env-train", type=int, default=16)
-    parser.add_argument("--n-env-test", type=int, default=32)
-    parser.add_argument("--log-dir", type=str, default="./logs")
-    parser.add_argument("--eval-interval", type=int, default=1)
-    parser.add_argument("--eval-epi", type=int, default=1)
-    parser.add_argument("--save-interval", type=int, default=10)
-    parser.add_argument("--cpu", action="store_true", default=False)
-    args = parser.parse_args()
-    train(args)
+    for names, kind, default in flags:
+        if kind == "flag":
+            parser.add_argument(*names, action="store_true", default=default)
+        elif default == "required":
+            parser.add_argument(*names, type=kind, required=True)
+        else:
+            parser.add_argument(*names, type=kind, default=default)
+    return parser
+
+
+def main():
+    train(build_parser(FLAGS).parse_args())
 
 
 if __name__ == "__main__":
