@@ -322,7 +322,10 @@ def gemm_roofline(torch, _lib, dev, n_edges: int, n_agents: int):
             "train_shape": {"M": Mt, "K": 256, "N": 256, "us_per_launch": ms_t * 1e3, "achieved": ach_t,
                             "frac": ach_t / tf_burst, "tf32_mma_tflops": 3 * ach_t,
                             "frac_of_tf32_peak": 3 * ach_t / (tf_burst / 2),
-                            "simt_fp32_kernel_tflops": 2.0 * Mt * 256 * 256 / (ms_s * 1e-3) / 1e12},
+                            "simt_fp32_kernel_tflops": 2.0 * Mt * 256 * 256 / (ms_s * 1e-3) / 1e12,
+                            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu
+                            # --set full capture (profiles/r01_final_summary.md), not re-measured here
+                            "traffic": 205.6e6 + 151.5e6, "algorithmic_bytes": 4.0 * (Mt * 256 + 256 * 256 + Mt * 256)},
             "note": "rollout launches are single-wave (110 row tiles on 148 SMs): latency-bound; the train-shape "
                     "line shows the kernel at scale.  TF32 dense peak taken as half the measured bf16 peak."}
 
