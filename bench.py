@@ -380,7 +380,19 @@ def cpu_baseline(args, steps: int = 1, verbose: bool = False):
             if s > 0 or steps == 0:
                 times.append(dt)
     sec = sum(times) / max(len(times), 1)
-    return {"value": N / sec, "unit": "env-steps/s", "cores": cores, "kind": "port",
+    # same step with the masked edges dropped first (the CUDA path's formulation) -> separates the algorithmic
+    # (dense -> sparse) factor from the hardware (CPU -> B200) one, BASELINE.md section 3
+    sparse_times = []
+    with torch.no_grad():
+        for s in range(2):
+            t0 = time.perf_counter()
+            gs = oenv.sparsify(g)
+            a = act(oenv, ap, gs)
+            g, r, c = oenv.step(gs, a)
+            if s > 0:
+                sparse_times.append(time.perf_counter() - t0)
+    sec_sparse = sum(sparse_times) / max(len(sparse_times), 1)
+    return {"value": N / sec, "unit": "env-steps/s", "cores": cores, "kind": "port", "sparse_value": N / sec_sparse,
             "sample": f"1 env x n={N} x {len(times)} env-step(s) after 1 warm-up step, dense reference formulation "
                       f"({2 * N * N + N * N_RAYS} padded edges/graph), torch-CPU fp32; {sec:.2f} s per env-step; "
                       f"{cores} of {ncpu} host threads (fastest of {cands} on a n=128 probe)",
@@ -402,7 +414,7 @@ def run_reference(args):
                                   "bounded sample: 1 env, per step 1 env-step",
                       "note": "JAX/Flax/jraph are not installable in this image: the arm is the restated "
                               "reference (oracle, dense formulation), not the JAX code"},
-           "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "sparse_value")},
            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(out))
