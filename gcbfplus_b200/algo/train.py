@@ -42,6 +42,9 @@ class TrainState:
         self.norm_cbf = torch.zeros(2 + 512, dtype=f32, device=dev)
         self.norm_act = torch.zeros(2 + 512, dtype=f32, device=dev)
         self.denoms = torch.zeros(4, dtype=f32, device=dev)
+        # sticky OR of the edge-capacity overflow flag (counters[1]) of every graph trained on / labelled since the
+        # last read_info(): an overflowed build drops rows, which must never train silently
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self.ws: Optional[torch.Tensor] = None
         self.ws_key = None
 
@@ -73,6 +76,7 @@ def train_minibatch(algo, graph: SwarmGraph, safe_mask: torch.Tensor, unsafe_mas
         ts.ws = torch.empty(int(n), dtype=torch.float32, device=env.device)
         ts.ws_key = key
     st = env._stream()
+    ts.overflow |= graph.counters[1:2]
     safe_mask = safe_mask.reshape(B * N).to(torch.uint8).contiguous()
     unsafe_mask = unsafe_mask.reshape(B * N).to(torch.uint8).contiguous()
     u_qp = u_qp.reshape(B * N, env.action_dim).float().contiguous()
@@ -114,6 +118,10 @@ def apply_gradients(algo, ts: TrainState) -> None:
 def read_info(algo) -> Dict[str, float]:
     """Info dict of the last minibatch with the reference's keys (gcbf_plus.py:423-440). Syncs."""
     ts: TrainState = algo._trainer_state
+    if int(ts.overflow.item()) != 0:
+        ts.overflow.zero_()
+        raise RuntimeError("edge capacity overflow in a training / labelling graph: rows were dropped, the update is "
+                           "invalid; raise env.edge_cap_per_agent")
     s = ts.stats.cpu().numpy().astype(np.float64)
     den = ts.denoms.cpu().numpy().astype(np.float64)
     n_unsafe, n_safe, n_tot = den[0], den[1], den[2]
@@ -204,20 +212,27 @@ def update(algo, rollout: Rollout, step: int) -> dict:
         algo.unsafe_buffer.append_graphs(new, new["unsafe"].any(dim=-1))
         batch = new
     n = batch["agent"].shape[0]
-    u_qp = batch_u_qp(algo, batch)
+    qp_info: Dict[str, float] = {}
+    u_qp = batch_u_qp(algo, batch, info=qp_info)
     # sharded run: this rank holds 1/world of the environments, so its share of every batch_size-graph minibatch
     # is batch_size / world graphs (same number of minibatches, hence of collectives, on every rank)
     dist = _dist()
     world = dist.get_world_size() if dist is not None else 1
     n_mb = max(n // max(algo.batch_size // world, 1), 1)
+    mb_graphs = -(-n // n_mb)
+    # exact upper bound on a minibatch's edge count from the per-graph counts measured while labelling: no
+    # minibatch can overflow its edge lists whatever graphs the permutation puts together
+    mb_cap = max(int(qp_info["graph/max_edges"]) * mb_graphs, 64)
     info = {}
     for _ in range(algo.inner_epoch):
         idx = torch.from_numpy(algo.rng.permutation(n)).to(env.device)
         for mb in np.array_split(np.arange(n), n_mb):
             sel = idx[torch.from_numpy(mb).to(env.device)]
-            g = env.get_graph(batch["agent"][sel], batch["goal"][sel], None, hits=batch["hits"][sel].contiguous())
+            g = env.get_graph(batch["agent"][sel], batch["goal"][sel], None, hits=batch["hits"][sel].contiguous(),
+                              edge_cap=mb_cap)
             train_minibatch(algo, g, batch["safe"][sel], batch["unsafe"][sel], u_qp[sel])
     info = read_info(algo)
+    info.update(qp_info)
     update_tgt(algo, 0.5)
     return info
 
@@ -238,9 +253,10 @@ QP_TOL = 1e-5           # projected dual-gradient residual
 
 
 def qp_labels(algo, graph: SwarmGraph, params=None, with_aux: bool = False, max_iter: int = QP_MAX_ITER,
-              tol: float = QP_TOL):
+              tol: float = QP_TOL, with_iters: bool = False):
     """get_qp_action vmapped over the graphs of `graph` (gcbf_plus.py:193-196, 299-352): u_qp [G, N, nu];
-    with_aux also returns (lam, r) [G, N, 2] and the iteration counts [G]."""
+    with_aux also returns (lam, r) [G, N, 2] and the iteration counts [G]; with_iters returns (u_qp, iters).
+    A graph whose count equals max_iter stopped at the cap (its label is the capped iterate)."""
     env = algo._env
     lib = env.lib
     G, N = graph.n_graphs, env.num_agents
@@ -258,7 +274,7 @@ def qp_labels(algo, graph: SwarmGraph, params=None, with_aux: bool = False, max_
     p = params if params is not None else algo.cbf_tgt_params
     u_qp = torch.empty(G, N, env.action_dim, dtype=torch.float32, device=env.device)
     aux = torch.empty(G, N, 2, dtype=torch.float32, device=env.device) if with_aux else None
-    iters = torch.empty(G, dtype=torch.int32, device=env.device) if with_aux else None
+    iters = torch.empty(G, dtype=torch.int32, device=env.device) if (with_aux or with_iters) else None
     rc = lib.gcbf_qp_labels(C.byref(d), float(algo.alpha), 1 if _lib.USE_TC else 0, int(max_iter), float(tol),
                             _lib.ptr(p.flat), _lib.ptr(graph.agent), _lib.ptr(graph.goal), _lib.ptr(graph.hits),
                             _lib.ptr(graph.row_start), _lib.ptr(graph.row_deg), _lib.ptr(graph.edge_recv),
@@ -267,19 +283,67 @@ def qp_labels(algo, graph: SwarmGraph, params=None, with_aux: bool = False, max_
     _lib.check(rc, "gcbf_qp_labels")
     if with_aux:
         return u_qp, aux, iters & 0x3FFFFFFF      # bit 30 flags the global-memory fallback of dense graphs
+    if with_iters:
+        return u_qp, iters & 0x3FFFFFFF
     return u_qp
 
 
-def batch_u_qp(algo, batch, agents_per_chunk: int = 32768) -> torch.Tensor:
+QP_POLISH_ITER = 60000   # second pass for the graphs that stopped at QP_MAX_ITER (same method, 15x the budget)
+
+
+def batch_u_qp(algo, batch, agents_per_chunk: int = 32768, info: Optional[dict] = None) -> torch.Tensor:
     """update_nets' label pass (gcbf_plus.py:201-211): the reference cuts the batch into 8 chunks to bound the
-    dense QP memory; here the chunk only bounds the activation workspace."""
+    dense QP memory; here the chunk only bounds the activation workspace.
+
+    No silent caps: every graph's iteration count is read back (one sync per update); graphs that stopped at
+    QP_MAX_ITER are solved again with QP_POLISH_ITER, and what is still capped after that is reported
+    (`qp/capped_frac` first pass, `qp/unconverged_frac` after the polish) in `info`.  The same pass measures the
+    largest per-graph edge count (`graph/max_edges`, sizes the minibatch edge lists exactly) and ORs the
+    edge-capacity overflow flags of the chunk graphs; an overflow doubles env.edge_cap_per_agent and relabels."""
     env = algo._env
-    n = batch["agent"].shape[0]
-    chunk = max(1, agents_per_chunk // env.num_agents)
-    out = torch.empty(n, env.num_agents, env.action_dim, dtype=torch.float32, device=env.device)
-    for lo in range(0, n, chunk):
-        hi = min(n, lo + chunk)
-        g = env.get_graph(batch["agent"][lo:hi].contiguous(), batch["goal"][lo:hi].contiguous(), None,
-                          hits=batch["hits"][lo:hi].contiguous())
-        out[lo:hi] = qp_labels(algo, g)
+    if algo._trainer_state is None:
+        algo._trainer_state = TrainState(algo)
+    ts: TrainState = algo._trainer_state
+    n, N = batch["agent"].shape[0], env.num_agents
+    chunk = max(1, agents_per_chunk // N)
+    dev = env.device
+    out = torch.empty(n, N, env.action_dim, dtype=torch.float32, device=dev)
+    iters = torch.empty(n, dtype=torch.int32, device=dev)
+    n_edges = torch.empty(n, dtype=torch.int32, device=dev)
+
+    def sub_graph(sel):
+        return env.get_graph(batch["agent"][sel].contiguous(), batch["goal"][sel].contiguous(), None,
+                             hits=batch["hits"][sel].contiguous())
+
+    for attempt in range(6):
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            g = sub_graph(slice(lo, hi))
+            out[lo:hi], iters[lo:hi] = qp_labels(algo, g, with_iters=True)
+            n_edges[lo:hi] = g.row_deg.reshape(hi - lo, N).sum(dim=1)
+            flag |= g.counters[1:2]
+        if int(flag.item()) == 0:                      # the one host sync of the label pass
+            break
+        env.edge_cap_per_agent *= 2                    # rows were dropped: grow the edge lists and label again
+    else:
+        raise RuntimeError("edge capacity overflow persists after growing env.edge_cap_per_agent 32x")
+    capped = torch.nonzero(iters >= QP_MAX_ITER).flatten()
+    n_capped = int(capped.numel())
+    n_left = 0
+    if n_capped:
+        for lo in range(0, n_capped, chunk):
+            sel = capped[lo:lo + chunk]
+            g = sub_graph(sel)
+            u2, it2 = qp_labels(algo, g, with_iters=True, max_iter=QP_POLISH_ITER)
+            out[sel] = u2
+            iters[sel] = it2
+            ts.overflow |= g.counters[1:2]
+        n_left = int((iters[capped] >= QP_POLISH_ITER).sum().item())
+    if info is not None:
+        info["qp/capped_frac"] = n_capped / n
+        info["qp/unconverged_frac"] = n_left / n
+        info["qp/iters_median"] = float(iters.float().median().item())
+        info["graph/max_edges"] = int(n_edges.max().item())
+        info["graph/mean_edges"] = float(n_edges.float().mean().item())
     return out

@@ -43,11 +43,16 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+LAST = {"compiled": 0, "reused": 0}   # what the last build() call did (printed by __graft_entry__.build)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.stamp")
     dig = _digest()
+    n_units = sum(os.path.exists(os.path.join(CSRC, u)) for u in UNITS)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        LAST.update(compiled=0, reused=n_units)
         return LIB
     nvcc = _nvcc()
     objs = []
@@ -74,6 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f"link failed:\n{r.stdout.decode()}")
     with open(stamp, "w") as f:
         f.write(dig)
+    LAST.update(compiled=len(objs), reused=0)
     return LIB
 
 

@@ -231,6 +231,11 @@ class MultiAgentEnv(ABC):
         return max(int(n_graphs * N * per_agent), 64)
 
     def _stream(self) -> int:
+        # the library launches on the CURRENT device with the stream handed in: make the env's device current so
+        # that make_env(device="cuda:1") (or a rank whose LOCAL_RANK != 0) does not pair a device-1 stream with device 0
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        if torch.cuda.current_device() != idx:
+            torch.cuda.set_device(idx)
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def clip_state(self, state: torch.Tensor) -> torch.Tensor:
@@ -408,9 +413,10 @@ class MultiAgentEnv(ABC):
 
     # ------------------------------------------------------------------ graph
     def get_graph(self, agent: torch.Tensor, goal: torch.Tensor, obstacle, hits: Optional[torch.Tensor] = None,
-                  out: Optional[SwarmGraph] = None) -> SwarmGraph:
+                  out: Optional[SwarmGraph] = None, edge_cap: Optional[int] = None) -> SwarmGraph:
         """env.get_graph (double_integrator.py:288-320): LiDAR + radius neighbour lists.
-        With `hits` given only the topology is rebuilt (replayed graphs)."""
+        With `hits` given only the topology is rebuilt (replayed graphs).  edge_cap overrides the
+        edge_cap_per_agent sizing (callers that know an upper bound on the edge count)."""
         if agent.dim() == 2:
             agent, goal = agent[None], goal[None]
         agent = agent.contiguous().float()
@@ -422,7 +428,7 @@ class MultiAgentEnv(ABC):
         if obstacle is not None and obstacle.packed.shape[0] != G:
             assert obstacle.packed.shape[0] == 1, "obstacle batch must be G or 1"
             per_graph = 0
-        d = self.desc(G, O, obs_per_graph=per_graph)
+        d = self.desc(G, O, edge_cap=edge_cap, obs_per_graph=per_graph)
         dev = agent.device
         cast = hits is None
         if out is None:
@@ -431,8 +437,8 @@ class MultiAgentEnv(ABC):
                 hits = torch.empty(G, N, self.n_hits, self.pos_dim, device=dev, dtype=torch.float32)
             out = SwarmGraph(self, agent, goal, obstacle, hits.contiguous(),
                              torch.empty(A, dtype=torch.int32, device=dev), torch.empty(A, dtype=torch.int32, device=dev),
-                             torch.empty(d.edge_cap, dtype=torch.int32, device=dev),
-                             torch.empty(d.edge_cap, dtype=torch.int32, device=dev),
+                             torch.zeros(d.edge_cap, dtype=torch.int32, device=dev),
+                             torch.zeros(d.edge_cap, dtype=torch.int32, device=dev),
                              torch.zeros(4, dtype=torch.int32, device=dev))
         else:
             d.edge_cap = out.edge_recv.numel()
@@ -528,13 +534,31 @@ class MultiAgentEnv(ABC):
         return self._masks(graph, "finish")
 
     def inside_obstacles(self, graph: SwarmGraph) -> torch.Tensor:
-        """inside_obstacles(agent_pos, obstacles, r=radius) (info of env.step)."""
-        return self._masks(graph, "collision") & ~self._agent_collision(graph)
-
-    def _agent_collision(self, graph: SwarmGraph) -> torch.Tensor:
-        pos = graph.agent[..., : self.pos_dim]
-        dist = torch.cdist(pos, pos) + torch.eye(self.num_agents, device=pos.device) * 1e6
-        return (dist < 2 * self.radius).any(dim=-1)
+        """inside_obstacles(agent_pos, obstacles, r=radius): the eval info of env.step
+        (double_integrator.py:172-175), independent of agent-agent collisions.  Computed by the collision-mask
+        kernel on single-agent graphs (no other agent to collide with -> only the obstacle term is left)."""
+        G, N = graph.n_graphs, self.num_agents
+        O = graph.obstacle.n_obs if graph.obstacle is not None else 0
+        dev = graph.agent.device
+        if O == 0:
+            return torch.zeros(G, N, dtype=torch.bool, device=dev)
+        shared = graph.obstacle.packed.shape[0] != G
+        agent = graph.agent.reshape(G * N, 1, self.state_dim).contiguous()
+        goal = graph.goal.reshape(G * N, 1, self.state_dim).contiguous()
+        packed = graph.obstacle.packed
+        if not shared:
+            packed = packed[:, None].expand(G, N, *packed.shape[1:]).reshape(G * N, *packed.shape[1:]).contiguous()
+        out = torch.empty(G * N, dtype=torch.uint8, device=dev)
+        chunk = 32768                                       # grid.y limit of the mask kernel
+        for lo in range(0, G * N, chunk):
+            hi = min(G * N, lo + chunk)
+            d = self.desc(hi - lo, O, edge_cap=1, obs_per_graph=0 if shared else 1)
+            d.n_agents = 1
+            rc = self.lib.gcbf_masks(C.byref(d), _lib.ptr(agent[lo:hi]), _lib.ptr(goal[lo:hi]), None,
+                                     _lib.ptr(packed if shared else packed[lo:hi]), None, _lib.ptr(out[lo:hi]), None,
+                                     None, self._stream())
+            _lib.check(rc, "gcbf_masks")
+        return out.reshape(G, N).bool()
 
     # ------------------------------------------------------------------ rollouts
     def rollout_fn(self, policy: Callable, rollout_length: int = None) -> Callable:

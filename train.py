@@ -17,12 +17,14 @@ def train(args):
     if args.cpu:
         raise SystemExit("--cpu: gcbfplus_b200 is the sm_100a CUDA path only (no CPU fallback by design)")
     os.environ.setdefault("WANDB_MODE", "offline")
-    np.random.seed(args.seed)
     # one process per GPU under torchrun (python -m torch.distributed.run --nproc-per-node N train.py ...):
     # environments are sharded over the ranks, gradients all-reduced once per optimizer step
     import torch
     from gcbfplus_b200 import dist as gdist
     rank, local_rank, world = gdist.init_from_env()
+    # replay sampling draws from NumPy's global RNG (trainer/buffer.py:82-87, seeded at train.py:22 in the reference):
+    # rank 0 keeps the reference's stream, the other ranks sample their own replay with an offset seed
+    np.random.seed(args.seed + rank)
     device = torch.device("cuda", local_rank)
     if args.debug or rank != 0:
         os.environ["WANDB_MODE"] = "disabled"
