@@ -77,6 +77,8 @@ _SIGNATURES = {
                                     C.c_float, C.c_float, _P]),
     "gcbf_polyak": (C.c_int32, [_P, _P, C.c_int32, C.c_float, _P]),
     "gcbf_reset_positions": (C.c_int32, [C.POINTER(EnvDesc), _P, _P, C.c_float, C.c_float, C.c_float, _P, _P, _P]),
+    "gcbf_reset_positions_ex": (C.c_int32, [C.POINTER(EnvDesc), _P, _P, C.c_float, C.c_float, C.c_float, C.c_int32, _P, _P,
+                                            _P]),
     "gcbf_qp_workspace_floats": (C.c_int64, [C.POINTER(EnvDesc)]),
     "gcbf_qp_workspace_layout": (C.c_int32, [C.POINTER(EnvDesc), C.POINTER(C.c_int64)]),
     "gcbf_qp_labels": (C.c_int32, [C.POINTER(EnvDesc), C.c_float, C.c_int32, C.c_int32, C.c_float] + [_P] * 13 +

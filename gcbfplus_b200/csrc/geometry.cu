@@ -932,15 +932,36 @@ __device__ __forceinline__ void threefry2x32(TfKey k, uint32_t c0, uint32_t c1, 
     y0 = x0;
     y1 = x1;
 }
-// jr.split(key, 2) / jr.split(key, 3): threefry over iota(2 num) split in halves
+// jr.split(key, 2) / jr.split(key, 3).  PART = false: jax's legacy layout, threefry over iota(2 num) split in halves;
+// PART = true: jax_threefry_partitionable (default from JAX 0.5.0): child i = the output pair of threefry(key, (0, i)).
+template <bool PART>
 __device__ __forceinline__ void tf_split2(TfKey k, TfKey& k0, TfKey& k1) {
+    if (PART) {
+        TfKey c0, c1;
+        threefry2x32(k, 0u, 0u, c0.a, c0.b);
+        threefry2x32(k, 0u, 1u, c1.a, c1.b);
+        k0 = c0;
+        k1 = c1;
+        return;
+    }
     uint32_t a0, a1, b0, b1;
     threefry2x32(k, 0u, 2u, a0, a1);
     threefry2x32(k, 1u, 3u, b0, b1);
     k0 = {a0, b0};
     k1 = {a1, b1};
 }
+template <bool PART>
 __device__ __forceinline__ void tf_split3(TfKey k, TfKey& k0, TfKey& k1, TfKey& k2) {
+    if (PART) {
+        TfKey c0, c1, c2;
+        threefry2x32(k, 0u, 0u, c0.a, c0.b);
+        threefry2x32(k, 0u, 1u, c1.a, c1.b);
+        threefry2x32(k, 0u, 2u, c2.a, c2.b);
+        k0 = c0;
+        k1 = c1;
+        k2 = c2;
+        return;
+    }
     uint32_t a0, a1, b0, b1, c0, c1;
     threefry2x32(k, 0u, 3u, a0, a1);
     threefry2x32(k, 1u, 4u, b0, b1);
@@ -951,9 +972,17 @@ __device__ __forceinline__ void tf_split3(TfKey k, TfKey& k0, TfKey& k1, TfKey& 
 }
 __device__ __forceinline__ float tf_unit(uint32_t bits) { return __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f; }
 // jr.uniform(key, (PD,), minval, maxval): max(minval, f * (maxval - minval) + minval), fp32 (this TU has no FMA)
-template <int PD>
+template <int PD, bool PART>
 __device__ __forceinline__ void tf_uniform(TfKey k, float lo, float hi, float* out) {
     uint32_t y0, y1;
+    if (PART) {   // element i: bits = y0 ^ y1 of threefry(key, (0, i))
+#pragma unroll
+        for (int c = 0; c < PD; ++c) {
+            threefry2x32(k, 0u, (uint32_t)c, y0, y1);
+            out[c] = fmaxf(lo, tf_unit(y0 ^ y1) * (hi - lo) + lo);
+        }
+        return;
+    }
     if (PD == 2) {
         threefry2x32(k, 0u, 1u, y0, y1);
         out[0] = fmaxf(lo, tf_unit(y0) * (hi - lo) + lo);
@@ -968,7 +997,7 @@ __device__ __forceinline__ void tf_uniform(TfKey k, float lo, float hi, float* o
     }
 }
 
-template <int PD>
+template <int PD, bool PART>
 __global__ void __launch_bounds__(32)
 reset_kernel(const int N, const int O, const int sd, const uint32_t* __restrict__ keys,
              const float* __restrict__ obstacles, const float L, const float min_dist, const float max_travel,
@@ -1001,17 +1030,17 @@ reset_kernel(const int N, const int O, const int sd, const uint32_t* __restrict_
     int agent_id = 0;
     while (agent_id < N) {
         TfKey agent_key, goal_key;
-        tf_split3(this_key, agent_key, goal_key, this_key);
+        tf_split3<PART>(this_key, agent_key, goal_key, this_key);
         // ---- start position
         float cand[PD];
-        tf_uniform<PD>(agent_key, 0.f, L, cand);
+        tf_uniform<PD, PART>(agent_key, 0.f, L, cand);
         int it_a = 0;
         TfKey k = agent_key;
         while ((too_close(st, cand) || inside_any<PD>(ob, O, cand, min_dist)) && it_a < max_iter) {
             TfKey use;
-            tf_split2(k, use, k);
+            tf_split2<PART>(k, use, k);
             ++it_a;
-            tf_uniform<PD>(use, 0.f, L, cand);
+            tf_uniform<PD, PART>(use, 0.f, L, cand);
         }
         __syncwarp();
         if (lane == 0) {
@@ -1021,9 +1050,9 @@ reset_kernel(const int N, const int O, const int sd, const uint32_t* __restrict_
         // ---- goal position
         float gp[PD];
         if (!has_mt) {
-            tf_uniform<PD>(goal_key, 0.f, L, gp);
+            tf_uniform<PD, PART>(goal_key, 0.f, L, gp);
         } else {
-            tf_uniform<PD>(goal_key, 0.f, max_travel, gp);
+            tf_uniform<PD, PART>(goal_key, 0.f, max_travel, gp);
 #pragma unroll
             for (int c = 0; c < PD; ++c) gp[c] = gp[c] + cand[c];
         }
@@ -1044,12 +1073,12 @@ reset_kernel(const int N, const int O, const int sd, const uint32_t* __restrict_
             }
             if (!bad || it_g >= max_iter) break;
             TfKey use;
-            tf_split2(k, use, k);
+            tf_split2<PART>(k, use, k);
             ++it_g;
             if (!has_mt) {
-                tf_uniform<PD>(use, 0.f, L, gp);
+                tf_uniform<PD, PART>(use, 0.f, L, gp);
             } else {
-                tf_uniform<PD>(use, -max_travel, max_travel, gp);
+                tf_uniform<PD, PART>(use, -max_travel, max_travel, gp);
 #pragma unroll
                 for (int c = 0; c < PD; ++c) gp[c] = gp[c] + cand[c];
             }
@@ -1075,9 +1104,18 @@ reset_kernel(const int N, const int O, const int sd, const uint32_t* __restrict_
 }
 }  // namespace gcbf
 
-extern "C" __attribute__((visibility("default"))) int32_t gcbf_reset_positions(
+template <int PD, bool PART>
+static void launch_reset(const gcbf_env_desc* desc, int sd, size_t smem, const uint32_t* keys, const float* obstacles,
+                         float area_size, float min_dist, float max_travel, float* agent, float* goal, cudaStream_t st) {
+    auto kern = gcbf::reset_kernel<PD, PART>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<desc->n_graphs, 32, smem, st>>>(desc->n_agents, desc->n_obs, sd, keys, obstacles, area_size, min_dist, max_travel,
+                                           agent, goal);
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_reset_positions_ex(
     const gcbf_env_desc* desc, const uint32_t* keys, const float* obstacles, float area_size, float min_dist,
-    float max_travel, float* agent, float* goal, void* stream) {
+    float max_travel, int32_t threefry_partitionable, float* agent, float* goal, void* stream) {
     GCBF_REQUIRE(desc && keys && agent && goal, "gcbf_reset_positions: NULL pointer argument");
     GCBF_REQUIRE(desc->env_kind >= 0 && desc->env_kind <= 3 && desc->n_graphs > 0 && desc->n_agents > 0,
                  "gcbf_reset_positions: bad descriptor");
@@ -1087,17 +1125,22 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_reset_positions(
     const size_t smem = sizeof(float) * 2 * (size_t)desc->n_agents * pd;
     GCBF_REQUIRE(smem <= 200 * 1024, "gcbf_reset_positions: too many agents (%d)", desc->n_agents);
     cudaStream_t st = (cudaStream_t)stream;
+    const bool part = threefry_partitionable != 0;
     if (pd == 2) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(gcbf::reset_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        gcbf::reset_kernel<2><<<desc->n_graphs, 32, smem, st>>>(desc->n_agents, desc->n_obs, sd, keys, obstacles, area_size,
-                                                              min_dist, max_travel, agent, goal);
+        if (part) launch_reset<2, true>(desc, sd, smem, keys, obstacles, area_size, min_dist, max_travel, agent, goal, st);
+        else launch_reset<2, false>(desc, sd, smem, keys, obstacles, area_size, min_dist, max_travel, agent, goal, st);
     } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(gcbf::reset_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        gcbf::reset_kernel<3><<<desc->n_graphs, 32, smem, st>>>(desc->n_agents, desc->n_obs, sd, keys, obstacles, area_size,
-                                                              min_dist, max_travel, agent, goal);
+        if (part) launch_reset<3, true>(desc, sd, smem, keys, obstacles, area_size, min_dist, max_travel, agent, goal, st);
+        else launch_reset<3, false>(desc, sd, smem, keys, obstacles, area_size, min_dist, max_travel, agent, goal, st);
     }
     count_launch();
     return check_launch("reset_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_reset_positions(
+    const gcbf_env_desc* desc, const uint32_t* keys, const float* obstacles, float area_size, float min_dist,
+    float max_travel, float* agent, float* goal, void* stream) {
+    return gcbf_reset_positions_ex(desc, keys, obstacles, area_size, min_dist, max_travel, 0, agent, goal, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_env_step(const gcbf_env_desc* desc, const float* agent, const float* goal,

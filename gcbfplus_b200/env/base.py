@@ -388,9 +388,11 @@ class MultiAgentEnv(ABC):
             keys_t = torch.from_numpy(np.ascontiguousarray(keys).view(np.int32)).to(self.device)
             d = self.desc(E, obstacles.n_obs, edge_cap=1)
             mt = -1.0 if self._max_travel is None else float(self._max_travel)
-            rc = self.lib.gcbf_reset_positions(C.byref(d), _lib.ptr(keys_t), _lib.ptr(obstacles.packed) if obstacles.n_obs else None,
-                                               float(self.area_size), float(np.float32(4 * self.radius)), mt,
-                                               _lib.ptr(agent_t), _lib.ptr(goal_t), self._stream())
+            rc = self.lib.gcbf_reset_positions_ex(C.byref(d), _lib.ptr(keys_t),
+                                                  _lib.ptr(obstacles.packed) if obstacles.n_obs else None,
+                                                  float(self.area_size), float(np.float32(4 * self.radius)), mt,
+                                                  1 if jr.PARTITIONABLE else 0, _lib.ptr(agent_t), _lib.ptr(goal_t),
+                                                  self._stream())
             _lib.check(rc, "gcbf_reset_positions")
             if type(self)._reset_extra is not MultiAgentEnv._reset_extra:      # DubinsCar headings (tiny, host)
                 agent, goal = agent_t.cpu().numpy(), goal_t.cpu().numpy()

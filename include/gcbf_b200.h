@@ -174,6 +174,13 @@ int32_t gcbf_act(const gcbf_env_desc* desc, const float* agent, const float* goa
 int32_t gcbf_reset_positions(const gcbf_env_desc* desc, const uint32_t* keys, const float* obstacles,
                              float area_size, float min_dist, float max_travel, float* agent, float* goal,
                              void* stream);
+/* Same with the threefry stream layout selectable: threefry_partitionable = 0 -> jax's legacy layout (default of
+ * the 0.4.x line, what gcbf_reset_positions uses); 1 -> jax_threefry_partitionable=True (default from JAX 0.5.0:
+ * split child i = threefry(key, (0, i)), random bits = y0 ^ y1).  The reference does not pin a JAX version
+ * (requirements.txt: jax>=0.4.14), so "identical seeds" is defined per layout. */
+int32_t gcbf_reset_positions_ex(const gcbf_env_desc* desc, const uint32_t* keys, const float* obstacles,
+                                float area_size, float min_dist, float max_travel, int32_t threefry_partitionable,
+                                float* agent, float* goal, void* stream);
 
 /* ---------------------------------------------------------------- fused rollout step (a8 body)
  * One iteration of the scan body of rollout() (gcbfplus/trainer/utils.py:46-49): algo.step

@@ -184,3 +184,19 @@ def rates(collision: np.ndarray, finish: np.ndarray):
     unsafe = collision.max(axis=0)
     fin = finish.max(axis=0)
     return float(1 - unsafe.mean()), float(fin.mean()), float(((1 - unsafe) * fin).mean())
+
+
+def get_bb_cbf(env: OracleEnv, cbf_p, g: Graph, agent_id: int, x_dim: int = 0, y_dim: int = 1, n_mesh: int = 20):
+    """trainer/utils.py:149-168: h of agent `agent_id` over an n_mesh x n_mesh grid of its (x, y), other states
+    frozen, topology of `g`, edge features through add_edge_feats.  bb_h[i, j] is at (b_xs[j], b_ys[i])."""
+    b_xs = np.linspace(0.0, env.area_size, n_mesh).astype(np.float32)
+    b_ys = np.linspace(0.0, env.area_size, n_mesh).astype(np.float32)
+    out = np.zeros((n_mesh, n_mesh), dtype=np.float32)
+    with torch.no_grad():
+        for i in range(n_mesh):
+            for j in range(n_mesh):
+                st = g.states[:-1].clone()
+                st[agent_id, x_dim] = float(b_xs[j])
+                st[agent_id, y_dim] = float(b_ys[i])
+                out[i, j] = float(get_cbf(cbf_p, env.add_edge_feats(g, st))[agent_id, 0])
+    return b_xs, b_ys, out

@@ -17,6 +17,11 @@ import numpy as np
 
 M32 = 0xFFFFFFFF
 _ROT = ((13, 15, 26, 6), (17, 29, 16, 24))
+# jax_threefry_partitionable (False: the 0.4.x default the reference was written on; True: default from JAX 0.5.0).
+# Partitionable layout (jax/_src/prng.py _threefry_split_foldlike / _threefry_random_bits_partitionable): element i
+# uses the counter pair (hi(i), lo(i)) of its 64-bit row-major index; split keeps the output pair, random bits
+# are y0 ^ y1.  Tests flip this together with gcbfplus_b200.utils.jrandom.set_partitionable.
+PARTITIONABLE = False
 
 
 def threefry2x32(k0: int, k1: int, c0: int, c1: int) -> Tuple[int, int]:
@@ -49,6 +54,8 @@ def prng_key(seed: int) -> Tuple[int, int]:
 
 
 def split(key: Tuple[int, int], num: int = 2) -> List[Tuple[int, int]]:
+    if PARTITIONABLE:
+        return [threefry2x32(key[0], key[1], 0, i) for i in range(num)]
     b = _bits(key, 2 * num)
     return [(b[2 * i], b[2 * i + 1]) for i in range(num)]
 
@@ -56,7 +63,11 @@ def split(key: Tuple[int, int], num: int = 2) -> List[Tuple[int, int]]:
 def uniform(key: Tuple[int, int], shape: Tuple[int, ...], minval: float, maxval: float) -> np.ndarray:
     n = int(np.prod(shape)) if len(shape) else 1
     f = np.float32
-    bits = np.array(_bits(key, n), dtype=np.uint32)
+    if PARTITIONABLE:
+        pairs = [threefry2x32(key[0], key[1], 0, i) for i in range(n)]
+        bits = np.array([a ^ b for a, b in pairs], dtype=np.uint32)
+    else:
+        bits = np.array(_bits(key, n), dtype=np.uint32)
     fl = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - f(1.0)
     lo, hi = f(minval), f(maxval)
     return np.maximum(lo, fl * (hi - lo) + lo).astype(f).reshape(shape)

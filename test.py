@@ -1,6 +1,9 @@
 """test.py -- evaluation CLI with the reference's flags (test.py:239-266): rollouts with a trained
 (or --u-ref nominal) controller and safe / finish / success rates (test.py:184-198).
-Video rendering / CBF contour plots are out of scope -> --no-video is implied."""
+Video rendering is out of scope -> --no-video is implied; --cbf <agent id> computes the CBF
+contour grids the reference hands to its renderer (test.py:125-131, trainer/utils.py:149-168) and saves them as
+<path>/cbf_contours/epi<k>_agent<id>.npz (b_xs, b_ys, bb_h per time step).  --nojit-rollout is accepted: the
+reference needs it to survive n >= 512 with dense graphs (env/base.py:191-259); the sparse rollout engine has no such limit."""
 import argparse
 import os
 
@@ -10,7 +13,7 @@ import yaml
 from gcbfplus_b200.algo import make_algo
 from gcbfplus_b200.env import make_env
 from gcbfplus_b200.trainer.rollout import RolloutEngine
-from gcbfplus_b200.trainer.utils import test_rates
+from gcbfplus_b200.trainer.utils import cbf_contours, test_rates
 
 
 def test(args):
@@ -77,6 +80,15 @@ def test(args):
             f.write(f"{env.num_agents},{args.epi},{env.max_episode_steps},{env.area_size},{env.params['n_obs']},"
                     f"{safe_mean * 100:.3f},{safe_std * 100:.3f},{finish_mean * 100:.3f},{finish_std * 100:.3f},"
                     f"{succ.mean() * 100:.3f},{succ.std() * 100:.3f}\n")
+    if args.cbf is not None:
+        assert algo is not None, "--cbf needs a trained CBF (--path)"
+        out_dir = os.path.join(path, "cbf_contours")
+        os.makedirs(out_dir, exist_ok=True)
+        for i in range(n_epi):
+            b_x, b_y, bb_h = cbf_contours(algo, env, ro, i, args.cbf)
+            f_out = os.path.join(out_dir, f"epi{i + args.offset:02}_agent{args.cbf}.npz")
+            np.savez_compressed(f_out, b_xs=b_x, b_ys=b_y, bb_h=bb_h, agent_id=args.cbf)
+            print(f"cbf contour grid: {f_out} {bb_h.shape}")
     if not args.no_video:
         print("video rendering is out of scope of the B200 hot path (SURVEY.md section 2, row 17); skipped")
 

@@ -132,3 +132,21 @@ def edge_sets_oracle(og, n_agents: int, n_hits: int):
     for i in range(n_agents):
         out[i] = goal[i] + sorted(agents[i]) + sorted(hits[i], reverse=True)
     return out
+
+
+def probe_reference_stack() -> dict:
+    """Can the reference itself run here?  Re-probed on every call (never cached): its JAX stack and a
+    driver-provided install under baseline/_ref.  Used by tests/test_reference_goldens.py and by
+    `bench.py --impl reference` (which records the outcome in its JSON line)."""
+    import importlib
+    mods = {}
+    for m in ("jax", "flax", "jraph", "optax"):
+        try:
+            importlib.import_module(m)
+            mods[m] = "ok"
+        except Exception as e:                       # noqa: BLE001 -- any failure means "cannot run the reference"
+            mods[m] = f"missing ({type(e).__name__})"
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    has_ref = os.path.isdir(os.path.join(ref_dir, "gcbfplus"))
+    return {"modules": mods, "baseline_ref_installed": has_ref,
+            "runnable": all(v == "ok" for v in mods.values())}

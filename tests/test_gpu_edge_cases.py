@@ -66,3 +66,28 @@ def test_qp_label_equals_clipped_u_ref_when_no_constraint_binds():
     assert float(aux[..., 0].abs().max()) == 0.0 and float(aux[..., 1].abs().max()) == 0.0
     assert torch.equal(u, u_ref)
     assert int(iters.max()) <= 2
+
+
+@pytest.mark.parametrize("env_id", ["DoubleIntegrator", "LinearDrone"])
+def test_inside_obstacles_is_independent_of_agent_collisions(env_id):
+    """env.step(get_eval_info=True)['inside_obstacles'] = inside_obstacles(agent_pos, obstacles, r) alone
+    (double_integrator.py:172-175): an agent that sits in an obstacle AND touches another agent is still inside
+    (the mask used to be collision & ~agent_collision)."""
+    from oracle.geometry import inside_obstacles
+    N, G, area, n_obs = 12, 3, 1.2, 3
+    agent, goal, obs = random_scene(env_id, N, G, area, n_obs, seed=5)
+    pd = 3 if env_id == "LinearDrone" else 2
+    agent[:, 0, :pd] = obs["center"][:, 0]                        # agent 0: at the centre of obstacle 0 ...
+    agent[:, 1, :pd] = obs["center"][:, 0] + 0.01                 # ... and 1 cm from agent 1 (colliding pair)
+    env = product_env(env_id, N, area, n_obs)
+    pobs = product_obstacles(env_id, obs)
+    graph = env.get_graph(torch.from_numpy(agent).cuda(), torch.from_numpy(goal).cuda(), pobs)
+    got = env.inside_obstacles(graph).cpu().numpy()
+    info = env.step(graph, env.u_ref(graph), get_eval_info=True).info["inside_obstacles"].cpu().numpy()
+    torch.cuda.synchronize()
+    assert got[:, 0].all() and got[:, 1].all()
+    packed = pobs.packed.cpu().numpy()
+    for g in range(G):
+        want = inside_obstacles(torch.from_numpy(agent[g, :, :pd]), oracle_obstacles(packed[g]), r=0.05).numpy()
+        np.testing.assert_array_equal(got[g], want)
+        np.testing.assert_array_equal(info[g], want)

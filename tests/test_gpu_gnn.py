@@ -78,3 +78,28 @@ def test_dense_reference_layout_equals_sparse_on_gpu_inputs(gemm_path):
                            oracle_obstacles(pobs.packed.cpu().numpy()[0]))
     with torch.no_grad():
         np.testing.assert_allclose(h, get_cbf(cp, dense).numpy(), atol=TOL_NET, rtol=0)
+
+
+@pytest.mark.parametrize("env_id", ["DoubleIntegrator", "LinearDrone"])
+def test_cbf_contour_grid_matches_oracle(env_id):
+    """test.py --cbf: get_bb_cbf (trainer/utils.py:149-168) as one batched get_cbf over 400 copies of the graph with
+    tiled topology, against the oracle's 400 separate add_edge_feats + get_cbf evaluations."""
+    from gcbfplus_b200.trainer.utils import get_bb_cbf
+    from oracle.algo import get_bb_cbf as oracle_bb
+    N, area, n_obs = 7, 1.5, 3
+    agent, goal, obs = random_scene(env_id, N, 1, area, n_obs, seed=9)
+    env = product_env(env_id, N, area, n_obs)
+    env.edge_cap_per_agent = 48
+    pobs = product_obstacles(env_id, obs)
+    graph = env.get_graph(torch.from_numpy(agent).cuda(), torch.from_numpy(goal).cuda(), pobs)
+    algo = product_algo(env, env_id)
+    xs, ys, h = get_bb_cbf(algo, env, graph.agent[0], graph.goal[0], graph.hits[0], agent_id=2)
+    torch.cuda.synchronize()
+    oenv = oracle_env(env_id, N, area, n_obs)
+    _, cp = oracle_params(env_id)
+    og = oenv.sparsify(oenv.get_graph(torch.from_numpy(agent[0]), torch.from_numpy(goal[0]),
+                                      oracle_obstacles(pobs.packed.cpu().numpy()[0])))
+    oxs, oys, oh = oracle_bb(oenv, cp, og, 2)
+    np.testing.assert_array_equal(xs.cpu().numpy(), oxs)
+    np.testing.assert_allclose(h.cpu().numpy(), oh, atol=3e-5)
+    assert np.abs(oh).max() > 1e-3

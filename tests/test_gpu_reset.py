@@ -14,9 +14,12 @@ pytestmark = pytest.mark.gpu
     ("SingleIntegrator", 8, 5, 1.6, 3, None), ("DoubleIntegrator", 24, 4, 2.6, 8, None),
     ("DoubleIntegrator", 6, 3, 3.0, 4, 1.0), ("DubinsCar", 9, 3, 2.2, 4, None), ("LinearDrone", 12, 4, 1.4, 4, None),
     ("DoubleIntegrator", 512, 2, 32.0, 8, None)])
-def test_device_reset_matches_host_sampler(env_id, N, E, area, n_obs, max_travel):
+@pytest.mark.parametrize("partitionable", [False, True])
+def test_device_reset_matches_host_sampler(env_id, N, E, area, n_obs, max_travel, partitionable, monkeypatch):
+    """Both threefry stream layouts (jax_threefry_partitionable off / on, utils/jrandom.py)."""
     from gcbfplus_b200.env import make_env
     from gcbfplus_b200.utils import jrandom as jr
+    monkeypatch.setattr(jr, "PARTITIONABLE", partitionable)
     keys = jr.split(jr.PRNGKey(17), E)
     out = []
     for host in (False, True):

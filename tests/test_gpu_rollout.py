@@ -18,6 +18,11 @@ def _reset_scene(env_id, N, E, area, n_obs, seed):
 
 
 @pytest.mark.parametrize("env_id,N,E,area,n_obs,T", [("DoubleIntegrator", 8, 3, 2.0, 4, 96),
+                                                      # BASELINE.json configs[0] literally: SingleIntegrator n=8, area-size 4,
+                                                      # 16 envs, obs 0, full 256-step episode
+                                                      ("SingleIntegrator", 8, 16, 4.0, 0, 256),
+                                                      # configs[1] literally: DoubleIntegrator n=8, 16 envs (PARAMS default 8 obstacles)
+                                                      ("DoubleIntegrator", 8, 16, 4.0, 8, 256),
                                                       ("SingleIntegrator", 8, 2, 2.0, 4, 64),
                                                       ("DubinsCar", 8, 2, 2.5, 4, 64),
                                                       ("LinearDrone", 8, 2, 1.2, 3, 48)])

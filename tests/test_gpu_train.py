@@ -11,8 +11,10 @@ from helpers import (oracle_env, oracle_obstacles, oracle_params, product_algo, 
 
 pytestmark = pytest.mark.gpu
 
+# the last two rows: gradient parity at a size where every agent has real neighbours and several row tiles / CTAs
+# contribute to each dW: DoubleIntegrator N=64, B=4 and LinearDrone N=32, B=3 on the oracle's sparse graph
 CASES = [("DoubleIntegrator", 6, 4, 1.4, 3), ("SingleIntegrator", 6, 3, 1.4, 3), ("DubinsCar", 6, 3, 1.6, 3),
-         ("LinearDrone", 6, 3, 1.0, 2)]
+         ("LinearDrone", 6, 3, 1.0, 2), ("DoubleIntegrator", 64, 4, 3.2, 6), ("LinearDrone", 32, 3, 1.7, 3)]
 
 
 def _setup(env_id, N, B, area, n_obs, seed=21, pretrained=True):

@@ -298,15 +298,70 @@ def test_threefry_known_answers():
         assert (jr.uniform(k, (5,), 0, 3) == orr.uniform(kk, (5,), 0, 3)).all()
 
 
+def _jax_normal(jr_uniform, key):
+    """jax.random.normal(key): sqrt(2) * erf_inv(uniform(key, minval=nextafter(-1, 0), maxval=1)) (jax/_src/random.py)."""
+    from scipy.special import erfinv
+    lo = np.nextafter(np.float32(-1), np.float32(0), dtype=np.float32)
+    u = jr_uniform(key, lo, 1.0)
+    return float(np.float32(np.sqrt(2)) * np.float32(erfinv(np.float64(u))))
+
+
+@pytest.mark.parametrize("partitionable", [False, True])
+def test_threefry_stream_layouts_against_values_jax_publishes(partitionable):
+    """Both threefry stream layouts (`jax_threefry_partitionable` off = default of JAX 0.4.x, on = default from
+    JAX 0.5.0) against numbers JAX's own documentation prints -- the `Pseudorandom numbers` tutorial's
+    `key = random.key(42)`, `random.normal(key)` and its three split-and-draw iterations, and `random.uniform(key(0))`
+    of the jax.random docs -- for the product's host RNG and the oracle's scalar restatement.  (Values quoted from the
+    public docs of the respective JAX generations; there is no network here to re-fetch them, and an independent
+    implementation reproducing them to 7 digits is what makes them known answers.)"""
+    from gcbfplus_b200.utils import jrandom as jr
+    from oracle import reset as orr
+    want = {False: dict(normal42=-0.18471177, uniform0=0.41845703,
+                        draws=(1.369469404220581, -0.19947023689746857, -2.298278331756592)),
+            True: dict(normal42=-0.028304616, uniform0=0.947667,
+                       draws=(0.6057640314102173, -0.21089035272598267, -0.3948981463909149))}[partitionable]
+    old_h, old_o = jr.set_partitionable(partitionable), orr.PARTITIONABLE
+    orr.PARTITIONABLE = partitionable
+    try:
+        impls = {
+            "host": (lambda seed: jr.PRNGKey(seed), lambda k: [r for r in jr.split(k)],
+                     lambda k, lo, hi: jr.uniform(k, (), lo, hi)),
+            "oracle": (lambda seed: orr.prng_key(seed), lambda k: orr.split(k),
+                       lambda k, lo, hi: orr.uniform(k, (), lo, hi)),
+        }
+        for name, (mk, split, uni) in impls.items():
+            assert abs(float(uni(mk(0), 0.0, 1.0)) - want["uniform0"]) < 6e-7, name
+            assert abs(_jax_normal(uni, mk(42)) - want["normal42"]) < 2e-7, name
+            key = mk(42)
+            for i in range(3):
+                key, sub = split(key)
+                assert abs(_jax_normal(uni, sub) - want["draws"][i]) < 1e-6 * max(1.0, abs(want["draws"][i])), (name, i)
+        # host (vectorised over keys) == oracle (scalar) in this layout, shaped draws included
+        ks = jr.split(jr.PRNGKey(7), 5)
+        assert (jr.split(ks, 3) == np.stack([jr.split(k, 3) for k in ks])).all()
+        for k in ks:
+            kk = (int(k[0]), int(k[1]))
+            assert [tuple(map(int, r)) for r in jr.split(k, 3)] == orr.split(kk, 3)
+            assert (jr.uniform(k, (5,), 0, 3) == orr.uniform(kk, (5,), 0, 3)).all()
+            assert (jr.uniform(k, (4, 2), 0, 3).ravel() == orr.uniform(kk, (8,), 0, 3)).all()
+    finally:
+        jr.set_partitionable(old_h)
+        orr.PARTITIONABLE = old_o
+
+
 @pytest.mark.parametrize("env_id,N,area,n_obs,max_travel", [
     ("SingleIntegrator", 6, 1.5, 3, None), ("DoubleIntegrator", 8, 2.0, 8, None), ("DoubleIntegrator", 5, 3.0, 4, 1.0),
     ("DubinsCar", 6, 2.0, 4, None), ("LinearDrone", 6, 1.0, 4, None)])
-def test_reset_matches_oracle_bit_exact(env_id, N, area, n_obs, max_travel):
+@pytest.mark.parametrize("partitionable", [False, True])
+def test_reset_matches_oracle_bit_exact(env_id, N, area, n_obs, max_travel, partitionable, monkeypatch):
     """The product's vectorised host reset against the oracle's scalar, per-environment restatement of
-    get_node_goal_rng (crowded scenes: rejection loops and per-env divergence are exercised)."""
+    get_node_goal_rng (crowded scenes: rejection loops and per-env divergence are exercised), in both threefry
+    stream layouts."""
     from gcbfplus_b200.env import make_env
     from gcbfplus_b200.utils import jrandom as jr
     from oracle import reset as orr
+    monkeypatch.setattr(jr, "PARTITIONABLE", partitionable)
+    monkeypatch.setattr(orr, "PARTITIONABLE", partitionable)
     env = make_env(env_id, N, area_size=area, num_obs=n_obs, max_travel=max_travel, device="cpu")
     keys = jr.split(jr.PRNGKey(3), 4)
     obstacles, k2 = env._sample_obstacles(keys)
