@@ -9,6 +9,7 @@ once per epoch loop (the reference returns the last minibatch's info, gcbf_plus.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -57,9 +58,11 @@ def _dist():
 
 
 def train_minibatch(algo, graph: SwarmGraph, safe_mask: torch.Tensor, unsafe_mask: torch.Tensor,
-                    u_qp: torch.Tensor, apply: bool = True) -> TrainState:
+                    u_qp: torch.Tensor, apply: bool = True, denoms_ready: bool = False) -> TrainState:
     """One `update_fn` (gcbf_plus.py:356-441) on the (local shard of the) minibatch `graph`.
-    safe/unsafe_mask uint8 [B, N]; u_qp [B, N, nu].  Enqueues only (no host sync)."""
+    safe/unsafe_mask uint8 [B, N]; u_qp [B, N, nu].  Enqueues only (no host sync).
+    denoms_ready: ts.denoms already holds the GLOBAL label counts of this minibatch (update() all-reduces the counts
+    of a whole epoch's minibatches in one collective) -> no count kernel, no count all-reduce here."""
     env = algo._env
     lib = env.lib
     if algo._trainer_state is None:
@@ -80,11 +83,12 @@ def train_minibatch(algo, graph: SwarmGraph, safe_mask: torch.Tensor, unsafe_mas
     safe_mask = safe_mask.reshape(B * N).to(torch.uint8).contiguous()
     unsafe_mask = unsafe_mask.reshape(B * N).to(torch.uint8).contiguous()
     u_qp = u_qp.reshape(B * N, env.action_dim).float().contiguous()
-    _lib.check(lib.gcbf_mask_counts(_lib.ptr(safe_mask), _lib.ptr(unsafe_mask), B * N, _lib.ptr(ts.denoms), st),
-               "gcbf_mask_counts")
     dist = _dist()
-    if dist is not None:
-        dist.all_reduce(ts.denoms)                      # global ratio-of-sums denominators
+    if not denoms_ready:
+        _lib.check(lib.gcbf_mask_counts(_lib.ptr(safe_mask), _lib.ptr(unsafe_mask), B * N, _lib.ptr(ts.denoms), st),
+                   "gcbf_mask_counts")
+        if dist is not None:
+            dist.all_reduce(ts.denoms)                  # global ratio-of-sums denominators
     hp = (C.c_float * 7)(algo.alpha, algo.eps, algo.loss_action_coef, algo.loss_unsafe_coef, algo.loss_safe_coef,
                          algo.loss_h_dot_coef, 1.0 if _lib.USE_TC else 0.0)
     rc = lib.gcbf_train_step(C.byref(d), hp, _lib.ptr(algo.cbf_params.flat), _lib.ptr(algo.actor_net_params.flat),
@@ -99,6 +103,80 @@ def train_minibatch(algo, graph: SwarmGraph, safe_mask: torch.Tensor, unsafe_mas
     if apply:
         apply_gradients(algo, ts)
     return ts
+
+
+class MinibatchRunner:
+    """One optimizer step of update_inner as ONE CUDA-graph replay.
+
+    Captured once per (minibatch size, edge capacity, batch storage): gather of the selected graphs out of the update's
+    batch arrays into static buffers -> neighbour lists (gcbf_graph_build, topology only) -> gcbf_train_step ->
+    [the ONE NCCL all-reduce of (grad_cbf | grad_actor | stats)] -> grad norm + clip + AdamW for both networks.
+    Per minibatch the host then does two tiny device copies (selection indices, global label counts) and one graph
+    launch instead of ~170 kernel launches with per-launch tensor-map encoding: the train step stops being bound by
+    Python / launch overhead when a rank's share of the minibatch is small (8 GPUs: 32 graphs per rank).
+    GCBF_TRAIN_GRAPH=0 keeps the eager path (same kernels, same order -> same bits)."""
+
+    def __init__(self, algo, batch: dict, mb_size: int, edge_cap: int, u_qp: torch.Tensor):
+        env = algo._env
+        dev = env.device
+        self.algo, self.batch, self.u_qp_all = algo, batch, u_qp
+        N = env.num_agents
+        self.sel = torch.zeros(mb_size, dtype=torch.int64, device=dev)
+        self.agent = torch.zeros(mb_size, N, env.state_dim, dtype=torch.float32, device=dev)
+        self.goal = torch.zeros_like(self.agent)
+        self.hits = torch.zeros(mb_size, N, env.n_hits, env.pos_dim, dtype=torch.float32, device=dev)
+        self.safe = torch.zeros(mb_size, N, dtype=batch["safe"].dtype, device=dev)
+        self.unsafe = torch.zeros(mb_size, N, dtype=batch["unsafe"].dtype, device=dev)
+        self.u_qp = torch.zeros(mb_size, N, env.action_dim, dtype=torch.float32, device=dev)
+        i32 = torch.int32
+        cap = max(int(edge_cap), 64)
+        self.graph = SwarmGraph(env, self.agent, self.goal, None, self.hits,
+                                torch.zeros(mb_size * N, dtype=i32, device=dev), torch.zeros(mb_size * N, dtype=i32, device=dev),
+                                torch.zeros(cap, dtype=i32, device=dev), torch.zeros(cap, dtype=i32, device=dev),
+                                torch.zeros(4, dtype=i32, device=dev))
+        self.cuda_graph: Optional[torch.cuda.CUDAGraph] = None
+
+    def _body(self) -> None:
+        algo, env, b = self.algo, self.algo._env, self.batch
+        torch.index_select(b["agent"], 0, self.sel, out=self.agent)
+        torch.index_select(b["goal"], 0, self.sel, out=self.goal)
+        torch.index_select(b["hits"], 0, self.sel, out=self.hits)
+        torch.index_select(b["safe"], 0, self.sel, out=self.safe)
+        torch.index_select(b["unsafe"], 0, self.sel, out=self.unsafe)
+        torch.index_select(self.u_qp_all, 0, self.sel, out=self.u_qp)
+        env.get_graph(self.agent, self.goal, None, hits=self.hits, out=self.graph)
+        train_minibatch(algo, self.graph, self.safe, self.unsafe, self.u_qp, apply=True, denoms_ready=True)
+
+    def run(self, sel: torch.Tensor, denoms: torch.Tensor) -> None:
+        ts: TrainState = self.algo._trainer_state
+        self.sel.copy_(sel, non_blocking=True)
+        ts.denoms.copy_(denoms, non_blocking=True)
+        if os.environ.get("GCBF_TRAIN_GRAPH", "1") == "0":
+            self._body()
+            return
+        if self.cuda_graph is None:
+            self._body()                                   # warm-up outside capture: function attributes, workspaces,
+            torch.cuda.synchronize(self.agent.device)      # NCCL communicator setup
+            # (the warm-up was a real optimizer step on this minibatch; the capture below records, it does not run)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.cuda_graph = g
+            return
+        self.cuda_graph.replay()
+
+
+def _minibatch_counts(batch: dict, idx: torch.Tensor, bounds: np.ndarray) -> torch.Tensor:
+    """[n_mb, 4] = (n_unsafe, n_safe, n_agents, 0) of every minibatch idx[bounds[i]:bounds[i+1]] of an epoch, on the
+    device, without a loop: per-graph counts -> permute -> cumulative sums at the split points."""
+    N = batch["safe"].shape[1]
+    per = torch.stack([batch["unsafe"].reshape(len(idx), -1).float().sum(1), batch["safe"].reshape(len(idx), -1).float().sum(1)],
+                      dim=1)[idx]                                               # [n, 2] in minibatch order
+    cs = torch.cat([torch.zeros(1, 2, device=per.device, dtype=torch.float64), per.double().cumsum(0)])
+    b = torch.from_numpy(bounds).to(per.device)
+    cnt = (cs[b[1:]] - cs[b[:-1]]).float()
+    n_ag = ((b[1:] - b[:-1]) * N).float()[:, None]
+    return torch.cat([cnt, n_ag, torch.zeros_like(n_ag)], dim=1).contiguous()
 
 
 def apply_gradients(algo, ts: TrainState) -> None:
@@ -223,14 +301,23 @@ def update(algo, rollout: Rollout, step: int) -> dict:
     # exact upper bound on a minibatch's edge count from the per-graph counts measured while labelling: no
     # minibatch can overflow its edge lists whatever graphs the permutation puts together
     mb_cap = max(int(qp_info["graph/max_edges"]) * mb_graphs, 64)
-    info = {}
+    # fixed-address copies of what the captured gather reads (the batch dict holds views / cat results of this update)
+    batch = {k: v.contiguous() for k, v in batch.items()}
+    bounds = np.concatenate([[0], np.cumsum([len(m) for m in np.array_split(np.arange(n), n_mb)])]).astype(np.int64)
+    runners: Dict[int, MinibatchRunner] = {}
     for _ in range(algo.inner_epoch):
         idx = torch.from_numpy(algo.rng.permutation(n)).to(env.device)
-        for mb in np.array_split(np.arange(n), n_mb):
-            sel = idx[torch.from_numpy(mb).to(env.device)]
-            g = env.get_graph(batch["agent"][sel], batch["goal"][sel], None, hits=batch["hits"][sel].contiguous(),
-                              edge_cap=mb_cap)
-            train_minibatch(algo, g, batch["safe"][sel], batch["unsafe"][sel], u_qp[sel])
+        # label counts of all minibatches of the epoch: ONE small all-reduce per epoch instead of one per optimizer
+        # step (the counts depend on the data only)
+        denoms_all = _minibatch_counts(batch, idx, bounds)
+        if dist is not None:
+            dist.all_reduce(denoms_all)
+        for i in range(n_mb):
+            lo, hi = int(bounds[i]), int(bounds[i + 1])
+            r = runners.get(hi - lo)
+            if r is None:
+                r = runners[hi - lo] = MinibatchRunner(algo, batch, hi - lo, mb_cap, u_qp)
+            r.run(idx[lo:hi], denoms_all[i])
     info = read_info(algo)
     info.update(qp_info)
     update_tgt(algo, 0.5)

@@ -204,7 +204,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_gemm_tn_tc(const 
                                                                           int32_t m_cap, int32_t K1, int32_t N,
                                                                           int32_t n_agents_total, void* stream) {
     GCBF_REQUIRE(X && dY && C, "gcbf_gemm_tn_tc: NULL pointer");
-    GCBF_REQUIRE((((uintptr_t)X | (uintptr_t)dY) & 15) == 0, "gcbf_gemm_tn_tc: 16-byte alignment required");
+    GCBF_REQUIRE((((uintptr_t)X | (uintptr_t)dY | (uintptr_t)C) & 15) == 0, "gcbf_gemm_tn_tc: 16-byte alignment required");
     return gcbf::tc::launch_gemm_tn_tc(X, ldx, dY, C, roww, row2agent, RowCount{m_ptr, m_fixed, m_cap}, K1, N,
                                        n_agents_total, (cudaStream_t)stream);
 }
