@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/sec (agents x envs x steps / s) of the GCBF+ rollout hot path.
 
-Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]`
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference] [--config 3|4|5]`
 (N > 1: launched by torch.distributed.run, one rank per GPU).  One JSON line on rank 0.
 
-A "step" is one steady-state T = 256-step closed-loop rollout of E envs per
-GPU of the BASELINE.json config `DoubleIntegrator n=512, 16 envs, obs 8, n-rays 32`:
-per env-step {actor GNN forward, a = 2 pi + u_ref, clip, Euler, reward/cost, LiDAR ray cast,
-radius neighbour lists} with the reference's pretrained DoubleIntegrator weights.
+A "step" is one steady-state T = 256-step closed-loop rollout of E envs per GPU of a BASELINE.json
+config -- default configs[2] `DoubleIntegrator n=512, 16 envs, obs 8, n-rays 32` (the config the metric is quoted
+on); `--config 4` = DubinsCar n=256, obs 16, 32 envs over 8 GPUs (4 per GPU); `--config 5` = LinearDrone n=1024,
+64 envs over 8 GPUs (8 per GPU; `--envs-per-gpu` runs the E in {64,128,256,512} sweep).  Per env-step: actor GNN
+forward, a = 2 pi + u_ref, clip, Euler, reward / cost, LiDAR ray cast + top-k, radius neighbour lists, with the
+reference's pretrained weights of that environment.
 `value` : inputs resident in HBM (CUDA events around K replays of the rollout CUDA graph).
 `e2e`   : through RolloutEngine with HOST (pinned) initial conditions, H2D + D2H inside.
-`--impl reference`: the restated reference (dense padded N x N formulation of
-gcbfplus/utils/graph.py + nn/gnn.py, torch-CPU fp32, all host threads) on a bounded
-sample -- JAX is not installable in this image, so the CPU oracle is the arm.
+`roofline`: the kernel with the largest measured share of the env-step (every kernel of the step is timed alone,
+            back to back in a CUDA graph on the buffers a real step left behind), algorithmic FLOPs / its time.
+`--impl reference`: the restated reference (dense padded N x N formulation of gcbfplus/utils/graph.py + nn/gnn.py,
+torch-CPU fp32, host threads) -- JAX is not installable in this image (re-probed on every run and
+recorded in the line), so the CPU oracle is the arm.  Each of its K steps is ONE env-step of ONE env of the workload.
 """
 from __future__ import annotations
 
@@ -28,10 +32,33 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "env-steps/sec (agents x envs x steps/s) DoubleIntegrator n=512"
-ENV_ID, N_AGENTS, ENVS_PER_GPU, N_OBS, N_RAYS, AREA, T_STEPS = "DoubleIntegrator", 512, 16, 8, 32, 32.0, 256
-F_EDGE, F_NODE = 267520, 461312          # FLOP per real edge / per agent (actor, DI)
-B_ALG = 312                              # algorithmic bytes per agent-env-step (DI, recording on)
+T_STEPS = 256
+# BASELINE.json configs[2..4] (1-based 3..5).  area: density-preserving sqrt(2N) / N^(1/3).
+# F_edge / F_node: SURVEY 8d FLOP per real edge / per agent (actor net, unfolded reference formulation);
+# F_edge_folded / F_node_folded: what the folded inference kernels execute; B_alg: algorithmic bytes per agent-env-step.
+CONFIGS = {
+    3: dict(env="DoubleIntegrator", N=512, envs_total=16, gpus=1, obs=8, rays=32, area=32.0, F_edge=267520,
+            F_node=461312, B_alg=312, name="configs[2]"),
+    4: dict(env="DubinsCar", N=256, envs_total=32, gpus=8, obs=16, rays=32, area=22.63, F_edge=267520, F_node=461312,
+            B_alg=312, name="configs[3]"),
+    5: dict(env="LinearDrone", N=1024, envs_total=64, gpus=8, obs=4, rays=32, area=10.08, F_edge=268544, F_node=461824,
+            B_alg=276, name="configs[4]"),
+}
+STEP_KERNELS = ["edge message + chained gate GEMM (gemm_tc_prod_kernel<...,CHAIN>)", "segment softmax + aggregate",
+                "update layer GEMM 128->256", "folded update/head GEMM 256->256 + output partial sums",
+                "policy tail + LiDAR + neighbour lists (graph_build_kernel)"]
+
+
+def metric_name(cfg) -> str:
+    return f"env-steps/sec (agents x envs x steps/s) {cfg['env']} n={cfg['N']}"
+
+
+def folded_flops(cfg):
+    """FLOP per real edge / per agent of the FOLDED inference path: layer 1 (ed + bias table) x 256,
+    W23 256x128, gate 128x128 + gate vector; per agent update 128x256, UH 256x256, output 256 x nu."""
+    ed = {"SingleIntegrator": 2, "DoubleIntegrator": 4, "DubinsCar": 4, "LinearDrone": 6}[cfg["env"]]
+    nu = 3 if cfg["env"] == "LinearDrone" else 2
+    return 2 * ((ed + 1) * 256 + 256 * 128 + 128 * 128 + 128), 2 * (128 * 256 + 256 * 256 + 256 * nu)
 
 
 def load_peaks():
@@ -92,11 +119,12 @@ class ClockSampler:
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from helpers import GOLDEN, product_algo
+    from helpers import product_algo
     from gcbfplus_b200 import _lib
     from gcbfplus_b200.env import make_env
     from gcbfplus_b200.trainer.rollout import RolloutEngine
 
+    cfg = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -108,11 +136,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.load(build_if_missing=False)
 
-    E, N, T = args.envs_per_gpu, N_AGENTS, args.T
-    env = make_env(ENV_ID, N, area_size=AREA, num_obs=N_OBS, n_rays=N_RAYS, device=dev)
-    algo = product_algo(env, ENV_ID)
+    env_id, N, T = cfg["env"], cfg["N"], args.T
+    E = args.envs_per_gpu or max(cfg["envs_total"] // cfg["gpus"], 1)
+    env = make_env(env_id, N, area_size=cfg["area"], num_obs=cfg["obs"], n_rays=cfg["rays"], device=dev)
+    algo = product_algo(env, env_id)
     g0 = env.reset(1000 + rank, n_envs=E)
-    eng = RolloutEngine(env, E, T=T, n_obs=N_OBS)
+    eng = RolloutEngine(env, E, T=T, n_obs=cfg["obs"])
     eng.set_params(algo.actor_params)
     # host-side (pinned) copies for the e2e leg
     h_agent = g0.agent.cpu().pin_memory()
@@ -183,37 +212,38 @@ def run_ours(args):
     d2h = (h_rew.numel() + h_cost.numel() + h_final.numel()) * 4
 
     # ---- train step (update_inner, reported separately per SURVEY 8d): minibatch of 256 graphs of the
-    # recorded rollout, sharded over ranks, incl. the denominator + packed-gradient all-reduces
+    # recorded rollout, sharded over ranks, incl. the packed-gradient all-reduce
     train = None if args.no_train else train_step_bench(torch, dist if world > 1 else None, env, algo, eng, rank, world,
-                                                        args, max_over_ranks, barrier)
+                                                        cfg, max_over_ranks, barrier)
 
-    # ---- roofline of the dominant kernel (fp32 GEMM 256x256 over the edge rows), timed alone
-    roof = gemm_roofline(torch, _lib, dev, int(n_edges), E * N) if rank == 0 else None
-    cpu = cpu_baseline(args, steps=1) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    # ---- every kernel of the env-step timed alone -> dominant kernel -> roofline
+    roof = step_kernel_rooflines(torch, _lib, env, eng, cfg, n_edges, E * N, ms_per_step / T) if rank == 0 else None
+    cpu = cpu_baseline(cfg, steps=1, warmup=1) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
     if rank == 0:
         hbm, tf_burst, tf_sus, src = load_peaks()
-        flop_step = (deg_real * F_EDGE + F_NODE) * N * E * world          # per env-step, whole job
+        flop_step = (deg_real * cfg["F_edge"] + cfg["F_node"]) * N * E * world          # per env-step, whole job
         out = {
-            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(cfg), "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{ENV_ID} n={N} envs/gpu={E} obs={N_OBS} n_rays={N_RAYS} area={AREA} "
-                                   f"T={T} rollout (configs[2])", "step": f"one {T}-step rollout of {E} envs per GPU",
-                       "weights": "reference pretrained DoubleIntegrator gcbf+ (tests/golden fixture)",
-                       "l2": "no flush: each rollout streams ~0.6 GB of trajectory records (> 126 MB L2)",
-                       "deg_real": deg_real, "edges_per_step": n_edges},
+            "config": {"workload": f"{env_id} n={N} envs/gpu={E} obs={cfg['obs']} n_rays={cfg['rays']} area={cfg['area']} "
+                                   f"T={T} rollout ({cfg['name']})", "step": f"one {T}-step rollout of {E} envs per GPU",
+                       "weights": f"reference pretrained {env_id} gcbf+ (tests/golden fixture)",
+                       "l2": "no flush: each rollout streams its whole trajectory record (0.6 GB at configs[2], > 126 MB L2) "
+                             "and every env-step rewrites the ~60 MB activation workspace",
+                       "deg_real": deg_real, "edges_per_step": n_edges, "us_per_env_step": ms_per_step / T * 1e3},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": eng.launches_per_run * args.steps,
             "clocks": clocks,
             "roofline": roof,
             "rollout_rooflines": {
-                "hbm_frac_of_" + src: value * B_ALG / (hbm * 1e9 * world),
+                "hbm_frac_of_" + src: value * cfg["B_alg"] / (hbm * 1e9 * world),
                 "algorithmic_tflops_per_gpu": value / (N * E * world) * flop_step / 1e12 / world,
-                "note": "whole rollout vs HBM (312 B/agent-step) and achieved TFLOP/s per GPU counting the reference's "
-                        "unfolded F_edge/F_node (SURVEY 8d); the path is latency-bound (8 dependent launches per "
-                        "env-step over 8192 agents), not HBM-bound"},
+                "note": f"whole rollout vs HBM ({cfg['B_alg']} B/agent-step) and achieved TFLOP/s per GPU counting the "
+                        "reference's unfolded F_edge / F_node (SURVEY 8d); the path is latency-bound "
+                        f"({eng.launches_per_run // max(T, 1)} dependent single-wave launches per env-step), not HBM-bound"},
             "train_step": train,
             "cpu_baseline": cpu,
         }
@@ -222,168 +252,232 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def train_step_bench(torch, dist, env, algo, eng, rank, world, args, max_over_ranks, barrier):
-    """GCBF+ update_inner throughput: global minibatch of 256 graphs (N=512) drawn from the recorded
-    rollout, B/world graphs per rank, u_qp := u_ref + 0.1 (QP labels are an input)."""
+def train_step_bench(torch, dist, env, algo, eng, rank, world, cfg, max_over_ranks, barrier):
+    """GCBF+ update_inner throughput: global minibatch of 256 graphs drawn from the recorded rollout, B/world graphs
+    per rank, u_qp := u_ref + 0.1 (label values do not change the work), every optimizer step = ONE CUDA-graph
+    replay (algo/train.py MinibatchRunner: gather -> neighbour lists -> train step -> all-reduce -> clip + AdamW)."""
     from gcbfplus_b200.algo import train as T
     B_glob = 256
     B = max(B_glob // world, 1)
     ro = eng.result()
-    tsel = torch.arange(B, device=env.device) % eng.T
-    esel = torch.arange(B, device=env.device) % eng.E
-    agent = eng.agent[tsel, esel].contiguous()
-    hits = eng.hits[tsel, esel].contiguous()
-    goal = eng.goal[esel].contiguous()
-    old = env.edge_cap_per_agent
-    env.edge_cap_per_agent = 4
-    g = env.get_graph(agent, goal, None, hits=hits)
-    env.edge_cap_per_agent = old
+    n_pool = 4 * B
+    tsel = torch.arange(n_pool, device=env.device) % eng.T
+    esel = (torch.arange(n_pool, device=env.device) // 7) % eng.E
+    batch = {"agent": eng.agent[tsel, esel].contiguous(), "hits": eng.hits[tsel, esel].contiguous(),
+             "goal": eng.goal[esel].contiguous()}
+    g_all = env.get_graph(batch["agent"], batch["goal"], None, hits=batch["hits"])
     obs_rep = ro.obstacle.select(esel.cpu().numpy()) if hasattr(ro.obstacle, "select") else None
-    gm = g._replace(obstacle=obs_rep)
-    unsafe = env.unsafe_mask(gm)
-    safe = ~unsafe
-    u_qp = env.u_ref(g) + 0.1
+    unsafe = env.unsafe_mask(g_all._replace(obstacle=obs_rep))
+    batch["unsafe"] = unsafe.to(torch.uint8).contiguous()
+    batch["safe"] = (~unsafe).to(torch.uint8).contiguous()
+    u_qp = env.u_ref(g_all) + 0.1
+    per_graph = g_all.row_deg.reshape(n_pool, -1).sum(dim=1)
+    cap = int(per_graph.max().item()) * B
     algo._trainer_state = None
-    for _ in range(2):
-        T.train_minibatch(algo, g, safe, unsafe, u_qp, apply=True)
+    algo._trainer_state = T.TrainState(algo)
+    runner = T.MinibatchRunner(algo, batch, B, cap, u_qp)
+    sels = [torch.arange(i * B, (i + 1) * B, device=env.device) for i in range(4)]
+    import numpy as np
+    denoms = T._minibatch_counts(batch, torch.arange(n_pool, device=env.device), np.arange(0, n_pool + 1, B))
+    if dist is not None:
+        dist.all_reduce(denoms)
+    for i in range(3):                      # eager warm-up, capture, first replay
+        runner.run(sels[i % 4], denoms[i % 4])
     torch.cuda.synchronize()
-    g.check_overflow()
-    n_it = 5
+    runner.graph.check_overflow()
+    n_it = 8
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = env.lib.gcbf_launch_count()
     barrier()
     ev0.record()
-    for _ in range(n_it):
-        T.train_minibatch(algo, g, safe, unsafe, u_qp, apply=True)
+    for i in range(n_it):
+        runner.run(sels[i % 4], denoms[i % 4])
     ev1.record()
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1)) / n_it
-    launches = (env.lib.gcbf_launch_count() - n0) // n_it
-    n_edges = g.n_edge
+    # launch count of one step: one eager pass
+    os.environ["GCBF_TRAIN_GRAPH"] = "0"
+    n0 = env.lib.gcbf_launch_count()
+    runner.run(sels[0], denoms[0])
+    launches = env.lib.gcbf_launch_count() - n0
+    os.environ["GCBF_TRAIN_GRAPH"] = "1"
+    torch.cuda.synchronize()
+    n_edges = float(per_graph[:B].sum().item())
     N = env.num_agents
-    flops = 9.0 * (n_edges * F_EDGE + B * N * F_NODE) * world       # 3 passes x (fwd + ~2x bwd), SURVEY 8d
+    flops = 9.0 * (n_edges * cfg["F_edge"] + B * N * cfg["F_node"]) * world       # 3 passes x (fwd + ~2x bwd), SURVEY 8d
     return {"ms_per_minibatch": ms, "graphs_per_s": B * world / (ms * 1e-3),
             "agent_samples_per_s": B * world * N / (ms * 1e-3), "global_batch_graphs": B * world,
-            "graphs_per_rank": B, "edges_per_rank": n_edges, "launches_per_step": int(launches),
+            "graphs_per_rank": B, "edges_per_rank": n_edges, "kernels_per_step": int(launches),
+            "launch_mode": "one CUDA-graph replay per optimizer step (gather + graph build + train step + all-reduce + "
+                           "clip/AdamW)",
             "approx_tflops_per_gpu": flops / world / (ms * 1e-3) / 1e12,
-            "allreduce_bytes_per_step": 4 * (algo._trainer_state.packed.numel() + 4) if world > 1 else 0}
+            "collectives_per_step": 1 if world > 1 else 0,
+            "allreduce_bytes_per_step": 4 * algo._trainer_state.packed.numel() if world > 1 else 0}
 
 
-def gemm_roofline(torch, _lib, dev, n_edges: int, n_agents: int):
-    """Dominant kernel = tc::gemm_tc_kernel (tcgen05 kind::tf32, 3xTF32 operand split, TMA + mbarrier pipeline,
-    fp32 accumulators in TMEM): ~49% of a rollout step and ~45% of a train step.  Timed alone with CUDA events
-    on the launching stream, L2 flushed between launches.  `achieved` counts ALGORITHMIC flops (2 M K N, one
-    fp32-equivalent GEMM); the tensor pipe executes 3x that in TF32 MMAs."""
+def step_kernel_rooflines(torch, _lib, env, eng, cfg, n_edges: float, n_agents: int, step_ms: float):
+    """Times every kernel of the env-step ALONE (gcbf_rollout_step_select: one launch per call, 40 calls captured in
+    one CUDA graph, CUDA events around its replay, on the buffers the last full step left behind -- i.e. warm L2 and
+    back-to-back launches, like inside the rollout graph), picks the one with the largest share and reports its
+    algorithmic work / time against the measured peaks."""
+    import ctypes as C
     hbm, tf_burst, tf_sus, src = load_peaks()
-    lib = _lib.load()
-    st = torch.cuda.current_stream(dev).cuda_stream
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    lib = env.lib
+    ch = eng.chains[0]
+    d = ch.desc
+    t = 1
+    b = t % 2
+    obs = eng.obstacles[ch.e0].data_ptr() if eng.O > 0 else None
+    REP = 40
 
-    def time_tc(M, K, Nn, simt=False):
-        A = torch.randn(M, K, device=dev)
-        W = torch.randn(K, Nn, device=dev) * 0.05
-        Bt = W.t().contiguous()
-        Bh, Bl = torch.empty_like(Bt), torch.empty_like(Bt)
-        _lib.check(lib.gcbf_split_tf32(Bt.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), Bt.numel(), st), "split")
-        b = torch.zeros(Nn, device=dev)
-        Cout = torch.empty(M, Nn, device=dev)
-        times = []
-        for it in range(8):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            if simt:
-                _lib.check(lib.gcbf_gemm_nn(0, 0, A.data_ptr(), W.data_ptr(), b.data_ptr(), None, Cout.data_ptr(), None,
-                                            None, M, M, K, Nn, st), "gcbf_gemm_nn")
-            else:
-                _lib.check(lib.gcbf_gemm_tc(0, 0, A.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), b.data_ptr(), None,
-                                            Cout.data_ptr(), None, None, M, M, K, Nn, st), "gcbf_gemm_tc")
-            e1.record()
-            torch.cuda.synchronize()
-            if it >= 3:
-                times.append(e0.elapsed_time(e1))
-        return sum(times) / len(times)
+    def enqueue(select: int, stream: int):
+        rc = lib.gcbf_rollout_step_select(
+            C.byref(d), eng.params_buf.data_ptr(), eng.infer_blob.data_ptr(), 1,
+            eng.agent[t, ch.e0].data_ptr(), eng.goal[ch.e0].data_ptr(), obs, env.ray_table.data_ptr(),
+            eng.hits[t, ch.e0].data_ptr(), ch.row_start[b].data_ptr(), ch.row_deg[b].data_ptr(),
+            ch.edge_recv[b].data_ptr(), ch.edge_src[b].data_ptr(), ch.counters[t].data_ptr(),
+            eng.actions[t, ch.e0].data_ptr(), eng.agent[t + 1, ch.e0].data_ptr(), eng.hits[t + 1, ch.e0].data_ptr(),
+            ch.row_start[1 - b].data_ptr(), ch.row_deg[1 - b].data_ptr(), ch.edge_recv[1 - b].data_ptr(),
+            ch.edge_src[1 - b].data_ptr(), ch.counters[t + 1].data_ptr(), eng.rewards[t, ch.e0:].data_ptr(),
+            eng.costs[t, ch.e0:].data_ptr(), ch.ws.data_ptr(), ch.ws.numel(), select, stream)
+        _lib.check(rc, "gcbf_rollout_step_select")
 
-    M, K, Nn = max(n_edges, 128), 256, 128                      # message layer of the rollout (edge rows)
-    ms = time_tc(M, K, Nn)
-    flops = 2.0 * M * K * Nn
-    achieved = flops / (ms * 1e-3) / 1e12
-    Mt = 200000                                                 # train-step sized launch (256 graphs x 512 agents)
-    ms_t = time_tc(Mt, 256, 256)
-    ach_t = 2.0 * Mt * 256 * 256 / (ms_t * 1e-3) / 1e12
-    ms_s = time_tc(Mt, 256, 256, simt=True)
-    alg_bytes = 4.0 * (M * K + K * Nn + M * Nn)
-    return {"kernel": "tc::gemm_tc_kernel<128,EPI_BIAS> (tcgen05 3xTF32) M=%d K=256 N=128: folded message layer "
-                      "over the rollout's edge rows" % M,
-            "bound": "tensor", "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
-            "peak_source": src + " bf16 cuBLAS burst (kernel timed alone)",
-            "us_per_launch": ms * 1e3, "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes, "traffic": None,
-            "tf32_mma_tflops": 3 * achieved, "frac_of_tf32_peak": 3 * achieved / (tf_burst / 2),
-            "train_shape": {"M": Mt, "K": 256, "N": 256, "us_per_launch": ms_t * 1e3, "achieved": ach_t,
-                            "frac": ach_t / tf_burst, "tf32_mma_tflops": 3 * ach_t,
-                            "frac_of_tf32_peak": 3 * ach_t / (tf_burst / 2),
-                            "simt_fp32_kernel_tflops": 2.0 * Mt * 256 * 256 / (ms_s * 1e-3) / 1e12,
-                            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu
-                            # --set full capture (profiles/r01_final_summary.md), not re-measured here
-                            "traffic": 205.6e6 + 151.5e6, "algorithmic_bytes": 4.0 * (Mt * 256 + 256 * 256 + Mt * 256)},
-            "note": "rollout launches are single-wave (110 row tiles on 148 SMs): latency-bound; the train-shape "
-                    "line shows the kernel at scale.  TF32 dense peak taken as half the measured bf16 peak."}
+    if not eng.use_tc:
+        return None
+    # bring the buffers of step t into the state a rollout leaves them in (edge lists of state t in half b)
+    st = torch.cuda.current_stream(env.device).cuda_stream
+    eng._build(ch, t, st)
+    enqueue(31, st)
+    torch.cuda.synchronize()
+    us = []
+    for k in range(5):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            s = torch.cuda.current_stream(env.device).cuda_stream
+            for _ in range(REP):
+                enqueue(1 << k, s)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us.append(e0.elapsed_time(e1) * 1e3 / (3 * REP))
+    total = sum(us)
+    fe, fn = folded_flops(cfg)
+    nu = 3 if cfg["env"] == "LinearDrone" else 2
+    ed = {"SingleIntegrator": 2, "DoubleIntegrator": 4, "DubinsCar": 4, "LinearDrone": 6}[cfg["env"]]
+    sd = {"SingleIntegrator": 2, "DoubleIntegrator": 4, "DubinsCar": 4, "LinearDrone": 6}[cfg["env"]]
+    pd = 3 if cfg["env"] == "LinearDrone" else 2
+    R = env.n_hits
+    # algorithmic work per launch (flops, compulsory bytes): per edge / per agent figures x the units of one launch
+    rays = env.n_rays_cast
+    ray_flops = rays * max(cfg["obs"], 1) * (4 * 30 if pd == 2 else 40)        # SURVEY 8d: ~30 FLOP per ray-edge test
+    work = [
+        (n_edges * fe, n_edges * (2 * 4 + 4 * sd * 2 + 4 * 128 + 4)),                        # idx + states in, MSG + logit out
+        (n_edges * (2 * 128 + 8), n_edges * (4 * 128 + 4) + n_agents * (8 + 4 * 128)),        # MSG + logit in, AG out
+        (n_agents * 2 * 128 * 256, n_agents * 4 * (128 + 256)),
+        (n_agents * 2 * (256 * 256 + 256 * nu), n_agents * 4 * (256 + 4)),
+        (n_agents * (ray_flops + 8 * cfg["N"]), n_agents * (4 * sd * 3 + 4 * nu + 4 * pd * R + 8) + n_edges * 8),
+    ]
+    kernels = []
+    for k in range(5):
+        fl, by = work[k]
+        kernels.append({"kernel": STEP_KERNELS[k], "us": us[k], "share": us[k] / total,
+                        "algorithmic_gflop": fl / 1e9, "achieved_tflops": fl / (us[k] * 1e-6) / 1e12,
+                        "algorithmic_mb": by / 1e6, "achieved_gbs": by / (us[k] * 1e-6) / 1e9})
+    dom = max(range(5), key=lambda k: us[k])
+    fl, by = work[dom]
+    tensor = dom in (0, 2, 3)
+    achieved = fl / (us[dom] * 1e-6) / 1e12 if tensor else by / (us[dom] * 1e-6) / 1e9
+    peak = tf_burst if tensor else hbm
+    traffic = load_traffic(dom)
+    return {"kernel": STEP_KERNELS[dom], "bound": "tensor" if tensor else "hbm", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s" if tensor else "GB/s", "frac": achieved / peak,
+            "peak_source": src + (" bf16 cuBLAS burst (MEASURED_PEAKS.json; the kernel computes fp32-class results with "
+                                  "3 tf32 MMAs per product, so its own ceiling is 1/6 of this)" if tensor else " HBM copy"),
+            "us_per_launch": us[dom], "share_of_step": us[dom] / total,
+            "algorithmic_flops": fl, "algorithmic_bytes": by, "traffic": traffic["bytes"] if traffic else None,
+            "traffic_source": traffic["source"] if traffic else "no ncu capture of this build under profiles/ (null)",
+            "step_kernels": kernels, "sum_of_isolated_us": total, "measured_step_us": step_ms * 1e3,
+            "whole_step": {"algorithmic_gflop_folded": (n_edges * fe + n_agents * fn) / 1e9,
+                           "achieved_tflops_folded": (n_edges * fe + n_agents * fn) / (step_ms * 1e-3) / 1e12,
+                           "frac_of_bf16_peak": (n_edges * fe + n_agents * fn) / (step_ms * 1e-3) / 1e12 / tf_burst},
+            "note": "each kernel timed alone: 40 back-to-back launches in a CUDA graph (warm L2, the buffers of a real "
+                    "step), CUDA events; algorithmic FLOPs count the folded fp32-equivalent work (2 M K N per GEMM), "
+                    "not the 3x tf32 MMAs the tensor pipe executes"}
+
+
+def load_traffic(kernel_index: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of step kernel `kernel_index`, from the ncu --set full
+    capture of THIS build (profiles/r02_traffic.json, written by tools/ncu_traffic.py with the source digest of the
+    build it profiled).  None when absent or stale -- never a hard-coded number."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        from gcbfplus_b200 import build as _b
+        d = json.load(open(p))
+        ent = d.get("kernels", {}).get(str(kernel_index))
+        if ent is None:
+            return None
+        stale = d.get("source_digest") != _b._digest()
+        return {"bytes": ent["dram_bytes_per_launch"],
+                "source": f"profiles/r02_traffic.json ({ent['ncu_kernel']}, {ent['launches']} launches, ncu --set full"
+                          + (", captured on an EARLIER build of the sources" if stale else ", this build") + ")"}
+    except Exception:
+        return None
 
 
 # ======================================================================================== CPU arm
-def cpu_baseline(args, steps: int = 1, verbose: bool = False):
-    """Restated reference (dense padded formulation), torch-CPU fp32, all host threads, on a
-    bounded sample: 1 env of the same workload (n=512, obs 8, 32 rays), `steps` env-steps."""
+def cpu_baseline(cfg, steps: int = 1, warmup: int = 1, verbose: bool = False):
+    """Restated reference (dense padded formulation), torch-CPU fp32, on a bounded sample: ONE env of the workload,
+    `steps` timed env-steps after `warmup`.  The thread count is the fastest of a probe AT THE WORKLOAD'S SIZE
+    (one dense policy forward per candidate)."""
     import numpy as np
     import torch
     from helpers import oracle_env, oracle_params
     from oracle.algo import act
-    from oracle.geometry import Rectangle
+    from oracle.geometry import Rectangle, Sphere
     ncpu = os.cpu_count() or 1
     rng = np.random.Generator(np.random.PCG64(0))
-    ap, _ = oracle_params(ENV_ID)
-
-    def probe(threads: int) -> float:
-        """Seconds for one dense policy forward at n=128 with `threads` intra-op threads."""
-        torch.set_num_threads(threads)
-        n = 128
-        e = oracle_env(ENV_ID, n, 16.0, 0, N_RAYS)
-        ag = torch.zeros(n, 4)
-        ag[:, :2] = torch.rand(n, 2) * 16.0
-        with torch.no_grad():
-            g = e.get_graph(ag, ag.flip(0).clone(), None)
-            act(e, ap, g)
-            t0 = time.perf_counter()
-            act(e, ap, g)
-            return time.perf_counter() - t0
-
+    env_id, N, area, n_obs = cfg["env"], cfg["N"], cfg["area"], cfg["obs"]
+    ap, _ = oracle_params(env_id)
+    oenv = oracle_env(env_id, N, area, n_obs, cfg["rays"])
+    pd, sd = oenv.pos_dim, oenv.state_dim
+    if pd == 2:
+        obs = Rectangle.create(rng.uniform(0, area, (n_obs, 2)), rng.uniform(0.1, 0.5, n_obs),
+                               rng.uniform(0.1, 0.5, n_obs), rng.uniform(0, 2 * np.pi, n_obs))
+    else:
+        obs = Sphere.create(rng.uniform(0, area, (n_obs, 3)), rng.uniform(0.075, 0.15, n_obs))
+    agent = torch.zeros(N, sd)
+    agent[:, :pd] = torch.from_numpy(rng.uniform(0, area, (N, pd)).astype(np.float32))
+    goal = torch.zeros(N, sd)
+    goal[:, :pd] = torch.from_numpy(rng.uniform(0, area, (N, pd)).astype(np.float32))
     cands = sorted({c for c in (ncpu, ncpu // 2, 64, 32, 16, 8) if 1 <= c <= ncpu}, reverse=True)
-    timings = {c: probe(c) for c in cands}
-    cores = min(timings, key=timings.get)            # the thread count the restated reference runs fastest with
-    torch.set_num_threads(cores)
-    N = N_AGENTS
-    oenv = oracle_env(ENV_ID, N, AREA, N_OBS, N_RAYS)
-    obs = Rectangle.create(rng.uniform(0, AREA, (N_OBS, 2)), rng.uniform(0.1, 0.5, N_OBS),
-                           rng.uniform(0.1, 0.5, N_OBS), rng.uniform(0, 2 * np.pi, N_OBS))
-    agent = torch.zeros(N, 4)
-    agent[:, :2] = torch.from_numpy(rng.uniform(0, AREA, (N, 2)).astype(np.float32))
-    goal = torch.zeros(N, 4)
-    goal[:, :2] = torch.from_numpy(rng.uniform(0, AREA, (N, 2)).astype(np.float32))
-    times = []
+    timings = {}
     with torch.no_grad():
         g = oenv.get_graph(agent, goal, obs)
-        for s in range(steps + 1):
+        for c in cands:                               # probe at the workload's own size
+            torch.set_num_threads(c)
+            act(oenv, ap, g)
             t0 = time.perf_counter()
-            a = act(oenv, ap, g)                     # dense: all 2N^2 + NR padded edges, like the reference
+            act(oenv, ap, g)
+            timings[c] = time.perf_counter() - t0
+        cores = min(timings, key=timings.get)
+        torch.set_num_threads(cores)
+        times = []
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            a = act(oenv, ap, g)                     # dense: all padded edges, like the reference
             g, r, c = oenv.step(g, a)
-            dt = time.perf_counter() - t0
-            if s > 0 or steps == 0:
-                times.append(dt)
-    sec = sum(times) / max(len(times), 1)
-    # same step with the masked edges dropped first (the CUDA path's formulation) -> separates the algorithmic
-    # (dense -> sparse) factor from the hardware (CPU -> B200) one, BASELINE.md section 3
-    sparse_times = []
-    with torch.no_grad():
+            if s >= warmup:
+                times.append(time.perf_counter() - t0)
+        sec = sum(times) / max(len(times), 1)
+        # same step with the masked edges dropped first (the CUDA path's formulation) -> separates the algorithmic
+        # (dense -> sparse) factor from the hardware (CPU -> B200) one, BASELINE.md section 3
+        sparse_times = []
         for s in range(2):
             t0 = time.perf_counter()
             gs = oenv.sparsify(g)
@@ -392,28 +486,33 @@ def cpu_baseline(args, steps: int = 1, verbose: bool = False):
             if s > 0:
                 sparse_times.append(time.perf_counter() - t0)
     sec_sparse = sum(sparse_times) / max(len(sparse_times), 1)
+    n_dense = g.edges.shape[0] if hasattr(g, "edges") else 0
     return {"value": N / sec, "unit": "env-steps/s", "cores": cores, "kind": "port", "sparse_value": N / sec_sparse,
-            "sample": f"1 env x n={N} x {len(times)} env-step(s) after 1 warm-up step, dense reference formulation "
-                      f"({2 * N * N + N * N_RAYS} padded edges/graph), torch-CPU fp32; {sec:.2f} s per env-step; "
-                      f"{cores} of {ncpu} host threads (fastest of {cands} on a n=128 probe)",
-            "sec_per_env_step": sec}
+            "sample": f"1 env x n={N} x {len(times)} timed env-step(s) after {warmup} warm-up step(s) of the restated "
+                      f"reference (oracle/, dense padded formulation, torch-CPU fp32; NOT the JAX code); {sec:.2f} s per "
+                      f"env-step; {cores} of {ncpu} host threads (fastest of {cands} on a dense forward at n={N}: "
+                      + ", ".join(f"{c}: {timings[c]:.2f} s" for c in cands) + ")",
+            "sec_per_env_step": sec, "steps_run": len(times)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from helpers import probe_reference_stack
+    cfg = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     t0 = time.perf_counter()
-    cpu = cpu_baseline(args, steps=max(1, min(args.steps, 3)))
+    # every "step" of this arm is ONE env-step of ONE env (bounded sample); W warm-up + exactly K timed steps are run
+    cpu = cpu_baseline(cfg, steps=args.steps, warmup=args.warmup)
     value = cpu["value"]
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["sec_per_env_step"] * 1e3,
+    out = {"impl": "reference", "metric": metric_name(cfg), "value": value, "unit": "env-steps/s", "n_gpus": world,
+           "steps": cpu["steps_run"], "warmup": args.warmup, "ms_per_step": cpu["sec_per_env_step"] * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{ENV_ID} n={N_AGENTS} obs={N_OBS} n_rays={N_RAYS} area={AREA} (configs[2]); "
-                                  "bounded sample: 1 env, per step 1 env-step",
-                      "note": "JAX/Flax/jraph are not installable in this image: the arm is the restated "
-                              "reference (oracle, dense formulation), not the JAX code"},
+           "config": {"workload": f"{cfg['env']} n={cfg['N']} obs={cfg['obs']} n_rays={cfg['rays']} area={cfg['area']} "
+                                  f"({cfg['name']}); bounded sample: per step ONE env-step of ONE env",
+                      "arm": "restated reference (CPU oracle port, dense formulation) -- not the JAX code",
+                      "reference_stack_probe": probe_reference_stack()},
            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "sparse_value")},
            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
@@ -426,7 +525,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
+    ap.add_argument("--envs-per-gpu", type=int, default=None,
+                    help="default: the config's envs / its GPU count (16, 4, 8)")
     ap.add_argument("--T", type=int, default=T_STEPS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")

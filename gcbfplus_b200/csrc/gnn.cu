@@ -304,7 +304,10 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
                               const float* agent, const float* goal, const float* hits, const int32_t* row_start,
                               const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src,
                               const int32_t* counters, int clip_all, float* out, float* ws, cudaStream_t st,
-                              float* z_out = nullptr, int* z_parts = nullptr, int32_t* zero_counter = nullptr) {
+                              float* z_out = nullptr, int* z_parts = nullptr, int32_t* zero_counter = nullptr,
+                              int select = 0xF) {
+    // select (gcbf_rollout_step_select, measurement hook): bit 0 edge message (+ chained gate) kernel, bit 1 attention
+    // aggregate, bit 2 update layer, bit 3 folded update/head layer; a cleared bit skips that launch
     // z_out != nullptr (rollout step): instead of `out`, write the output layer's pre-activation partial sums
     // z[part][A][4] (no bias, no tanh) for the policy tail fused into graph_build_kernel
     const int ed = env_ed(d->env_kind);
@@ -327,7 +330,8 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
         // {update/head folded layer (+ output layer) below}
         // GCBF_CHAIN=0: gate layer as its own GEMM launch (A/B measurements)
         static const bool chain_on = [] { const char* e = getenv("GCBF_CHAIN"); return !(e && e[0] == '0'); }();
-        if (chain_on) {
+        if (!(select & 1)) {
+        } else if (chain_on) {
             tc::ChainArgs ch;
             ch.bias_g = P + L.b[L_ATT0];
             ch.avec = blob + I.a23;
@@ -346,15 +350,15 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
         // (measured: producing the aggregate inside the update GEMM (tc::launch_attn_upd) is slower than the
         //  separate warp-per-receiver kernel + TMA-fed GEMM: 36.6 us vs 13.2 + 11.7 us -- its N-split repeats
         //  the aggregation and the per-thread MSG gathers are latency-bound; the edge producer above is a win)
-        {
+        if (select & 2) {
             const int grid = min((A + 7) / 8, 8 * nsm);   // 8 x 256 threads per SM: one receiver per warp in flight (latency-bound kernel)
             attn_aggregate_kernel<<<grid, 256, 0, st>>>(A, cap, nullptr, ws + W.msg, blob + I.a23, blob + I.c23, row_start,
                                                         row_deg, ws + W.att, ws + W.ag, zero_counter);
             count_launch();
             if ((rc = check_launch("attn_aggregate_kernel"))) return rc;
         }
-        if ((rc = gemm(EPI_BIAS_RELU, ws + W.ag, P + L.w[L_UPD0] + 3 * 256, I.t_u1, 128, 256, P + L.b[L_UPD0],
-                       P + L.w[L_UPD0] + 2 * 256, ws + W.v1, ra))) return rc;
+        if ((select & 4) && (rc = gemm(EPI_BIAS_RELU, ws + W.ag, P + L.w[L_UPD0] + 3 * 256, I.t_u1, 128, 256, P + L.b[L_UPD0],
+                                       P + L.w[L_UPD0] + 2 * 256, ws + W.v1, ra))) return rc;
     } else {
         {
             const int grid = min((cap + 7) / 8, 4 * nsm);
@@ -379,6 +383,8 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
     }
     if (z_out != nullptr) {
         if (use_tc) {   // last hidden layer + output layer partial sums in the GEMM epilogue (h1 never leaves the SM)
+            *z_parts = (2 * ((A + tc::BM - 1) / tc::BM) <= sm_count()) ? 2 : 1;
+            if (!(select & 8)) return 0;
             return tc::launch_gemm_tc(EPI_RELU_DOTN, false, ws + W.v1, blob + I.t_uh, blob + I.t_uh + 256 * 256, blob + I.buh,
                                       nullptr, z_out, blob + I.ho, ra, 256, 256, st, out_dim, z_parts);
         }
@@ -446,13 +452,13 @@ int32_t graph_build_impl(const gcbf_env_desc* desc, const float* agent, const fl
                          int32_t* counters, int32_t flags, const TailArgs& tail, float* reward, float* cost, void* stream);
 }  // namespace gcbf
 
-extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step(
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step_select(
     const gcbf_env_desc* desc, const float* actor_params, const float* infer_blob, int32_t use_tensor_cores,
     const float* agent, const float* goal, const float* obstacles, const float* ray_table, const float* hits,
     const int32_t* row_start, const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src,
     const int32_t* counters, float* action, float* next_agent, float* next_hits, int32_t* next_row_start,
     int32_t* next_row_deg, int32_t* next_edge_recv, int32_t* next_edge_src, int32_t* next_counters, float* reward,
-    float* cost, float* workspace, int64_t workspace_floats, void* stream) {
+    float* cost, float* workspace, int64_t workspace_floats, int32_t select, void* stream) {
     GCBF_REQUIRE(desc && actor_params && infer_blob && agent && goal && ray_table && hits && row_start && row_deg &&
                      edge_recv && edge_src && counters && action && next_agent && next_hits && next_row_start &&
                      next_row_deg && next_edge_recv && next_edge_src && next_counters && reward && cost && workspace,
@@ -481,8 +487,11 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step(
     //  kernel-to-kernel gap is already ~1 us) and it was NOT safe as written -- a dependent kernel that starts early
     //  can keep L1 / read-only-cache lines of buffers its predecessor rewrites (DubinsCar rollouts became
     //  non-deterministic with only the edge-message GEMM launched that way).  Removed.)
+    GCBF_REQUIRE(select == GCBF_STEP_ALL || use_tensor_cores, "gcbf_rollout_step_select: partial steps need the tensor-core path");
     if ((rc = gnn_infer_impl(desc, nu, actor_params, infer_blob, use_tensor_cores, agent, goal, hits, row_start, row_deg,
-                             edge_recv, edge_src, counters, 0, nullptr, workspace, st, z, &parts, next_counters))) return rc;
+                             edge_recv, edge_src, counters, 0, nullptr, workspace, st, z, &parts, next_counters,
+                             select & 0xF))) return rc;
+    if (!(select & 16)) return 0;
     TailArgs tl;
     tl.z = z;
     tl.parts = parts;
@@ -495,8 +504,22 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step(
     tl.edge_src_prev = edge_src;
     tl.action = action;
     tl.next_agent = next_agent;
+    // the attention kernel cleared the next edge counter; a partial step without it lets the build clear it itself
     return graph_build_impl(desc, nullptr, obstacles, ray_table, next_hits, next_row_start, next_row_deg, next_edge_recv,
-                            next_edge_src, next_counters, 1 | 4, tl, reward, cost, stream);
+                            next_edge_src, next_counters, 1 | ((select & 2) ? 4 : 0), tl, reward, cost, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_step(
+    const gcbf_env_desc* desc, const float* actor_params, const float* infer_blob, int32_t use_tensor_cores,
+    const float* agent, const float* goal, const float* obstacles, const float* ray_table, const float* hits,
+    const int32_t* row_start, const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src,
+    const int32_t* counters, float* action, float* next_agent, float* next_hits, int32_t* next_row_start,
+    int32_t* next_row_deg, int32_t* next_edge_recv, int32_t* next_edge_src, int32_t* next_counters, float* reward,
+    float* cost, float* workspace, int64_t workspace_floats, void* stream) {
+    return gcbf_rollout_step_select(desc, actor_params, infer_blob, use_tensor_cores, agent, goal, obstacles, ray_table,
+                                    hits, row_start, row_deg, edge_recv, edge_src, counters, action, next_agent, next_hits,
+                                    next_row_start, next_row_deg, next_edge_recv, next_edge_src, next_counters, reward, cost,
+                                    workspace, workspace_floats, GCBF_STEP_ALL, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t gcbf_rollout_workspace_floats(const gcbf_env_desc* desc) {

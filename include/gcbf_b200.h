@@ -207,6 +207,21 @@ int32_t gcbf_rollout_step(const gcbf_env_desc* desc, const float* actor_params, 
                           int32_t* next_counters, float* reward, float* cost, float* workspace,
                           int64_t workspace_floats, void* stream);
 
+/* Measurement hook: the same step with only the launches whose bit is set in `select` enqueued (bench.py times every
+ * kernel of the step alone, on the buffers a full step left behind, to find the dominant one and its roofline):
+ * bit 0 edge features + message layer + chained gate layer, bit 1 segment softmax + aggregate, bit 2 update layer,
+ * bit 3 folded update/head layer, bit 4 policy tail + graph build of the next state.  GCBF_STEP_ALL = gcbf_rollout_step. */
+#define GCBF_STEP_ALL 31
+int32_t gcbf_rollout_step_select(const gcbf_env_desc* desc, const float* actor_params, const float* infer_blob,
+                                 int32_t use_tensor_cores, const float* agent, const float* goal,
+                                 const float* obstacles, const float* ray_table, const float* hits,
+                                 const int32_t* row_start, const int32_t* row_deg, const int32_t* edge_recv,
+                                 const int32_t* edge_src, const int32_t* counters, float* action,
+                                 float* next_agent, float* next_hits, int32_t* next_row_start,
+                                 int32_t* next_row_deg, int32_t* next_edge_recv, int32_t* next_edge_src,
+                                 int32_t* next_counters, float* reward, float* cost, float* workspace,
+                                 int64_t workspace_floats, int32_t select, void* stream);
+
 /* ---------------------------------------------------------------- labels / masks (a9)
  * Replaces env.unsafe_mask / collision_mask / finish_mask / safe_mask
  * (env/double_integrator.py:356-440 and twins).  Any output pointer may be NULL.
