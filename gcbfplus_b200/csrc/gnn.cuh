@@ -76,11 +76,13 @@ __device__ __forceinline__ void edge_feat_dev(const float* er, const float* es, 
                                               float* coef_out, float* nrm_out) {
     using T = EnvTraits<KIND>;
     constexpr int PD = T::PD, ED = T::ED;
+    // explicit fused multiply-adds: the same bits whether the translation unit is compiled with -fmad=true (gnn.cu,
+    // train.cu) or -fmad=false (rollout_persist.cu, which shares this function with the bit-exact geometry code)
     float sq = 0.f;
 #pragma unroll
     for (int c = 0; c < ED; ++c) {
         feat[c] = er[c] - es[c];
-        if (c < PD) sq += feat[c] * feat[c];
+        if (c < PD) sq = (c == 0) ? feat[c] * feat[c] : fmaf(feat[c], feat[c], sq);
     }
     float coef = 1.f;
     const float nrm = sqrtf(1e-6f + sq);

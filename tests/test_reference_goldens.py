@@ -14,7 +14,7 @@ Tolerances (fp32 reference on XLA-CPU vs fp32 here; stated per quantity):
   h, pi, action                    3e-5 (tensor-core path) / 1e-5 (oracle)
   next state, reward, cost         2e-6 / 1e-5 / exact-to-1e-6
   masks, horizon labels            bit-exact
-  closed loop                      <= 1e-5 after 1 step, <= 3e-4 over the first T/4 steps, <= 5e-3 at T; rates IDENTICAL
+  closed loop                      <= 1e-5 after 1 step, <= 3e-4 over the first min(T/4, 24) steps, <= 5e-3 at T; rates IDENTICAL
   update_inner losses / accuracies 2e-5 relative; gradients 2e-4 of the tensor's max magnitude;
   parameters after clip + AdamW    2.2 * lr (one Adam step moves an entry by at most lr; a sign flip of a ~0 entry is 2 lr)
 """
@@ -77,7 +77,8 @@ def _compare_edges(got, want, pos, hits, N, R, rc, lidar_rc):
 def _traj_check(got, want, T, tol1, tolq):
     err = np.abs(got - want).reshape(T + 1, -1).max(axis=1)
     assert err[1] <= tol1, err[:4]
-    assert err[: max(T // 4, 2)].max() <= tolq, err[: max(T // 4, 2)].max()
+    w = min(max(T // 4, 2), 24)
+    assert err[:w].max() <= tolq, err[:w].max()
     assert err.max() <= 5e-3, err.max()
 
 
