@@ -21,6 +21,7 @@ UNITS = {  # translation unit -> extra flags
     "api.cu": [],
     "geometry.cu": ["-fmad=false"],
     "gnn.cu": [],
+    "rollout_persist.cu": ["-fmad=false"],
     "train.cu": [],
 }
 

@@ -221,31 +221,6 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_gemm_tn_tc(const 
 // =====================================================================================================
 namespace gcbf {
 
-struct InferLayout {
-    int w23, b23, a23, c23, uh, buh, ho, bho;          // folded fp32 weights
-    int t_w23, t_a1, t_u1, t_uh;                       // transposed tf32 planes: hi at t_x, lo at t_x + size
-    int total;
-};
-static InferLayout make_infer_layout(int out_dim) {
-    InferLayout I;
-    int o = 0;
-    auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-    I.w23 = take(256 * 128);
-    I.b23 = take(128);
-    I.a23 = take(128);
-    I.c23 = take(4);
-    I.uh = take(256 * 256);
-    I.buh = take(256);
-    I.ho = take(256 * out_dim);
-    I.bho = take(4);
-    I.t_w23 = take(2 * 128 * 256);
-    I.t_a1 = take(2 * 128 * 128);
-    I.t_u1 = take(2 * 256 * 128);
-    I.t_uh = take(2 * 256 * 256);
-    I.total = o;
-    return I;
-}
-
 // C[m,n] = A[m,k] @ B[k,n] (+ bias[n]); one thread per output, fp32 sequential accumulation (setup work).
 static __global__ void small_matmul_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                            const float* __restrict__ bias, float* __restrict__ C, int m, int k, int n) {

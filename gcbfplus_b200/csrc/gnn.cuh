@@ -36,6 +36,32 @@ inline GnnWs make_ws(int64_t cap, int64_t A) {
     return w;
 }
 
+// Folded inference weights (gcbf_prepare_infer, gnn.cu): float offsets inside the blob.
+struct InferLayout {
+    int w23, b23, a23, c23, uh, buh, ho, bho;          // folded fp32 weights
+    int t_w23, t_a1, t_u1, t_uh;                       // transposed tf32 planes: hi at t_x, lo at t_x + size
+    int total;
+};
+inline InferLayout make_infer_layout(int out_dim) {
+    InferLayout I;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+    I.w23 = take(256 * 128);
+    I.b23 = take(128);
+    I.a23 = take(128);
+    I.c23 = take(4);
+    I.uh = take(256 * 256);
+    I.buh = take(256);
+    I.ho = take(256 * out_dim);
+    I.bho = take(4);
+    I.t_w23 = take(2 * 128 * 256);
+    I.t_a1 = take(2 * 128 * 128);
+    I.t_u1 = take(2 * 256 * 128);
+    I.t_uh = take(2 * 256 * 256);
+    I.total = o;
+    return I;
+}
+
 // edge_state (dubins_car.py:260-264: (x, y, v cos th, v sin th); identity otherwise)
 template <int KIND>
 __device__ __forceinline__ void edge_state_dev(const float* s, float* es) {

@@ -1,11 +1,17 @@
 """Batched closed-loop rollout -- replaces jit(vmap(rollout)) of gcbfplus/trainer/utils.py:25-55
-and trainer/trainer.py:81-87.  One CUDA graph holds the whole T-step loop:
-per step {actor GNN forward -> act + clip + Euler + reward/cost -> LiDAR + neighbour lists},
-3 C-ABI calls / 14 kernel launches, no host sync inside the loop.
+and trainer/trainer.py:81-87.
+
+Two device paths with the same arithmetic (bit-identical results, tests/test_gpu_rollout.py):
+* persistent (default where supported: 2-D environments, n <= 512): ONE kernel launch for the whole T-step rollout, one
+  thread-block cluster per environment looping over the steps (csrc/rollout_persist.cu);
+* 5-launch env-step (gcbf_rollout_step), the whole T-step loop captured in one CUDA graph: LinearDrone, n > 512,
+  GCBF_PERSISTENT=0, the u_ref policy.
+No host sync inside the loop on either path.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -42,7 +48,8 @@ class _Chain:
 
 class RolloutEngine:
     def __init__(self, env, n_envs: int, T: Optional[int] = None, n_obs: Optional[int] = None,
-                 use_cuda_graph: bool = True, policy: str = "actor", n_chains: Optional[int] = None):
+                 use_cuda_graph: bool = True, policy: str = "actor", n_chains: Optional[int] = None,
+                 persistent: Optional[bool] = None):
         """policy: 'actor' (a = 2 pi + u_ref, algo.step) or 'u_ref' (test.py --u-ref).
         n_chains: the environments are split into independent chains that run as parallel branches of
         the CUDA graph (each per-step kernel is latency-bound and fills a fraction of the 148 SMs, so
@@ -77,6 +84,19 @@ class RolloutEngine:
         # folded inference weights (gcbf_prepare_infer), rebuilt by set_params()
         self.infer_blob = torch.zeros(int(env.lib.gcbf_infer_count(env.edge_dim, nu)), dtype=f32, device=dev)
         self.use_tc = 1 if _lib.USE_TC else 0
+        # persistent single-launch rollout (csrc/rollout_persist.cu) where the library supports the configuration
+        ok = (policy == "actor" and self.use_tc and len(self.chains) == 1 and
+              bool(env.lib.gcbf_rollout_persistent_supported(C.byref(self.desc))))
+        if persistent is None:
+            persistent = ok and os.environ.get("GCBF_PERSISTENT", "1") != "0"
+        if persistent and not ok:
+            raise ValueError("persistent rollout unsupported for this configuration (2-D env, n <= 512, tensor-core path, "
+                             "actor policy, one chain)")
+        self.persistent = bool(persistent)
+        self._pws = None
+        if self.persistent:
+            n = env.lib.gcbf_rollout_persistent_workspace_floats(C.byref(self.desc))
+            self._pws = torch.empty(int(n), dtype=f32, device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_run = 0
         self._obstacle_obj = None
@@ -127,9 +147,21 @@ class RolloutEngine:
         for t in range(self.T):
             self._step(ch, t, stream)
 
+    def _enqueue_persistent(self, n_steps: int, stream: int) -> None:
+        env, ch = self.env, self.chains[0]
+        rc = env.lib.gcbf_rollout_persistent(
+            C.byref(ch.desc), int(n_steps), self.params_buf.data_ptr(), self.infer_blob.data_ptr(), self.goal.data_ptr(),
+            self.obstacles.data_ptr() if self.O > 0 else None, env.ray_table.data_ptr(), self.agent.data_ptr(),
+            self.hits.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr(), self.costs.data_ptr(),
+            ch.counters.data_ptr(), self._pws.data_ptr(), self._pws.numel(), stream)
+        _lib.check(rc, "gcbf_rollout_persistent")
+
     def _enqueue_all(self) -> None:
         dev = self.env.device
         main = torch.cuda.current_stream(dev)
+        if self.persistent:
+            self._enqueue_persistent(self.T, main.cuda_stream)
+            return
         if len(self.chains) == 1:
             self._enqueue_chain(self.chains[0], main.cuda_stream)
             return
@@ -168,9 +200,13 @@ class RolloutEngine:
             if self._graph is None:
                 # warm-up outside capture (lazy module load, function attributes)
                 st = torch.cuda.current_stream(dev).cuda_stream
-                for ch in self.chains:
-                    self._build(ch, 0, st)
-                    self._step(ch, 0, st)
+                if self.persistent:
+                    self._enqueue_persistent(min(self.T, 1), st)
+                    self.chains[0].counters.zero_()
+                else:
+                    for ch in self.chains:
+                        self._build(ch, 0, st)
+                        self._step(ch, 0, st)
                 torch.cuda.synchronize(dev)
                 g = torch.cuda.CUDAGraph()
                 n0 = lib.gcbf_launch_count()

@@ -222,6 +222,25 @@ int32_t gcbf_rollout_step_select(const gcbf_env_desc* desc, const float* actor_p
                                  int32_t* next_counters, float* reward, float* cost, float* workspace,
                                  int64_t workspace_floats, int32_t select, void* stream);
 
+/* ---------------------------------------------------------------- persistent rollout (a8 whole scan)
+ * The WHOLE rollout() of gcbfplus/trainer/utils.py:25-55 (reset excluded) in ONE kernel launch: one thread-block cluster
+ * per environment loops over the n_steps env-steps; the kernel boundaries of gcbf_rollout_step become cluster barriers,
+ * pipeline / TMEM / table setup is paid once per rollout (csrc/rollout_persist.cu).  Same arithmetic as
+ * gcbf_rollout_step -> same bits.  Supported: SingleIntegrator / DoubleIntegrator / DubinsCar, n_agents <= 512,
+ * n_obs <= 32, one obstacle set per environment, desc->edge_cap >= n_graphs * n_agents (it is split evenly over the
+ * environments); gcbf_rollout_persistent_supported() tells, callers fall back to gcbf_rollout_step otherwise.
+ *   agent_rec [n_steps+1, G, N, sd]: slice 0 = initial states (input), slices 1.. written;  hits_rec [n_steps+1, G, N, R, pd]
+ *   (all slices written, slice 0 = LiDAR of the initial states);  actions_rec [n_steps, G, N, nu];  rewards / costs
+ *   [n_steps, G];  counters [n_steps+1, 4] (zeroed by the caller): [t][0] += edges of the graphs of state t, [t][1] |= overflow.
+ *   workspace: gcbf_rollout_persistent_workspace_floats(desc) floats, 256-byte aligned. */
+int64_t gcbf_rollout_persistent_workspace_floats(const gcbf_env_desc* desc);
+int32_t gcbf_rollout_persistent_supported(const gcbf_env_desc* desc);
+int32_t gcbf_rollout_persistent(const gcbf_env_desc* desc, int32_t n_steps, const float* actor_params,
+                                const float* infer_blob, const float* goal, const float* obstacles,
+                                const float* ray_table, float* agent_rec, float* hits_rec, float* actions_rec,
+                                float* rewards, float* costs, int32_t* counters, float* workspace,
+                                int64_t workspace_floats, void* stream);
+
 /* ---------------------------------------------------------------- labels / masks (a9)
  * Replaces env.unsafe_mask / collision_mask / finish_mask / safe_mask
  * (env/double_integrator.py:356-440 and twins).  Any output pointer may be NULL.

@@ -128,3 +128,33 @@ def test_chained_gate_gemm_is_bit_identical_to_separate_launch():
     assert out.returncode == 0, out.stderr[-2000:]
     other = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0].split()[1]
     assert other == _rollout_digest()
+
+
+@pytest.mark.parametrize("env_id,N,E,area,n_obs,T", [("DoubleIntegrator", 48, 3, 3.0, 6, 12), ("SingleIntegrator", 8, 16, 4.0, 0, 40),
+                                                      ("DubinsCar", 12, 2, 2.0, 4, 24), ("DoubleIntegrator", 200, 2, 6.0, 8, 8),
+                                                      ("DoubleIntegrator", 130, 1, 4.0, 3, 6),
+                                                      ("DoubleIntegrator", 512, 3, 16.0, 8, 5)])
+def test_persistent_rollout_is_bit_identical_to_5_launch_path(env_id, N, E, area, n_obs, T):
+    """The single-launch persistent rollout (one thread-block cluster per environment, csrc/rollout_persist.cu) against
+    the 5-launch env-step path: same operand splits, MMA order, epilogues and reduction orders -> the same bits for
+    states, LiDAR hits, actions, rewards, costs and per-step edge counts (dense scenes: several edge tiles per CTA,
+    ragged last tiles, N not a multiple of the cluster size)."""
+    from gcbfplus_b200.trainer.rollout import RolloutEngine
+    env, g0 = _reset_scene(env_id, N, E, area, n_obs, seed=21)
+    algo = product_algo(env, env_id)
+    outs = []
+    for persistent in (True, False):
+        eng = RolloutEngine(env, E, T=T, n_obs=n_obs, persistent=persistent)
+        assert eng.persistent == persistent
+        eng.set_params(algo.actor_params)
+        eng.set_initial(g0.agent, g0.goal, g0.obstacle)
+        eng.run()
+        eng.run()                                   # replay of the captured launch
+        torch.cuda.synchronize()
+        outs.append({k: getattr(eng, k).clone() for k in ("agent", "hits", "actions", "rewards", "costs")})
+        outs[-1]["n_edges"] = eng.counters[:, 0].clone()
+        assert eng.launches_per_run == (1 if persistent else 1 + 5 * T)
+    for k in outs[0]:
+        a, b = outs[0][k], outs[1][k]
+        same = torch.equal(a, b) or bool(((a == b) | (torch.isnan(a.float()) & torch.isnan(b.float()))).all())
+        assert same, (k, float((a.float() - b.float()).abs().nan_to_num().max()))
