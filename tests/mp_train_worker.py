@@ -56,9 +56,31 @@ def main(out_path):
     torch.distributed.all_reduce(pmax, op=torch.distributed.ReduceOp.MAX)
     torch.distributed.all_reduce(pmin, op=torch.distributed.ReduceOp.MIN)
     same = bool(torch.equal(pmax, pmin))
+    # --- the captured optimizer step (algo/train.py MinibatchRunner): gather + graph build + train step + the packed
+    # all-reduce INSIDE one CUDA graph, label counts all-reduced once for the "epoch"; 4 steps (eager warm-up, capture,
+    # 2 replays) must leave identical parameters on every rank
+    batch = {"agent": full.agent.contiguous(), "goal": full.goal.contiguous(), "hits": full.hits.contiguous(),
+             "safe": safe.to(torch.uint8).contiguous(), "unsafe": unsafe.to(torch.uint8).contiguous()}
+    mb = B // world
+    per_graph = full.row_deg.reshape(B, N).sum(dim=1)
+    runner = T.MinibatchRunner(algo, batch, mb, int(per_graph.max().item()) * mb, u_qp.contiguous())
+    # every rank trains on its shard [lo, hi) of the global minibatch; global counts = sum over the ranks' shards
+    den = T._minibatch_counts(batch, torch.arange(B, device=dev), np.array([lo, hi]))
+    torch.distributed.all_reduce(den)
+    before = algo.cbf_params.flat.clone()
+    for _ in range(4):
+        runner.run(torch.arange(lo, hi, device=dev), den[0])
+    torch.cuda.synchronize()
+    runner.graph.check_overflow()
+    p2 = torch.cat([algo.cbf_params.flat, algo.actor_net_params.flat])
+    p2max, p2min = p2.clone(), p2.clone()
+    torch.distributed.all_reduce(p2max, op=torch.distributed.ReduceOp.MAX)
+    torch.distributed.all_reduce(p2min, op=torch.distributed.ReduceOp.MIN)
+    graph_ok = bool(torch.equal(p2max, p2min)) and bool(torch.isfinite(p2).all()) and not torch.equal(before, algo.cbf_params.flat)
+    graph_ok = graph_ok and runner.cuda_graph is not None
     if rank == 0:
-        json.dump({"world": world, "grad_err": err, "grad_max": gmax, "stats_err": stats_err, "params_identical": same},
-                  open(out_path, "w"))
+        json.dump({"world": world, "grad_err": err, "grad_max": gmax, "stats_err": stats_err, "params_identical": same,
+                   "captured_step_ok": graph_ok}, open(out_path, "w"))
     torch.distributed.destroy_process_group()
 
 

@@ -34,3 +34,4 @@ def test_sharded_train_step_matches_single_gpu(tmp_path):
     assert res["world"] == n and res["params_identical"]
     assert res["grad_err"] <= 1e-4 * res["grad_max"] + 1e-8, res
     assert res["stats_err"] <= 1e-3, res
+    assert res["captured_step_ok"], res       # CUDA-graph optimizer step with the NCCL all-reduce captured inside

@@ -44,37 +44,57 @@ def test_gradients_match_oracle_autograd(env_id, N, B, area, n_obs, pretrained, 
     torch.cuda.synchronize()
     graph.check_overflow()
     info = read_info(algo)
-    # ---- oracle (float64)
-    oenv = oracle_env(env_id, N, area, n_obs, dtype=torch.float64)
-    cp = to_torch(algo.cbf_params.to_tree(), torch.float64, requires_grad=True)
-    ap = to_torch(algo.actor_net_params.to_tree(), torch.float64, requires_grad=True)
+    # ---- oracle: float64 autograd of the restated loss; float32 evaluated lazily for ReLU-kink ties (below)
     packed = pobs.packed.cpu().numpy()
-    graphs = [oenv.sparsify(oenv.get_graph(torch.from_numpy(agent[g]).double(), torch.from_numpy(goal[g]).double(),
-                                           oracle_obstacles(packed[g], torch.float64))) for g in range(B)]
-    total, oinfo = gcbf_plus_loss(oenv, cp, ap, graphs, safe.cpu(), unsafe.cpu(), u_qp.cpu().double(), alpha=algo.alpha,
-                                  eps=algo.eps, coef_action=algo.loss_action_coef, coef_unsafe=algo.loss_unsafe_coef,
-                                  coef_safe=algo.loss_safe_coef, coef_h_dot=algo.loss_h_dot_coef)
+
+    def oracle_grads(dt):
+        oenv = oracle_env(env_id, N, area, n_obs, dtype=dt)
+        cp = to_torch(algo.cbf_params.to_tree(), dt, requires_grad=True)
+        ap = to_torch(algo.actor_net_params.to_tree(), dt, requires_grad=True)
+        graphs = [oenv.sparsify(oenv.get_graph(torch.from_numpy(agent[g]).to(dt), torch.from_numpy(goal[g]).to(dt),
+                                               oracle_obstacles(packed[g], dt))) for g in range(B)]
+        total, oinfo = gcbf_plus_loss(oenv, cp, ap, graphs, safe.cpu(), unsafe.cpu(), u_qp.cpu().to(dt), alpha=algo.alpha,
+                                      eps=algo.eps, coef_action=algo.loss_action_coef, coef_unsafe=algo.loss_unsafe_coef,
+                                      coef_safe=algo.loss_safe_coef, coef_h_dot=algo.loss_h_dot_coef)
+        names_c, names_a = list(cp), list(ap)
+        gs = torch.autograd.grad(total, [cp[k] for k in names_c] + [ap[k] for k in names_a], allow_unused=True)
+        gs = [g.double() if g is not None else None for g in gs]
+        return oinfo, names_c, names_a, gs
+
+    oinfo, names_c, names_a, gs = oracle_grads(torch.float64)
     for k in ("loss/action", "loss/unsafe", "loss/safe", "loss/h_dot", "loss/total", "acc/unsafe", "acc/safe",
               "acc/h_dot", "acc/unsafe_data_ratio"):
         assert abs(info[k] - float(oinfo[k])) <= 2e-5 * max(1.0, abs(float(oinfo[k]))), (k, info[k], float(oinfo[k]))
-    names_c, names_a = list(cp), list(ap)
-    gs = torch.autograd.grad(total, [cp[k] for k in names_c] + [ap[k] for k in names_a], allow_unused=True)
     from gcbfplus_b200.algo.params import NetParams
     any_nonzero = False
-    for net, names, grads, flat in (("cbf", names_c, gs[:len(names_c)], ts.grad_cbf),
-                                    ("actor", names_a, gs[len(names_c):], ts.grad_act)):
+    gs32 = None          # float32 evaluation of the same oracle, computed only if a tensor disagrees with float64
+    n_kink = 0
+    for net, names, lo, flat in (("cbf", names_c, 0, ts.grad_cbf), ("actor", names_a, len(names_c), ts.grad_act)):
+        grads = gs[lo: lo + len(names)]
         proto = algo.cbf_params if net == "cbf" else algo.actor_net_params
         tmp = NetParams(proto.edge_dim, proto.out_dim, proto.kind, device="cuda")
         tmp.flat.copy_(flat)
         got = to_torch(tmp.to_tree(), torch.float64)
         gmax = max(float(g.abs().max()) for g in grads if g is not None)
         any_nonzero = any_nonzero or gmax > 0      # a converged pretrained CBF can have exactly zero loss terms
-        for k, g in zip(names, grads):
-            want = g if g is not None else torch.zeros_like(got[k])
+        for i, k in enumerate(names):
+            want = grads[i] if grads[i] is not None else torch.zeros_like(got[k])
             err = float((got[k] - want).abs().max())
             scale = max(float(want.abs().max()), 1e-3 * gmax)
-            assert err <= 2e-4 * scale + 1e-9, (net, k, err, scale)
+            if err <= 2e-4 * scale + 1e-9:
+                continue
+            # ReLU kinks: with ~1e6 hidden units per pass (N = 64: 2 700 edges x 256 x 3 passes) a few pre-activations
+            # sit within rounding of 0, where the float64 and the float32 evaluation of the SAME restated loss take
+            # different one-sided derivatives (measured: they differ by 4e-3 of this tensor, and the CUDA result equals
+            # the float32 one to 7 digits).  A tensor that misses float64 must then match the float32 oracle.
+            if gs32 is None:
+                gs32 = oracle_grads(torch.float32)[3]
+            want32 = gs32[lo + i] if gs32[lo + i] is not None else torch.zeros_like(got[k])
+            err32 = float((got[k] - want32).abs().max())
+            assert err32 <= 2e-4 * scale + 1e-9, (net, k, err, err32, scale)
+            n_kink += 1
     assert any_nonzero
+    assert n_kink <= 4, n_kink          # kink ties are rare: a handful of the 24 tensors at most
 
 
 def test_clip_adamw_and_polyak_match_oracle():
