@@ -56,6 +56,7 @@ struct PArgs {
     // per-environment scratch (L2)
     int32_t *row_start, *row_deg, *edge_recv, *edge_src; // [2][...] double-buffered lists
     float *msg, *logit, *ag, *v1, *z;
+    unsigned long long* prof;                            // optional [T + 1][8] %globaltimer stamps of cluster 0 / CTA 0 (ns)
 };
 
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
@@ -74,6 +75,11 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
             : "memory");
         if (!done && clock64() - t0 > 4000000000ll) __trap();     // ~2 s at 1.9 GHz
     }
+}
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ void cluster_sync_all() {
     __syncwarp();
@@ -207,6 +213,9 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
         const int32_t* rd_t = P.row_deg + (size_t)b * A_tot;
         const int32_t* er_t = P.edge_recv + (size_t)b * E * cap;
         const int32_t* es_t = P.edge_src + (size_t)b * E * cap;
+        const bool stamp = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
+        unsigned long long* pr = P.prof + (size_t)(t + 1) * 8;
+        if (stamp) pr[0] = gtime();
         if (t >= 0) {
             // ============================================================ phase E: edge tiles
             const int n_tiles = (M_cur + BM - 1) / BM;
@@ -379,6 +388,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
             ne += my_tiles;
             n0 += my_tiles;
             cluster_sync_all();
+            if (stamp) pr[1] = gtime();
 
             // ============================================================ phase A: segment softmax + aggregate
             for (int il = a_lo + warp; il < a_hi; il += PW) {
@@ -434,6 +444,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
             }
             fence_async_global();          // generic-proxy writes of AG -> TMA (async proxy) reads in phase U1
             cluster_sync_all();
+            if (stamp) pr[2] = gtime();
 
             // ============================================================ phases U1 / U2: agent-side GEMMs
             const int n_items = ((N + BM - 1) / BM) * 2;               // (agent tile, 128-column half)
@@ -561,6 +572,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 n0 += my_items;
                 if (ph2 == 0) fence_async_global();   // V1 rows (generic stores) -> TMA reads of phase U2
                 cluster_sync_all();
+                if (stamp) pr[3 + ph2] = gtime();
             }
         }
 
@@ -659,6 +671,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 }
             }
             __syncthreads();
+            if (stamp) pr[5] = gtime();
 
             // ---- LiDAR + neighbour bits for this CTA's agents (warp per agent, PW agents per round)
             const int n_slots = a_hi - a_lo;
@@ -795,6 +808,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 }
             }
             cluster_sync_all();
+            if (stamp) pr[6] = gtime();
             int base = 0, env_total = 0;
             for (int r2 = 0; r2 < C; ++r2) {
                 const int v = s_tot[r2];
@@ -846,6 +860,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
             if (rank == 0 && tid == 0) atomicAdd(&P.counters[(size_t)tn * 4 + 0], min(env_total, cap));
             M_cur = min(env_total, cap);
             cluster_sync_all();
+            if (stamp) pr[7] = gtime();
         }
     }
     tc_fence_before();
@@ -858,7 +873,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
 struct WsLayout {
     int64_t msg, logit, ag, v1, z, row_start, row_deg, edge_recv, edge_src, total;
 };
-static WsLayout make_ws_layout(int E, int N, int cap_env) {
+static WsLayout make_ws_layout(int E, int N, int cap_env) {   // (+ 16 (T + 1) floats of phase stamps appended by the caller)
     WsLayout W;
     int64_t o = 0;
     auto take = [&](int64_t n) { int64_t r = o; o += (n + 63) & ~(int64_t)63; return r; };
@@ -903,7 +918,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persisten
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persistent(
     const gcbf_env_desc* desc, int32_t n_steps, const float* actor_params, const float* infer_blob, const float* goal,
     const float* obstacles, const float* ray_table, float* agent_rec, float* hits_rec, float* actions_rec, float* rewards,
-    float* costs, int32_t* counters, float* workspace, int64_t workspace_floats, void* stream) {
+    float* costs, int32_t* counters, float* workspace, int64_t workspace_floats, uint64_t* phase_stamps, void* stream) {
     GCBF_REQUIRE(desc && actor_params && infer_blob && goal && ray_table && agent_rec && hits_rec && actions_rec && rewards &&
                      costs && counters && workspace, "gcbf_rollout_persistent: NULL pointer argument");
     GCBF_REQUIRE(gcbf_rollout_persistent_supported(desc), "gcbf_rollout_persistent: unsupported configuration (2-D envs, "
@@ -946,6 +961,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persisten
     P.rewards = rewards;
     P.costs = costs;
     P.counters = counters;
+    P.prof = reinterpret_cast<unsigned long long*>(phase_stamps);
     P.msg = workspace + W.msg;
     P.logit = workspace + W.logit;
     P.ag = workspace + W.ag;

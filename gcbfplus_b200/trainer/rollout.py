@@ -93,6 +93,9 @@ class RolloutEngine:
             raise ValueError("persistent rollout unsupported for this configuration (2-D env, n <= 512, tensor-core path, "
                              "actor policy, one chain)")
         self.persistent = bool(persistent)
+        #: optional [T + 1, 8] int64 device tensor: in-kernel %globaltimer stamps of the persistent rollout (set before
+        #: the first run(); see gcbf_rollout_persistent in include/gcbf_b200.h)
+        self.phase_stamps: Optional[torch.Tensor] = None
         self._pws = None
         if self.persistent:
             n = env.lib.gcbf_rollout_persistent_workspace_floats(C.byref(self.desc))
@@ -153,7 +156,8 @@ class RolloutEngine:
             C.byref(ch.desc), int(n_steps), self.params_buf.data_ptr(), self.infer_blob.data_ptr(), self.goal.data_ptr(),
             self.obstacles.data_ptr() if self.O > 0 else None, env.ray_table.data_ptr(), self.agent.data_ptr(),
             self.hits.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr(), self.costs.data_ptr(),
-            ch.counters.data_ptr(), self._pws.data_ptr(), self._pws.numel(), stream)
+            ch.counters.data_ptr(), self._pws.data_ptr(), self._pws.numel(),
+            self.phase_stamps.data_ptr() if self.phase_stamps is not None else None, stream)
         _lib.check(rc, "gcbf_rollout_persistent")
 
     def _enqueue_all(self) -> None:

@@ -232,14 +232,17 @@ int32_t gcbf_rollout_step_select(const gcbf_env_desc* desc, const float* actor_p
  *   agent_rec [n_steps+1, G, N, sd]: slice 0 = initial states (input), slices 1.. written;  hits_rec [n_steps+1, G, N, R, pd]
  *   (all slices written, slice 0 = LiDAR of the initial states);  actions_rec [n_steps, G, N, nu];  rewards / costs
  *   [n_steps, G];  counters [n_steps+1, 4] (zeroed by the caller): [t][0] += edges of the graphs of state t, [t][1] |= overflow.
- *   workspace: gcbf_rollout_persistent_workspace_floats(desc) floats, 256-byte aligned. */
+ *   workspace: gcbf_rollout_persistent_workspace_floats(desc) floats, 256-byte aligned.
+ *   phase_stamps: NULL, or [n_steps + 1][8] uint64 (device): %globaltimer (ns) of environment 0's first CTA at the phase
+ *   boundaries of every step (start, after edge phase, aggregate, update GEMM, head GEMM, policy tail, LiDAR + neighbour
+ *   bits, end) -- the in-kernel profile bench.py reports (row 0 = the initial graph build). */
 int64_t gcbf_rollout_persistent_workspace_floats(const gcbf_env_desc* desc);
 int32_t gcbf_rollout_persistent_supported(const gcbf_env_desc* desc);
 int32_t gcbf_rollout_persistent(const gcbf_env_desc* desc, int32_t n_steps, const float* actor_params,
                                 const float* infer_blob, const float* goal, const float* obstacles,
                                 const float* ray_table, float* agent_rec, float* hits_rec, float* actions_rec,
                                 float* rewards, float* costs, int32_t* counters, float* workspace,
-                                int64_t workspace_floats, void* stream);
+                                int64_t workspace_floats, uint64_t* phase_stamps, void* stream);
 
 /* ---------------------------------------------------------------- labels / masks (a9)
  * Replaces env.unsafe_mask / collision_mask / finish_mask / safe_mask
