@@ -60,6 +60,7 @@ _SIGNATURES = {
     "gcbf_rollout_step_select": (C.c_int32, [C.POINTER(EnvDesc), _P, _P, C.c_int32] + [_P] * 21 + [C.c_int64, C.c_int32, _P]),
     "gcbf_rollout_persistent_workspace_floats": (C.c_int64, [C.POINTER(EnvDesc)]),
     "gcbf_rollout_persistent_supported": (C.c_int32, [C.POINTER(EnvDesc)]),
+    "gcbf_rollout_persistent_max_clusters": (C.c_int32, [C.c_int32]),
     "gcbf_rollout_persistent": (C.c_int32, [C.POINTER(EnvDesc), C.c_int32] + [_P] * 12 + [C.c_int64, _P, _P]),
     "gcbf_params_t_count": (C.c_int32, [C.c_int32, C.c_int32]),
     "gcbf_prepare_params": (C.c_int32, [C.c_int32, C.c_int32, _P, _P, _P]),

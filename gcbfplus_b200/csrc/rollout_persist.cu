@@ -203,6 +203,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
     uint32_t n0 = 0;      // uses of accumulator 0 (edge tiles + U1 / U2 items)
     int M_cur = 0;        // edges of the current graph of this environment
     cluster_sync_all();
+    if (P.prof != nullptr && rank == 0 && tid == 0) P.prof[(size_t)(P.T + 1) * 8 + 2 * env] = gtime();   // cluster start
 
     // =================================================================================================
     for (int t = -1; t < P.T; ++t) {
@@ -863,6 +864,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
             if (stamp) pr[7] = gtime();
         }
     }
+    if (P.prof != nullptr && rank == 0 && tid == 0) P.prof[(size_t)(P.T + 1) * 8 + 2 * env + 1] = gtime();   // cluster end
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -913,6 +915,39 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persisten
     return (desc->env_kind >= 0 && desc->env_kind <= 2 && desc->n_agents >= 1 && desc->n_agents <= rp::MAX_N &&
             desc->n_obs <= rp::MAX_OBS && desc->n_rays <= 32 && desc->n_hits == desc->n_rays &&
             desc->edge_cap / desc->n_graphs >= desc->n_agents && (desc->obs_per_graph == 1 || desc->n_obs == 0)) ? 1 : 0;
+}
+
+static int persist_smem_bytes() {
+    return 3 * rp::STG + 512 + 7 * 256 * 4 + rp::MAX_N * 2 * 4 + rp::MAX_OBS * 24 * 4 + 64 * 4 + 64 * 16 * 4 + 72 * 4 + 64 * 4 +
+           3 * rp::PW * 4 + 1024;
+}
+
+/* Co-resident clusters of `cluster_size` CTAs of the persistent rollout kernel on the current device
+ * (cudaOccupancyMaxActiveClusters): environments beyond this number wait for a free cluster slot. */
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persistent_max_clusters(int32_t cluster_size) {
+    auto kern = rp::rollout_persist_kernel<GCBF_ENV_DOUBLE_INTEGRATOR>;
+    const int smem = persist_smem_bytes();
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    if (cluster_size > 8 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(cluster_size * 64), 1, 1);
+    cfg.blockDim = dim3(rp::PT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return n;
 }
 
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persistent(
@@ -985,8 +1020,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persisten
     RC(tc::make_map(&tAG, P.ag, E * N + 128, 128, 128));
     RC(tc::make_map(&tV1, P.v1, E * N + 128, 256, 128));
 #undef RC
-    const int smem = 3 * rp::STG + 512 + 7 * 256 * 4 + rp::MAX_N * 2 * 4 + rp::MAX_OBS * 24 * 4 + 64 * 4 + 64 * 16 * 4 + 72 * 4 +
-                     64 * 4 + 3 * rp::PW * 4 + 1024;
+    const int smem = persist_smem_bytes();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(E * P.C), 1, 1);

@@ -233,11 +233,14 @@ int32_t gcbf_rollout_step_select(const gcbf_env_desc* desc, const float* actor_p
  *   (all slices written, slice 0 = LiDAR of the initial states);  actions_rec [n_steps, G, N, nu];  rewards / costs
  *   [n_steps, G];  counters [n_steps+1, 4] (zeroed by the caller): [t][0] += edges of the graphs of state t, [t][1] |= overflow.
  *   workspace: gcbf_rollout_persistent_workspace_floats(desc) floats, 256-byte aligned.
- *   phase_stamps: NULL, or [n_steps + 1][8] uint64 (device): %globaltimer (ns) of environment 0's first CTA at the phase
+ *   phase_stamps: NULL, or [(n_steps + 1) * 8 + 2 * G] uint64 (device): first [n_steps + 1][8]: %globaltimer (ns) of environment 0's first CTA at the phase
  *   boundaries of every step (start, after edge phase, aggregate, update GEMM, head GEMM, policy tail, LiDAR + neighbour
- *   bits, end) -- the in-kernel profile bench.py reports (row 0 = the initial graph build). */
+ *   bits, end) -- the in-kernel profile bench.py reports (row 0 = the initial graph build); then [G][2] = start / end time
+ *   of every environment's cluster (shows whether all clusters were co-resident). */
 int64_t gcbf_rollout_persistent_workspace_floats(const gcbf_env_desc* desc);
 int32_t gcbf_rollout_persistent_supported(const gcbf_env_desc* desc);
+/* co-resident clusters of `cluster_size` CTAs of the persistent kernel on the current device (occupancy query) */
+int32_t gcbf_rollout_persistent_max_clusters(int32_t cluster_size);
 int32_t gcbf_rollout_persistent(const gcbf_env_desc* desc, int32_t n_steps, const float* actor_params,
                                 const float* infer_blob, const float* goal, const float* obstacles,
                                 const float* ray_table, float* agent_rec, float* hits_rec, float* actions_rec,

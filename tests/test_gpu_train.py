@@ -81,7 +81,10 @@ def test_gradients_match_oracle_autograd(env_id, N, B, area, n_obs, pretrained, 
             want = grads[i] if grads[i] is not None else torch.zeros_like(got[k])
             err = float((got[k] - want).abs().max())
             scale = max(float(want.abs().max()), 1e-3 * gmax)
-            if err <= 2e-4 * scale + 1e-9:
+            # 2e-4 of the tensor's own magnitude + 2e-6 of the network's largest gradient entry (fp32 / 3xTF32
+            # accumulation noise of a tensor whose entries are small differences of large per-edge terms)
+            tol = 2e-4 * scale + 2e-6 * gmax + 1e-9
+            if err <= tol:
                 continue
             # ReLU kinks: with ~1e6 hidden units per pass (N = 64: 2 700 edges x 256 x 3 passes) a few pre-activations
             # sit within rounding of 0, where the float64 and the float32 evaluation of the SAME restated loss take
@@ -91,7 +94,7 @@ def test_gradients_match_oracle_autograd(env_id, N, B, area, n_obs, pretrained, 
                 gs32 = oracle_grads(torch.float32)[3]
             want32 = gs32[lo + i] if gs32[lo + i] is not None else torch.zeros_like(got[k])
             err32 = float((got[k] - want32).abs().max())
-            assert err32 <= 2e-4 * scale + 1e-9, (net, k, err, err32, scale)
+            assert err32 <= tol, (net, k, err, err32, scale)
             n_kink += 1
     assert any_nonzero
     assert n_kink <= 4, n_kink          # kink ties are rare: a handful of the 24 tensors at most
