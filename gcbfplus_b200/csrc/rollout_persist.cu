@@ -151,17 +151,17 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
     if (tid == 0) {
         for (int s = 0; s < 3; ++s) {
             mbar_init(&bars[B_FULL + s], 1);
-            mbar_init(&bars[B_CONV + s], 128);
+            mbar_init(&bars[B_CONV + s], 256);
             mbar_init(&bars[B_EMPTY + s], 1);
         }
         mbar_init(&bars[B_TF0], 1);
-        mbar_init(&bars[B_TE0], 128);
+        mbar_init(&bars[B_TE0], 256);
         mbar_init(&bars[B_TE1], 128);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars[B_B2F + i], 1);
             mbar_init(&bars[B_B2E + i], 1);
         }
-        mbar_init(&bars[B_A2R], 128);
+        mbar_init(&bars[B_A2R], 256);
         mbar_init(&bars[B_T2F], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -278,68 +278,73 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                         umma_commit(&bars[B_T2F]);
                     }
                 }
-            } else if (warp < 6) {
-                // operand warps: thread = edge row; features + message layer 1, split into tf32 hi / lo, swizzled K-major
-                const int r = tid - 64;
-                uint32_t it_l = it, ne_l = ne;
-                for (int tile = rank; tile < n_tiles; tile += C, ++ne_l) {
-                    const int ml = tile * BM + r;
-                    const bool row_ok = ml < M_cur;
-                    if (ne_l > 0) mbar_wait_wd(&bars[B_T2F], (ne_l - 1) & 1);
-                    float f[ED];
-                    int stype = 0;
-#pragma unroll
-                    for (int c = 0; c < ED; ++c) f[c] = 0.f;
-                    if (row_ok) {
-                        const int a = min(max(er_t[env_e0 + ml], 0), A_tot - 1);
-                        const int code = min(es_t[env_e0 + ml], A_tot - 1);
-                        float er[ED], es[ED], coef, nrm;
-                        edge_state_dev<KIND>(agent_t + (size_t)a * SD, er);
-                        sender_state_dev<KIND>(code, a, R, agent_t, P.goal, hits_t, es);
-                        edge_feat_dev<KIND>(er, es, code == -1, d.comm_radius, f, &coef, &nrm);
-                        stype = (code >= 0) ? 2 : ((code == -1) ? 1 : 0);
-                    }
-                    for (int kb = 0; kb < 8; ++kb, ++it_l) {
-                        const int s = it_l % 3;
-                        mbar_wait_wd(&bars[B_EMPTY + s], ((it_l / 3) & 1) ^ 1);
-                        uint8_t* hi_row = smem + s * STG + r * 128;
-                        uint8_t* lo_row = hi_row + A_BYTES;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            float v[4] = {0.f, 0.f, 0.f, 0.f};
-                            if (row_ok) {
-                                const int n = kb * BK + c * 4;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float y = sW[(ED + stype) * 256 + n + j];
-#pragma unroll
-                                    for (int q = 0; q < ED; ++q) y = fmaf(f[q], sW[q * 256 + n + j], y);
-                                    v[j] = fmaxf(y, 0.f);
-                                }
-                            }
-                            float4 h, l;
-                            h.x = rn_tf32(v[0]); h.y = rn_tf32(v[1]); h.z = rn_tf32(v[2]); h.w = rn_tf32(v[3]);
-                            l.x = rn_tf32(v[0] - h.x); l.y = rn_tf32(v[1] - h.y);
-                            l.z = rn_tf32(v[2] - h.z); l.w = rn_tf32(v[3] - h.w);
-                            const int off = ((c ^ (r & 7)) << 4);
-                            *reinterpret_cast<float4*>(hi_row + off) = h;
-                            *reinterpret_cast<float4*>(lo_row + off) = l;
-                        }
-                        fence_async_smem();
-                        mbar_arrive(&bars[B_CONV + s]);
-                    }
-                }
             } else if (warp < 10) {
-                // epilogue warps: message tile -> global + shared-memory hand-over; gate logits from accumulator 1
-                const int quarter = warp & 3;
+                // worker warps 2..9 (256 threads): first PRODUCE the A operand of the tile (two threads per edge row, 16 of
+                // the 32 columns of a k-block each: features + message layer 1, tf32 hi / lo split, swizzled K-major),
+                // then drain it (message tile -> global + shared-memory hand-over, two warps per TMEM lane quarter with 64
+                // columns each), then warps 2..5 turn the chained accumulator into the gate logits.
+                const int pr_ = tid - 64;
+                const int r = pr_ & 127;                  // producer: row of the tile
+                const int half = pr_ >> 7;                // producer: 16-byte chunks 4 half .. 4 half + 3
+                const int quarter = warp & 3;             // epilogue: TMEM lane quarter of this warp
+                const int chalf = (warp - 2) >> 2;        // epilogue: message columns [64 chalf, 64 chalf + 64)
                 const int row = quarter * 32 + lane;
-                uint32_t ne_l = ne, n0_l = n0;
+                uint32_t it_l = it, ne_l = ne, n0_l = n0;
                 for (int tile = rank; tile < n_tiles; tile += C, ++ne_l, ++n0_l) {
+                    {
+                        const int ml = tile * BM + r;
+                        const bool row_ok = ml < M_cur;
+                        if (ne_l > 0) mbar_wait_wd(&bars[B_T2F], (ne_l - 1) & 1);
+                        float f[ED];
+                        int stype = 0;
+#pragma unroll
+                        for (int c = 0; c < ED; ++c) f[c] = 0.f;
+                        if (row_ok) {
+                            const int a = min(max(er_t[env_e0 + ml], 0), A_tot - 1);
+                            const int code = min(es_t[env_e0 + ml], A_tot - 1);
+                            float er[ED], es[ED], coef, nrm;
+                            edge_state_dev<KIND>(agent_t + (size_t)a * SD, er);
+                            sender_state_dev<KIND>(code, a, R, agent_t, P.goal, hits_t, es);
+                            edge_feat_dev<KIND>(er, es, code == -1, d.comm_radius, f, &coef, &nrm);
+                            stype = (code >= 0) ? 2 : ((code == -1) ? 1 : 0);
+                        }
+                        for (int kb = 0; kb < 8; ++kb, ++it_l) {
+                            const int s = it_l % 3;
+                            mbar_wait_wd(&bars[B_EMPTY + s], ((it_l / 3) & 1) ^ 1);
+                            uint8_t* hi_row = smem + s * STG + r * 128;
+                            uint8_t* lo_row = hi_row + A_BYTES;
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                const int c = half * 4 + cc;
+                                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                                if (row_ok) {
+                                    const int n = kb * BK + c * 4;
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        float y = sW[(ED + stype) * 256 + n + j];
+#pragma unroll
+                                        for (int q = 0; q < ED; ++q) y = fmaf(f[q], sW[q * 256 + n + j], y);
+                                        v[j] = fmaxf(y, 0.f);
+                                    }
+                                }
+                                float4 h, l;
+                                h.x = rn_tf32(v[0]); h.y = rn_tf32(v[1]); h.z = rn_tf32(v[2]); h.w = rn_tf32(v[3]);
+                                l.x = rn_tf32(v[0] - h.x); l.y = rn_tf32(v[1] - h.y);
+                                l.z = rn_tf32(v[2] - h.z); l.w = rn_tf32(v[3] - h.w);
+                                const int off = ((c ^ (r & 7)) << 4);
+                                *reinterpret_cast<float4*>(hi_row + off) = h;
+                                *reinterpret_cast<float4*>(lo_row + off) = l;
+                            }
+                            fence_async_smem();
+                            mbar_arrive(&bars[B_CONV + s]);
+                        }
+                    }
+                    // ---- drain accumulator 0: message tile -> global + hi / lo hand-over planes
                     const int ml = tile * BM + row;
                     mbar_wait_wd(&bars[B_TF0], n0_l & 1);
                     tc_fence_after();
 #pragma unroll 1
-                    for (int c0 = 0; c0 < 128; c0 += 32) {
+                    for (int c0 = chalf * 64; c0 < chalf * 64 + 64; c0 += 32) {
                         uint32_t v[32];
                         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
                         uint8_t* hi_row = smem + (c0 >> 5) * 32768 + row * 128;
@@ -369,20 +374,24 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                     fence_async_smem();
                     mbar_arrive(&bars[B_A2R]);
                     mbar_arrive(&bars[B_TE0]);
-                    mbar_wait_wd(&bars[B_T2F], ne_l & 1);
-                    tc_fence_after();
-                    float dot = 0.f;
+                    if (chalf == 0) {
+                        // ---- gate logit from the chained accumulator: one sequential fmaf chain over the 128 columns
+                        // (the summation order of the 5-launch path), so it stays with the four quarter-owning warps
+                        mbar_wait_wd(&bars[B_T2F], ne_l & 1);
+                        tc_fence_after();
+                        float dot = 0.f;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < 128; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + 128 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                        for (int c0 = 0; c0 < 128; c0 += 32) {
+                            uint32_t v[32];
+                            tmem_ld32(tmem_base + 128 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            dot = fmaf(fmaxf(__uint_as_float(v[j]) + P.bias_g[c0 + j], 0.f), P.avec[c0 + j], dot);
+                            for (int j = 0; j < 32; ++j)
+                                dot = fmaf(fmaxf(__uint_as_float(v[j]) + P.bias_g[c0 + j], 0.f), P.avec[c0 + j], dot);
+                        }
+                        if (ml < M_cur) P.logit[env_e0 + ml] = dot + P.cst[0];
+                        tc_fence_before();
+                        mbar_arrive(&bars[B_TE1]);
                     }
-                    if (ml < M_cur) P.logit[env_e0 + ml] = dot + P.cst[0];
-                    tc_fence_before();
-                    mbar_arrive(&bars[B_TE1]);
                 }
             }
             it += 8u * my_tiles;
