@@ -397,6 +397,286 @@ gemm_tc_prod_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_const
     (void)ndot;
 }
 
+// =====================================================================================================
+// edge_chain_kernel: the rollout's edge kernel (PROD_EDGE + CHAIN of gemm_tc_prod_kernel, same arithmetic and the
+// same bits) with EIGHT worker warps instead of 4 + 4: in-kernel %globaltimer stamps showed the tile bound by its 4
+// producer warps (0.93 us per k-block against 0.55 us of MMA issue) and by a 4.1 us single-pass drain of the
+// message tile.  Warps 2..9 first PRODUCE the A operand (two threads per edge row, 16 of the 32 columns of a k-block
+// each), then DRAIN accumulator 0 (two warps per TMEM lane quarter, 64 columns each: global store + tf32 hi / lo
+// hand-over planes for the chained gate GEMM); the gate logit stays one sequential fmaf chain per row on the four
+// quarter-owning warps (the summation order is part of the result).  320 threads, 1 CTA / SM, persistent tile loop.
+// =====================================================================================================
+template <int KIND>
+__global__ void __launch_bounds__(THREADS_NN, 1)
+edge_chain_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                  const __grid_constant__ CUtensorMap tmB2h, const __grid_constant__ CUtensorMap tmB2l,
+                  const __grid_constant__ ProdArgs pa, const float* __restrict__ bias, float* __restrict__ C,
+                  const int32_t* __restrict__ m_ptr, const int m_cap, const ChainArgs ch) {
+    using T = EnvTraits<KIND>;
+    constexpr int ED = T::ED, SD = T::SD;
+    constexpr int STG = 65536, A_BYTES = 16384, B_BYTES = 16384, BN = 128;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * STG);
+    uint64_t* full = bars;                 // [3] weight planes landed (TMA)
+    uint64_t* conv = bars + 3;             // [3] A planes written (256 arrivals)
+    uint64_t* empty = bars + 6;            // [3] MMAs of the stage retired
+    uint64_t* tf0 = bars + 9;              // message accumulator ready
+    uint64_t* te0 = bars + 10;             // message accumulator drained (256 arrivals)
+    uint64_t* te1 = bars + 11;             // gate accumulator drained (128 arrivals)
+    uint64_t* b2_full = bars + 12;         // [2] gate-weight slot landed
+    uint64_t* b2_empty = bars + 14;        // [2] gate-weight slot consumed
+    uint64_t* a2_ready = bars + 16;        // message tile handed over in shared memory (256 arrivals)
+    uint64_t* t2f = bars + 17;             // chained GEMM retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    float* sW = reinterpret_cast<float*>(smem + 3 * STG + 256);   // [ED + 3][256]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 3; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&conv[s], 256);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tf0, 1);
+        mbar_init(te0, 256);
+        mbar_init(te1, 128);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&b2_full[i], 1);
+            mbar_init(&b2_empty[i], 1);
+        }
+        mbar_init(a2_ready, 256);
+        mbar_init(t2f, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(256u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < ED * 256; i += blockDim.x) sW[i] = pa.W1[i];
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+        const int t = i / 256, c = i % 256;
+        sW[(ED + t) * 256 + c] = pa.W1[(ED + t) * 256 + c] + pa.W1[(ED + 3 + 2) * 256 + c] + pa.b1[c];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int M = min(*m_ptr, m_cap);
+    const int n_tiles = (M + BM - 1) / BM;
+    constexpr uint32_t idesc = make_idesc(BM, BN);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0, tc_ = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tc_) {
+                if (tc_ > 0) mbar_wait(t2f, (tc_ - 1) & 1);       // the previous tile's chained GEMM still reads the stages
+                for (int kb = 0; kb < 8; ++kb, ++it) {
+                    const int s = it % 3;
+                    mbar_wait(&empty[s], ((it / 3) & 1) ^ 1);
+                    uint8_t* st = smem + s * STG;
+                    mbar_expect_tx(&full[s], 2 * B_BYTES);
+                    tma_load_2d(st + 2 * A_BYTES, &tmBh, &full[s], kb * BK, 0);
+                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBl, &full[s], kb * BK, 0);
+                }
+                mbar_wait(tf0, tc_ & 1);                          // main-loop MMAs retired: stage 2 is free
+                for (int kb2 = 0; kb2 < 4; ++kb2) {
+                    const uint32_t j2 = tc_ * 4 + kb2, slot = j2 & 1, use = j2 >> 1;
+                    mbar_wait(&b2_empty[slot], (use & 1) ^ 1);
+                    uint8_t* sl = smem + 2 * STG + slot * 32768;
+                    mbar_expect_tx(&b2_full[slot], 32768);
+                    tma_load_2d(sl, &tmB2h, &b2_full[slot], kb2 * BK, 0);
+                    tma_load_2d(sl + 16384, &tmB2l, &b2_full[slot], kb2 * BK, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0, tc_ = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tc_) {
+                mbar_wait(te0, (tc_ & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < 8; ++kb, ++it) {
+                    const int s = it % 3;
+                    const uint32_t ph = (it / 3) & 1;
+                    mbar_wait(&conv[s], ph);
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(smem + s * STG);
+                    const uint32_t a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t koff = k * UMMA_K * 4;
+                        const uint64_t dah = make_desc(a_hi + koff), dal = make_desc(a_lo + koff);
+                        const uint64_t dbh = make_desc(b_hi + koff), dbl = make_desc(b_lo + koff);
+                        umma_tf32(tmem_base, dal, dbh, idesc, (kb | k) != 0);
+                        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(tf0);
+                mbar_wait(te1, (tc_ & 1) ^ 1);
+                mbar_wait(a2_ready, tc_ & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb2 = 0; kb2 < 4; ++kb2) {
+                    const uint32_t j2 = tc_ * 4 + kb2, slot = j2 & 1, use = j2 >> 1;
+                    mbar_wait(&b2_full[slot], use & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(smem + kb2 * 32768);
+                    const uint32_t a_lo = a_hi + 16384;
+                    const uint32_t b_hi = smem_u32(smem + 2 * STG + slot * 32768);
+                    const uint32_t b_lo = b_hi + 16384;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t koff = k * UMMA_K * 4;
+                        const uint64_t dah = make_desc(a_hi + koff), dal = make_desc(a_lo + koff);
+                        const uint64_t dbh = make_desc(b_hi + koff), dbl = make_desc(b_lo + koff);
+                        umma_tf32(tmem_base + BN, dal, dbh, idesc, (kb2 | k) != 0);
+                        umma_tf32(tmem_base + BN, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_base + BN, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(&b2_empty[slot]);
+                }
+                umma_commit(t2f);
+            }
+        }
+    } else {
+        const int pr_ = threadIdx.x - 64;
+        const int r = pr_ & 127;                  // producer: row of the tile
+        const int half = pr_ >> 7;                // producer: 16-byte chunks 4 half .. 4 half + 3
+        const int quarter = warp & 3;             // drain: TMEM lane quarter of this warp
+        const int chalf = (warp - 2) >> 2;        // drain: message columns [64 chalf, 64 chalf + 64)
+        const int row = quarter * 32 + lane;
+        const int A_tot = pa.d.n_graphs * pa.d.n_agents;
+        uint32_t it = 0, tc_ = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tc_) {
+            {
+                const int m = tile * BM + r;
+                const bool row_ok = m < M;
+                if (tc_ > 0) mbar_wait(t2f, (tc_ - 1) & 1);
+                float f[ED];
+                int stype = 0;
+#pragma unroll
+                for (int c = 0; c < ED; ++c) f[c] = 0.f;
+                if (row_ok) {
+                    const int a = min(max(pa.edge_recv[m], 0), A_tot - 1);
+                    const int code = min(pa.edge_src[m], A_tot - 1);
+                    float er[ED], es[ED], coef, nrm;
+                    edge_state_dev<KIND>(pa.agent + (size_t)a * SD, er);
+                    sender_state_dev<KIND>(code, a, pa.d.n_hits, pa.agent, pa.goal, pa.hits, es);
+                    edge_feat_dev<KIND>(er, es, pa.clip_all || code == -1, pa.d.comm_radius, f, &coef, &nrm);
+                    stype = (code >= 0) ? 2 : ((code == -1) ? 1 : 0);
+                }
+                for (int kb = 0; kb < 8; ++kb, ++it) {
+                    const int s = it % 3;
+                    mbar_wait(&empty[s], ((it / 3) & 1) ^ 1);
+                    uint8_t* hi_row = smem + s * STG + r * 128;
+                    uint8_t* lo_row = hi_row + A_BYTES;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int c = half * 4 + cc;
+                        float v[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (row_ok) {
+                            const int n = kb * BK + c * 4;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float y = sW[(ED + stype) * 256 + n + j];
+#pragma unroll
+                                for (int q = 0; q < ED; ++q) y = fmaf(f[q], sW[q * 256 + n + j], y);
+                                v[j] = fmaxf(y, 0.f);
+                            }
+                        }
+                        float4 h, l;
+                        h.x = rn_tf32(v[0]); h.y = rn_tf32(v[1]); h.z = rn_tf32(v[2]); h.w = rn_tf32(v[3]);
+                        l.x = rn_tf32(v[0] - h.x); l.y = rn_tf32(v[1] - h.y);
+                        l.z = rn_tf32(v[2] - h.z); l.w = rn_tf32(v[3] - h.w);
+                        const int off = ((c ^ (r & 7)) << 4);
+                        *reinterpret_cast<float4*>(hi_row + off) = h;
+                        *reinterpret_cast<float4*>(lo_row + off) = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&conv[s]);
+                }
+            }
+            const int m = tile * BM + row;
+            mbar_wait(tf0, tc_ & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c0 = chalf * 64; c0 < chalf * 64 + 64; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                uint8_t* hi_row = smem + (c0 >> 5) * 32768 + row * 128;
+                uint8_t* lo_row = hi_row + 16384;
+                float* crow = C + (size_t)m * BN + c0;
+                const bool wide = (reinterpret_cast<uintptr_t>(crow) & 31) == 0;
+                float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                           __uint_as_float(v[j + 3]));
+                    const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + j);
+                    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    if (m < M) {
+                        if (!wide) *reinterpret_cast<float4*>(crow + j) = o;
+                        else if (j & 4) st_global_v8(crow + j - 4, prev, o);
+                        else prev = o;
+                    }
+                    float4 h, l;
+                    h.x = rn_tf32(o.x); h.y = rn_tf32(o.y); h.z = rn_tf32(o.z); h.w = rn_tf32(o.w);
+                    l.x = rn_tf32(o.x - h.x); l.y = rn_tf32(o.y - h.y);
+                    l.z = rn_tf32(o.z - h.z); l.w = rn_tf32(o.w - h.w);
+                    const int off = (((j >> 2) ^ (row & 7)) << 4);
+                    *reinterpret_cast<float4*>(hi_row + off) = h;
+                    *reinterpret_cast<float4*>(lo_row + off) = l;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(a2_ready);
+            mbar_arrive(te0);
+            if (chalf == 0) {
+                mbar_wait(t2f, tc_ & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float dot = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        dot = fmaf(fmaxf(__uint_as_float(v[j]) + ch.bias_g[c0 + j], 0.f), ch.avec[c0 + j], dot);
+                }
+                if (m < M) ch.logits[m] = dot + ch.cst[0];
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(te1);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+template <int KIND>
+inline int32_t launch_edge_chain(const CUtensorMap& tmB, const CUtensorMap& tmBl, const CUtensorMap& tmG, const CUtensorMap& tmGl,
+                                 const ProdArgs& pa, const float* bias, float* C, RowCount rc, int grid, cudaStream_t st,
+                                 const ChainArgs& chain) {
+    constexpr int smem = 3 * 65536 + 256 + 9 * 256 * 4 + 1024;
+    auto kern = edge_chain_kernel<KIND>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_done = true;
+    }
+    kern<<<grid, THREADS_NN, smem, st>>>(tmB, tmBl, tmG, tmGl, pa, bias, C, rc.ptr, rc.cap, chain);
+    count_launch();
+    return check_launch("edge_chain_kernel");
+}
+
 template <int BN, int EPI, int PROD, int KIND, bool CHAIN = false>
 inline int32_t launch_prod_inst(const CUtensorMap& tmB, const CUtensorMap& tmBl, const ProdArgs& pa, const float* bias,
                                 const float* bias2, float* C, RowCount rc, int K, int N, int grid, cudaStream_t st,
@@ -442,6 +722,12 @@ inline int32_t launch_edge_msg(const gcbf_env_desc* d, const float* W1, const fl
         CUtensorMap tmG, tmGl;
         if (int32_t r = make_map(&tmG, gate_Bt_hi, 128, 128, 128)) return r;
         if (int32_t r = make_map(&tmGl, gate_Bt_lo, 128, 128, 128)) return r;
+        // GCBF_CHAIN8=0: the 4 + 4 warp version (gemm_tc_prod_kernel<..., CHAIN>), kept for A/B measurements
+        static const bool eight = [] { const char* e = getenv("GCBF_CHAIN8"); return !(e && e[0] == '0'); }();
+        if (eight && rc.ptr != nullptr) {
+            GCBF_DISPATCH_ENV(d->env_kind, { return launch_edge_chain<KIND>(tmB, tmBl, tmG, tmGl, pa, bias, msg, rc, grid, st, *chain); });
+            return -1;
+        }
         GCBF_DISPATCH_ENV(d->env_kind, {
             return launch_prod_inst<128, EPI_BIAS, PROD_EDGE, KIND, true>(tmB, tmBl, pa, bias, nullptr, msg, rc, K, N, grid, st,
                                                                           &tmG, &tmGl, chain);

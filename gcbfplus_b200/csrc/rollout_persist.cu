@@ -500,46 +500,45 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                             umma_commit(&bars[B_TF0]);
                         }
                     }
-                } else if (warp < 6) {
+                } else if (warp < 10) {
+                    // worker warps 2..9: split the TMA-landed A tile into tf32 hi / lo planes (256 threads, 4 float4 each),
+                    // then drain the accumulator: U1 = 8 warps x 64 columns (independent elements); U2's output-layer
+                    // partial sums are one sequential fmaf chain per row (the 5-launch order) -> the 4 quarter-owning warps
                     const int et = tid - 64;
-                    uint32_t it_l = it;
-                    for (int item = rank; item < n_items; item += C) {
+                    const int quarter = warp & 3;
+                    const int chalf = (warp - 2) >> 2;
+                    const int row = quarter * 32 + lane;
+                    uint32_t it_l = it, n0_l = n0;
+                    for (int item = rank; item < n_items; item += C, ++n0_l) {
                         for (int kb = 0; kb < nkb; ++kb, ++it_l) {
                             const int s = it_l % 3;
                             mbar_wait_wd(&bars[B_FULL + s], (it_l / 3) & 1);
                             float4* h4 = reinterpret_cast<float4*>(smem + s * STG);
                             float4* l4 = reinterpret_cast<float4*>(smem + s * STG + A_BYTES);
-                            float4 v[8];
+                            float4 v[4];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = h4[et + 128 * j];
+                            for (int j = 0; j < 4; ++j) v[j] = h4[et + 256 * j];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
+                            for (int j = 0; j < 4; ++j) {
                                 float4 h, l;
                                 h.x = rn_tf32(v[j].x); h.y = rn_tf32(v[j].y); h.z = rn_tf32(v[j].z); h.w = rn_tf32(v[j].w);
                                 l.x = rn_tf32(v[j].x - h.x); l.y = rn_tf32(v[j].y - h.y);
                                 l.z = rn_tf32(v[j].z - h.z); l.w = rn_tf32(v[j].w - h.w);
-                                h4[et + 128 * j] = h;
-                                l4[et + 128 * j] = l;
+                                h4[et + 256 * j] = h;
+                                l4[et + 256 * j] = l;
                             }
                             fence_async_smem();
                             mbar_arrive(&bars[B_CONV + s]);
                         }
-                    }
-                } else if (warp < 10) {
-                    const int quarter = warp & 3;
-                    const int row = quarter * 32 + lane;
-                    uint32_t n0_l = n0;
-                    for (int item = rank; item < n_items; item += C, ++n0_l) {
                         const int m0 = (item >> 1) * BM, nc0 = (item & 1) * 128;
                         const int ml = m0 + row;                   // agent inside the environment
                         mbar_wait_wd(&bars[B_TF0], n0_l & 1);
                         tc_fence_after();
-                        float dq[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (ph2 == 0) {
 #pragma unroll 1
-                        for (int c0 = 0; c0 < 128; c0 += 32) {
-                            uint32_t v[32];
-                            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-                            if (ph2 == 0) {
+                            for (int c0 = chalf * 64; c0 < chalf * 64 + 64; c0 += 32) {
+                                uint32_t v[32];
+                                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
                                 if (ml < N) {
                                     const int n = nc0 + c0;
                                     float* crow = P.v1 + (size_t)(env_a0 + ml) * 256 + n;
@@ -560,7 +559,13 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                                         st_global_v8(crow + j, o[0], o[1]);
                                     }
                                 }
-                            } else {
+                            }
+                        } else if (chalf == 0) {
+                            float dq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                            for (int c0 = 0; c0 < 128; c0 += 32) {
+                                uint32_t v[32];
+                                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
                                 const float* hw = P.ho + (size_t)(nc0 + c0) * NU;
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
@@ -570,10 +575,10 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                                         if (q < NU) dq[q] = fmaf(h, hw[j * NU + q], dq[q]);
                                 }
                             }
+                            if (ml < N)
+                                *reinterpret_cast<float4*>(P.z + ((size_t)(item & 1) * A_tot + env_a0 + ml) * 4) =
+                                    make_float4(dq[0], dq[1], dq[2], dq[3]);
                         }
-                        if (ph2 == 1 && ml < N)
-                            *reinterpret_cast<float4*>(P.z + ((size_t)(item & 1) * A_tot + env_a0 + ml) * 4) =
-                                make_float4(dq[0], dq[1], dq[2], dq[3]);
                         tc_fence_before();
                         mbar_arrive(&bars[B_TE0]);
                     }
