@@ -57,6 +57,12 @@ struct PArgs {
     int32_t *row_start, *row_deg, *edge_recv, *edge_src; // [2][...] double-buffered lists
     float *msg, *logit, *ag, *v1, *z;
     unsigned long long* prof;                            // optional [T + 1][8] %globaltimer stamps of cluster 0 / CTA 0 (ns)
+    // soft mode: no hardware cluster (B200 keeps at most 15 clusters of 8 CTAs resident, BASELINE's config has 16
+    // environments): the C CTAs of an environment are a software group of a cooperative launch, synchronised through
+    // a monotonic arrival counter in global memory; CTA edge totals are exchanged through `gtot` instead of DSMEM
+    int soft;
+    unsigned* gbar;                                      // [E] arrival counters (zeroed by the launcher)
+    int* gtot;                                           // [E][8]
 };
 
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
@@ -84,6 +90,24 @@ __device__ __forceinline__ unsigned long long gtime() {
 __device__ __forceinline__ void cluster_sync_all() {
     __syncwarp();
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// software group barrier (soft mode): bar.sync, then one thread publishes this CTA's writes (gpu-scope fence, cumulative
+// over the bar.sync), arrives on the environment's counter and spins with acquire loads until all C CTAs of the group
+// have arrived for this generation; its trailing gpu-scope fence invalidates the SM's L1 for the loads that follow
+__device__ __forceinline__ void soft_group_sync(unsigned* ctr, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned v;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            if (v < target && clock64() - t0 > 4000000000ll) __trap();
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
 }
 __device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -137,8 +161,19 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
     const int C = P.C;
     uint32_t rank_u;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
-    const int rank = (int)rank_u;
+    const bool soft = P.soft != 0;
+    const int rank = soft ? (int)(blockIdx.x % C) : (int)rank_u;
     const int env = blockIdx.x / C;
+    unsigned n_sync = 0;          // group barriers passed so far (soft mode: arrival target = n_sync * C)
+#define GROUP_SYNC()                                                   \
+    do {                                                               \
+        if (soft) {                                                    \
+            ++n_sync;                                                  \
+            soft_group_sync(P.gbar + env, n_sync * (unsigned)C);       \
+        } else {                                                       \
+            cluster_sync_all();                                        \
+        }                                                              \
+    } while (0)
     const int N = d.n_agents, E = d.n_graphs, O = d.n_obs, R = d.n_hits, cap = P.cap_env;
     const int A_tot = E * N;
     const int APC = (N + C - 1) / C;                 // agents per CTA
@@ -202,7 +237,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
     uint32_t ne = 0;      // edge tiles this CTA has processed (chain barriers)
     uint32_t n0 = 0;      // uses of accumulator 0 (edge tiles + U1 / U2 items)
     int M_cur = 0;        // edges of the current graph of this environment
-    cluster_sync_all();
+    GROUP_SYNC();
     if (P.prof != nullptr && rank == 0 && tid == 0) P.prof[(size_t)(P.T + 1) * 8 + 2 * env] = gtime();   // cluster start
 
     // =================================================================================================
@@ -397,7 +432,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
             it += 8u * my_tiles;
             ne += my_tiles;
             n0 += my_tiles;
-            cluster_sync_all();
+            GROUP_SYNC();
             if (stamp) pr[1] = gtime();
 
             // ============================================================ phase A: segment softmax + aggregate
@@ -453,7 +488,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 *reinterpret_cast<float4*>(P.ag + (size_t)a * 128 + lane * 4) = acc;
             }
             fence_async_global();          // generic-proxy writes of AG -> TMA (async proxy) reads in phase U1
-            cluster_sync_all();
+            GROUP_SYNC();
             if (stamp) pr[2] = gtime();
 
             // ============================================================ phases U1 / U2: agent-side GEMMs
@@ -586,7 +621,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 it += (uint32_t)nkb * my_items;
                 n0 += my_items;
                 if (ph2 == 0) fence_async_global();   // V1 rows (generic stores) -> TMA reads of phase U2
-                cluster_sync_all();
+                GROUP_SYNC();
                 if (stamp) pr[3 + ph2] = gtime();
             }
         }
@@ -816,17 +851,19 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 if (lane + 32 < APC) s_off[lane + 33] = tot0 + inc1;
                 __syncwarp();
                 const int total = s_off[APC];
-                if (lane < C) {                  // my total -> slot [rank] of every CTA of the cluster (DSMEM)
+                if (soft) {
+                    if (lane == 0) P.gtot[env * 8 + rank] = total;
+                } else if (lane < C) {           // my total -> slot [rank] of every CTA of the cluster (DSMEM)
                     uint32_t ra;
                     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(&s_tot[rank])), "r"(lane));
                     asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(total) : "memory");
                 }
             }
-            cluster_sync_all();
+            GROUP_SYNC();
             if (stamp) pr[6] = gtime();
             int base = 0, env_total = 0;
             for (int r2 = 0; r2 < C; ++r2) {
-                const int v = s_tot[r2];
+                const int v = soft ? P.gtot[env * 8 + r2] : s_tot[r2];
                 base += (r2 < rank) ? v : 0;
                 env_total += v;
             }
@@ -874,10 +911,11 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
             }
             if (rank == 0 && tid == 0) atomicAdd(&P.counters[(size_t)tn * 4 + 0], min(env_total, cap));
             M_cur = min(env_total, cap);
-            cluster_sync_all();
+            GROUP_SYNC();
             if (stamp) pr[7] = gtime();
         }
     }
+#undef GROUP_SYNC
     if (P.prof != nullptr && rank == 0 && tid == 0) P.prof[(size_t)(P.T + 1) * 8 + 2 * env + 1] = gtime();   // cluster end
     tc_fence_before();
     __syncthreads();
@@ -887,7 +925,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
 }
 
 struct WsLayout {
-    int64_t msg, logit, ag, v1, z, row_start, row_deg, edge_recv, edge_src, total;
+    int64_t msg, logit, ag, v1, z, row_start, row_deg, edge_recv, edge_src, gbar, gtot, total;
 };
 static WsLayout make_ws_layout(int E, int N, int cap_env) {   // (+ 16 (T + 1) floats of phase stamps appended by the caller)
     WsLayout W;
@@ -903,6 +941,8 @@ static WsLayout make_ws_layout(int E, int N, int cap_env) {   // (+ 16 (T + 1) f
     W.row_deg = take(2 * A);
     W.edge_recv = take(2 * EC);
     W.edge_src = take(2 * EC);
+    W.gbar = take(E);
+    W.gtot = take(8 * (int64_t)E);
     W.total = o;
     return W;
 }
@@ -924,11 +964,26 @@ extern "C" __attribute__((visibility("default"))) int64_t gcbf_rollout_persisten
     return rp::make_ws_layout(desc->n_graphs, desc->n_agents, desc->edge_cap / desc->n_graphs).total + 64;
 }
 
+extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persistent_max_clusters(int32_t cluster_size);
+
+// 0: unsupported configuration; 1: supported, but the device cannot keep one cluster per environment resident at the
+// same time (B200: at most 15 clusters of 8 CTAs with this kernel's 212 KB of shared memory per CTA -- environments
+// beyond that wait for a free cluster slot and the rollout takes two rounds); 2: supported and fully co-resident.
 extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persistent_supported(const gcbf_env_desc* desc) {
     if (!desc) return 0;
-    return (desc->env_kind >= 0 && desc->env_kind <= 2 && desc->n_agents >= 1 && desc->n_agents <= rp::MAX_N &&
-            desc->n_obs <= rp::MAX_OBS && desc->n_rays <= 32 && desc->n_hits == desc->n_rays &&
-            desc->edge_cap / desc->n_graphs >= desc->n_agents && (desc->obs_per_graph == 1 || desc->n_obs == 0)) ? 1 : 0;
+    const bool ok = desc->env_kind >= 0 && desc->env_kind <= 2 && desc->n_agents >= 1 && desc->n_agents <= rp::MAX_N &&
+                    desc->n_obs <= rp::MAX_OBS && desc->n_rays <= 32 && desc->n_hits == desc->n_rays && desc->n_graphs >= 1 &&
+                    desc->edge_cap / desc->n_graphs >= desc->n_agents && (desc->obs_per_graph == 1 || desc->n_obs == 0);
+    if (!ok) return 0;
+    const int C = rp::cluster_size(desc->n_agents, desc->edge_cap / desc->n_graphs);
+    static int cached[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // occupancy per cluster size (0 = not queried yet)
+    if (cached[C] == 0) {
+        const int n = gcbf_rollout_persistent_max_clusters(C);
+        cached[C] = n > 0 ? n : -1;
+    }
+    if (cached[C] > 0 && desc->n_graphs <= cached[C]) return 2;          // hardware clusters, all resident
+    if (desc->n_graphs * C <= sm_count()) return 2;                       // software groups of a cooperative launch
+    return 1;
 }
 
 static int persist_smem_bytes() {
@@ -970,7 +1025,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persisten
     float* costs, int32_t* counters, float* workspace, int64_t workspace_floats, uint64_t* phase_stamps, void* stream) {
     GCBF_REQUIRE(desc && actor_params && infer_blob && goal && ray_table && agent_rec && hits_rec && actions_rec && rewards &&
                      costs && counters && workspace, "gcbf_rollout_persistent: NULL pointer argument");
-    GCBF_REQUIRE(gcbf_rollout_persistent_supported(desc), "gcbf_rollout_persistent: unsupported configuration (2-D envs, "
+    GCBF_REQUIRE(gcbf_rollout_persistent_supported(desc) > 0, "gcbf_rollout_persistent: unsupported configuration (2-D envs, "
                  "n_agents <= 512, n_obs <= 32, edge_cap >= n_graphs * n_agents)");
     GCBF_REQUIRE(desc->n_obs == 0 || obstacles, "obstacles is NULL but n_obs > 0");
     GCBF_REQUIRE(n_steps >= 0, "n_steps must be >= 0");
@@ -990,6 +1045,14 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persisten
     P.T = n_steps;
     P.cap_env = cap_env;
     P.C = rp::cluster_size(N, cap_env);
+    const int max_cl = gcbf_rollout_persistent_max_clusters(P.C);
+    // hardware clusters when every environment's cluster is resident at once; otherwise (B200: 16 environments x 8 CTAs,
+    // 15 clusters fit) software groups of a cooperative launch when the grid fits on the device (1 CTA / SM)
+    static const int force_soft = [] { const char* e = getenv("GCBF_PERSIST_SOFT"); return e ? atoi(e) : -1; }();
+    P.soft = (force_soft >= 0) ? force_soft : ((E <= max_cl) ? 0 : ((E * P.C <= sm_count()) ? 1 : 0));
+    GCBF_REQUIRE(!P.soft || E * P.C <= sm_count(), "soft persistent mode needs n_graphs * %d <= %d CTAs", P.C, sm_count());
+    P.gbar = reinterpret_cast<unsigned*>(workspace + W.gbar);
+    P.gtot = reinterpret_cast<int*>(workspace + W.gtot);
     P.W1 = actor_params + L.w[L_MSG0];
     P.b1 = actor_params + L.b[L_MSG0];
     P.b23 = infer_blob + I.b23;
@@ -1042,13 +1105,22 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persisten
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)P.C;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    if (P.soft) {
+        attr[0].id = cudaLaunchAttributeCooperative;      // co-residency of the whole grid is guaranteed or the launch fails
+        attr[0].val.cooperative = 1;
+    } else {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)P.C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+    }
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaSuccess;
+    if (P.soft && (e = cudaMemsetAsync(P.gbar, 0, sizeof(unsigned) * E, (cudaStream_t)stream)) != cudaSuccess) {
+        set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+        return (int32_t)e;
+    }
     switch (desc->env_kind) {
 #define GCBF_RP_CASE(K)                                                                                               \
     case K: {                                                                                                         \

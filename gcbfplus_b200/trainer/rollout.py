@@ -85,10 +85,13 @@ class RolloutEngine:
         self.infer_blob = torch.zeros(int(env.lib.gcbf_infer_count(env.edge_dim, nu)), dtype=f32, device=dev)
         self.use_tc = 1 if _lib.USE_TC else 0
         # persistent single-launch rollout (csrc/rollout_persist.cu) where the library supports the configuration
-        ok = (policy == "actor" and self.use_tc and len(self.chains) == 1 and
-              bool(env.lib.gcbf_rollout_persistent_supported(C.byref(self.desc))))
+        level = int(env.lib.gcbf_rollout_persistent_supported(C.byref(self.desc))) \
+            if (policy == "actor" and self.use_tc and len(self.chains) == 1) else 0
+        ok = level > 0
         if persistent is None:
-            persistent = ok and os.environ.get("GCBF_PERSISTENT", "1") != "0"
+            # default only where every environment's cluster is resident at once (level 2): on a B200 at most 15
+            # clusters of 8 CTAs fit, so 16 environments of n = 512 would run in two rounds (measured: 134 vs 76 us / step)
+            persistent = level == 2 and os.environ.get("GCBF_PERSISTENT", "1") != "0"
         if persistent and not ok:
             raise ValueError("persistent rollout unsupported for this configuration (2-D env, n <= 512, tensor-core path, "
                              "actor policy, one chain)")

@@ -238,6 +238,9 @@ int32_t gcbf_rollout_step_select(const gcbf_env_desc* desc, const float* actor_p
  *   bits, end) -- the in-kernel profile bench.py reports (row 0 = the initial graph build); then [G][2] = start / end time
  *   of every environment's cluster (shows whether all clusters were co-resident). */
 int64_t gcbf_rollout_persistent_workspace_floats(const gcbf_env_desc* desc);
+/* 0: unsupported; 1: supported but the environments' clusters are not all co-resident on this device (measured on B200:
+ * at most 15 clusters of 8 CTAs -> 16 environments take two rounds, slower than gcbf_rollout_step); 2: supported and
+ * co-resident (the case callers should pick it for). */
 int32_t gcbf_rollout_persistent_supported(const gcbf_env_desc* desc);
 /* co-resident clusters of `cluster_size` CTAs of the persistent kernel on the current device (occupancy query) */
 int32_t gcbf_rollout_persistent_max_clusters(int32_t cluster_size);

@@ -165,3 +165,38 @@ def test_persistent_rollout_is_bit_identical_to_5_launch_path(env_id, N, E, area
             continue
         same = torch.equal(a, b) or bool(((a == b) | (torch.isnan(a.float()) & torch.isnan(b.float()))).all())
         assert same, (k, float((a.float() - b.float()).abs().nan_to_num().max()))
+
+
+def _persist_digest(n_agents=200, n_envs=2, T=8):
+    """sha256 of a persistent-kernel rollout's record (this or a child process)."""
+    import hashlib
+    from gcbfplus_b200.trainer.rollout import RolloutEngine
+    env, g0 = _reset_scene("DoubleIntegrator", n_agents, n_envs, 6.0, 8, seed=21)
+    algo = product_algo(env, "DoubleIntegrator")
+    eng = RolloutEngine(env, n_envs, T=T, n_obs=8, persistent=True)
+    eng.set_params(algo.actor_params)
+    eng.set_initial(g0.agent, g0.goal, g0.obstacle)
+    eng.run()
+    eng.run()
+    torch.cuda.synchronize()
+    h = hashlib.sha256()
+    for t in (eng.agent, eng.hits, eng.actions, eng.rewards, eng.costs, eng.counters[:, 0]):
+        h.update(t.cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def test_persistent_soft_groups_equal_hardware_clusters():
+    """The persistent kernel's two synchronisation modes -- hardware thread-block clusters (barrier.cluster + DSMEM) and
+    software groups of a cooperative launch (global arrival counters; what 16 environments x 8 CTAs need on a B200,
+    where only 15 such clusters are resident at once) -- must produce the same bits."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_rollout as t; "
+            "print('DIGEST', t._persist_digest())" % (here, os.path.dirname(here)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GCBF_PERSIST_SOFT="1"), capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    other = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0].split()[1]
+    assert other == _persist_digest()
