@@ -57,12 +57,16 @@ struct PArgs {
     int32_t *row_start, *row_deg, *edge_recv, *edge_src; // [2][...] double-buffered lists
     float *msg, *logit, *ag, *v1, *z;
     unsigned long long* prof;                            // optional [T + 1][8] %globaltimer stamps of cluster 0 / CTA 0 (ns)
-    // soft mode: no hardware cluster (B200 keeps at most 15 clusters of 8 CTAs resident, BASELINE's config has 16
-    // environments): the C CTAs of an environment are a software group of a cooperative launch, synchronised through
-    // a monotonic arrival counter in global memory; CTA edge totals are exchanged through `gtot` instead of DSMEM
-    int soft;
-    unsigned* gbar;                                      // [E] arrival counters (zeroed by the launcher)
-    int* gtot;                                           // [E][8]
+    // mode 0: one hardware cluster of C CTAs per environment (every barrier is barrier.cluster).
+    // mode 1 ("pairs"): B200 keeps at most 15 clusters of 8 CTAs resident and BASELINE's config has 16 environments, so
+    // the C CTAs of an environment are C/2 hardware clusters of 2.  A pair owns 2 APC consecutive agents, their edge
+    // rows (its own segment of the environment's edge lists), their edge tiles and their agent tile: the phases
+    // E -> A -> U1 -> U2 and the graph build only need pair barriers (barrier.cluster, DSMEM for the row prefix);
+    // the one environment-wide dependency -- the policy tail needs every agent's next state -- is a software barrier
+    // (arrival counter in global memory) once per step.
+    int soft;                                            // 0 / 1 = mode
+    unsigned* gbar;                                      // [E] arrival counters of the environment barrier (zeroed by the launcher)
+    int* gtot;                                           // [E][8] (unused since the pair mode; kept for the layout)
 };
 
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
@@ -148,8 +152,8 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 3 * STG + 256);
     int* s_tot = reinterpret_cast<int*>(smem + 3 * STG + 256 + 16);       // [8] CTA edge totals of the cluster
     float* sW = reinterpret_cast<float*>(smem + 3 * STG + 512);            // [(ED + 3)][256]
-    float* spos = sW + 7 * 256;                                            // [N][2]
-    float* sobs = spos + MAX_N * 2;                                        // [O][24]
+    float* sst = sW + 7 * 256;                                             // [N][SD] states of all agents of the environment
+    float* sobs = sst + MAX_N * 4;                                         // [O][24]
     float* stab = sobs + MAX_OBS * OBS2;                                   // [32][2]
     unsigned* sbits = reinterpret_cast<unsigned*>(stab + 64);              // [APC][n_words]
     int* s_off = reinterpret_cast<int*>(sbits + 64 * 16);                  // [APC + 1]
@@ -161,11 +165,17 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
     const int C = P.C;
     uint32_t rank_u;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
+    (void)rank_u;
     const bool soft = P.soft != 0;
-    const int rank = soft ? (int)(blockIdx.x % C) : (int)rank_u;
+    const int rank = (int)(blockIdx.x % C);          // CTA inside the environment
     const int env = blockIdx.x / C;
-    unsigned n_sync = 0;          // group barriers passed so far (soft mode: arrival target = n_sync * C)
-#define GROUP_SYNC()                                                   \
+    const int L = soft ? 2 : C;                      // CTAs per LOCAL group = hardware cluster size
+    const int lrank = rank % L, grp = rank / L;      // (cluster rank, group inside the environment)
+    unsigned n_sync = 0;          // environment barriers passed so far (pair mode: arrival target = n_sync * C)
+    // SYNC_LOCAL: barrier of the hardware cluster (the CTAs that share edge rows / agent tiles).
+    // SYNC_ENV: all C CTAs of the environment (mode 0: the same cluster barrier; pair mode: software barrier).
+#define SYNC_LOCAL() cluster_sync_all()
+#define SYNC_ENV()                                                     \
     do {                                                               \
         if (soft) {                                                    \
             ++n_sync;                                                  \
@@ -181,6 +191,9 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
     const int n_words = (N + 31) / 32;
     const size_t env_e0 = (size_t)env * cap;          // first edge slot of this environment
     const int env_a0 = env * N;                       // first global agent id
+    const int seg_cap = cap / (C / L);                // edge rows of one local group (mode 0: the whole environment)
+    const int seg_off = grp * seg_cap;                // ... and where they start inside the environment's lists
+    const int ga_lo = min(grp * L * APC, N), ga_hi = min(ga_lo + L * APC, N);   // agents of my local group
 
     // ---------------------------------------------------------------- one-time setup
     if (tid == 0) {
@@ -236,8 +249,8 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
     uint32_t it = 0;      // k-blocks pushed through the 3-stage ring so far (all roles advance it identically)
     uint32_t ne = 0;      // edge tiles this CTA has processed (chain barriers)
     uint32_t n0 = 0;      // uses of accumulator 0 (edge tiles + U1 / U2 items)
-    int M_cur = 0;        // edges of the current graph of this environment
-    GROUP_SYNC();
+    int M_cur = 0;        // edge rows of my local group's segment in the current graph
+    SYNC_LOCAL();
     if (P.prof != nullptr && rank == 0 && tid == 0) P.prof[(size_t)(P.T + 1) * 8 + 2 * env] = gtime();   // cluster start
 
     // =================================================================================================
@@ -254,12 +267,13 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
         if (stamp) pr[0] = gtime();
         if (t >= 0) {
             // ============================================================ phase E: edge tiles
-            const int n_tiles = (M_cur + BM - 1) / BM;
-            const int my_tiles = (n_tiles > rank) ? (n_tiles - rank + C - 1) / C : 0;
+            const int n_tiles = (M_cur + BM - 1) / BM;                  // tiles of my group's edge segment
+            const int my_tiles = (n_tiles > lrank) ? (n_tiles - lrank + L - 1) / L : 0;
+            const size_t seg_e0 = env_e0 + seg_off;                      // first slot of the segment
             if (warp == 0) {
                 if (lane == 0) {
                     uint32_t it_l = it, ne_l = ne, n0_l = n0;
-                    for (int tile = rank; tile < n_tiles; tile += C, ++ne_l, ++n0_l) {
+                    for (int tile = lrank; tile < n_tiles; tile += L, ++ne_l, ++n0_l) {
                         if (ne_l > 0) mbar_wait_wd(&bars[B_T2F], (ne_l - 1) & 1);
                         for (int kb = 0; kb < 8; ++kb, ++it_l) {
                             const int s = it_l % 3;
@@ -283,7 +297,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
             } else if (warp == 1) {
                 if (lane == 0) {
                     uint32_t it_l = it, ne_l = ne, n0_l = n0;
-                    for (int tile = rank; tile < n_tiles; tile += C, ++ne_l, ++n0_l) {
+                    for (int tile = lrank; tile < n_tiles; tile += L, ++ne_l, ++n0_l) {
                         mbar_wait_wd(&bars[B_TE0], (n0_l & 1) ^ 1);
                         tc_fence_after();
                         for (int kb = 0; kb < 8; ++kb, ++it_l) {
@@ -325,7 +339,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 const int chalf = (warp - 2) >> 2;        // epilogue: message columns [64 chalf, 64 chalf + 64)
                 const int row = quarter * 32 + lane;
                 uint32_t it_l = it, ne_l = ne, n0_l = n0;
-                for (int tile = rank; tile < n_tiles; tile += C, ++ne_l, ++n0_l) {
+                for (int tile = lrank; tile < n_tiles; tile += L, ++ne_l, ++n0_l) {
                     {
                         const int ml = tile * BM + r;
                         const bool row_ok = ml < M_cur;
@@ -335,11 +349,14 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
 #pragma unroll
                         for (int c = 0; c < ED; ++c) f[c] = 0.f;
                         if (row_ok) {
-                            const int a = min(max(er_t[env_e0 + ml], 0), A_tot - 1);
-                            const int code = min(es_t[env_e0 + ml], A_tot - 1);
+                            const int a = min(max(er_t[seg_e0 + ml], env_a0), env_a0 + N - 1);
+                            const int code = min(es_t[seg_e0 + ml], env_a0 + N - 1);
                             float er[ED], es[ED], coef, nrm;
-                            edge_state_dev<KIND>(agent_t + (size_t)a * SD, er);
-                            sender_state_dev<KIND>(code, a, R, agent_t, P.goal, hits_t, es);
+                            // agent states come from the CTA's own copy of the environment's states (the values the
+                            // record holds; no dependence on another CTA's global stores)
+                            edge_state_dev<KIND>(sst + (size_t)(a - env_a0) * SD, er);
+                            if (code >= 0) edge_state_dev<KIND>(sst + (size_t)(max(code, env_a0) - env_a0) * SD, es);
+                            else sender_state_dev<KIND>(code, a, R, agent_t, P.goal, hits_t, es);
                             edge_feat_dev<KIND>(er, es, code == -1, d.comm_radius, f, &coef, &nrm);
                             stype = (code >= 0) ? 2 : ((code == -1) ? 1 : 0);
                         }
@@ -384,7 +401,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
                         uint8_t* hi_row = smem + (c0 >> 5) * 32768 + row * 128;
                         uint8_t* lo_row = hi_row + 16384;
-                        float* crow = P.msg + (env_e0 + ml) * 128 + c0;
+                        float* crow = P.msg + (seg_e0 + ml) * 128 + c0;
                         float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -423,7 +440,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                             for (int j = 0; j < 32; ++j)
                                 dot = fmaf(fmaxf(__uint_as_float(v[j]) + P.bias_g[c0 + j], 0.f), P.avec[c0 + j], dot);
                         }
-                        if (ml < M_cur) P.logit[env_e0 + ml] = dot + P.cst[0];
+                        if (ml < M_cur) P.logit[seg_e0 + ml] = dot + P.cst[0];
                         tc_fence_before();
                         mbar_arrive(&bars[B_TE1]);
                     }
@@ -432,7 +449,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
             it += 8u * my_tiles;
             ne += my_tiles;
             n0 += my_tiles;
-            GROUP_SYNC();
+            SYNC_LOCAL();
             if (stamp) pr[1] = gtime();
 
             // ============================================================ phase A: segment softmax + aggregate
@@ -488,12 +505,13 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 *reinterpret_cast<float4*>(P.ag + (size_t)a * 128 + lane * 4) = acc;
             }
             fence_async_global();          // generic-proxy writes of AG -> TMA (async proxy) reads in phase U1
-            GROUP_SYNC();
+            SYNC_LOCAL();
             if (stamp) pr[2] = gtime();
 
             // ============================================================ phases U1 / U2: agent-side GEMMs
-            const int n_items = ((N + BM - 1) / BM) * 2;               // (agent tile, 128-column half)
-            const int my_items = (n_items > rank) ? (n_items - rank + C - 1) / C : 0;
+            const int n_items = ((ga_hi - ga_lo + BM - 1) / BM) * 2;   // (agent tile of my group, 128-column half)
+            const int my_items = (n_items > lrank) ? (n_items - lrank + L - 1) / L : 0;
+            float* z_t = P.z + (size_t)(t & 1) * 2 * A_tot * 4;         // output partial sums, double-buffered by step parity
 #pragma unroll 1
             for (int ph2 = 0; ph2 < 2; ++ph2) {
                 const int nkb = ph2 == 0 ? 4 : 8;                      // K = 128 (update layer) / 256 (folded update/head)
@@ -504,8 +522,8 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                     if (lane == 0) {
                         uint32_t it_l = it;
                         fence_async_global();      // consumer side of the generic-store -> TMA-load hand-over (AG / V1)
-                        for (int item = rank; item < n_items; item += C) {
-                            const int m0 = (item >> 1) * BM, nc0 = (item & 1) * 128;
+                        for (int item = lrank; item < n_items; item += L) {
+                            const int m0 = ga_lo + (item >> 1) * BM, nc0 = (item & 1) * 128;
                             for (int kb = 0; kb < nkb; ++kb, ++it_l) {
                                 const int s = it_l % 3;
                                 mbar_wait_wd(&bars[B_EMPTY + s], ((it_l / 3) & 1) ^ 1);
@@ -520,7 +538,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 } else if (warp == 1) {
                     if (lane == 0) {
                         uint32_t it_l = it, n0_l = n0;
-                        for (int item = rank; item < n_items; item += C, ++n0_l) {
+                        for (int item = lrank; item < n_items; item += L, ++n0_l) {
                             mbar_wait_wd(&bars[B_TE0], (n0_l & 1) ^ 1);
                             tc_fence_after();
                             for (int kb = 0; kb < nkb; ++kb, ++it_l) {
@@ -544,7 +562,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                     const int chalf = (warp - 2) >> 2;
                     const int row = quarter * 32 + lane;
                     uint32_t it_l = it, n0_l = n0;
-                    for (int item = rank; item < n_items; item += C, ++n0_l) {
+                    for (int item = lrank; item < n_items; item += L, ++n0_l) {
                         for (int kb = 0; kb < nkb; ++kb, ++it_l) {
                             const int s = it_l % 3;
                             mbar_wait_wd(&bars[B_FULL + s], (it_l / 3) & 1);
@@ -565,7 +583,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                             fence_async_smem();
                             mbar_arrive(&bars[B_CONV + s]);
                         }
-                        const int m0 = (item >> 1) * BM, nc0 = (item & 1) * 128;
+                        const int m0 = ga_lo + (item >> 1) * BM, nc0 = (item & 1) * 128;
                         const int ml = m0 + row;                   // agent inside the environment
                         mbar_wait_wd(&bars[B_TF0], n0_l & 1);
                         tc_fence_after();
@@ -574,7 +592,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                             for (int c0 = chalf * 64; c0 < chalf * 64 + 64; c0 += 32) {
                                 uint32_t v[32];
                                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-                                if (ml < N) {
+                                if (ml < ga_hi) {
                                     const int n = nc0 + c0;
                                     float* crow = P.v1 + (size_t)(env_a0 + ml) * 256 + n;
 #pragma unroll
@@ -610,8 +628,8 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                                         if (q < NU) dq[q] = fmaf(h, hw[j * NU + q], dq[q]);
                                 }
                             }
-                            if (ml < N)
-                                *reinterpret_cast<float4*>(P.z + ((size_t)(item & 1) * A_tot + env_a0 + ml) * 4) =
+                            if (ml < ga_hi)
+                                *reinterpret_cast<float4*>(z_t + ((size_t)(item & 1) * A_tot + env_a0 + ml) * 4) =
                                     make_float4(dq[0], dq[1], dq[2], dq[3]);
                         }
                         tc_fence_before();
@@ -621,7 +639,8 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 it += (uint32_t)nkb * my_items;
                 n0 += my_items;
                 if (ph2 == 0) fence_async_global();   // V1 rows (generic stores) -> TMA reads of phase U2
-                GROUP_SYNC();
+                if (ph2 == 0) SYNC_LOCAL();
+                else SYNC_ENV();                      // the policy tail needs the output sums of EVERY agent
                 if (stamp) pr[3 + ph2] = gtime();
             }
         }
@@ -640,7 +659,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 for (int i = tid; i < N; i += PT) {
                     const float* a = agent_n + (size_t)(env_a0 + i) * SD;
 #pragma unroll
-                    for (int c = 0; c < PD; ++c) spos[i * PD + c] = a[c];
+                    for (int c = 0; c < SD; ++c) sst[i * SD + c] = a[c];
                 }
             } else {
                 // fused policy tail (geometry.cu graph_build_kernel): every CTA recomputes the next state of all N
@@ -651,14 +670,15 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 for (int i = tid; i < N; i += PT) {
                     const size_t a = (size_t)env_a0 + i;
                     float zz[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float* z_t = P.z + (size_t)(t & 1) * 2 * A_tot * 4;
                     for (int p = 0; p < 2; ++p) {
-                        const float4 v = *reinterpret_cast<const float4*>(P.z + ((size_t)p * A_tot + a) * 4);
+                        const float4 v = *reinterpret_cast<const float4*>(z_t + ((size_t)p * A_tot + a) * 4);
                         zz[0] += v.x; zz[1] += v.y; zz[2] += v.z; zz[3] += v.w;
                     }
                     float x[SD], gl[SD], ur[NU], u[NU], xn[SD];
 #pragma unroll
                     for (int c = 0; c < SD; ++c) {
-                        x[c] = agent_t[a * SD + c];
+                        x[c] = sst[i * SD + c];              // state t (== agent_t[a], this CTA's copy)
                         gl[c] = P.goal[a * SD + c];
                     }
                     u_ref_dev<KIND>(d, x, gl, ur);
@@ -673,7 +693,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                     }
                     euler_dev<KIND>(d, x, gl, u, xn);
 #pragma unroll
-                    for (int c = 0; c < PD; ++c) spos[i * PD + c] = xn[c];
+                    for (int c = 0; c < SD; ++c) sst[i * SD + c] = xn[c];
                     if (rec) {
 #pragma unroll
                         for (int c = 0; c < SD; ++c) agent_n[a * SD + c] = xn[c];
@@ -732,7 +752,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 const int ii = valid ? i : 0;
                 float p[PD];
 #pragma unroll
-                for (int c = 0; c < PD; ++c) p[c] = spos[ii * PD + c];
+                for (int c = 0; c < PD; ++c) p[c] = sst[ii * SD + c];
                 const size_t a_glob = (size_t)env_a0 + ii;
                 float* my_hits = hits_n + a_glob * R * PD;
                 if (valid) {
@@ -802,7 +822,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
 #pragma unroll 4
                     for (int w = 0; w < n_full; ++w) {
                         const int j = (w << 5) + lane;
-                        const float2 q = *reinterpret_cast<const float2*>(spos + j * 2);
+                        const float2 q = *reinterpret_cast<const float2*>(sst + j * SD);
                         const float dx = p[0] - q.x, dy = p[1] - q.y;
                         float acc = dx * dx;
                         acc = acc + dy * dy;
@@ -818,7 +838,7 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                             float acc = 0.f;
 #pragma unroll
                             for (int c = 0; c < PD; ++c) {
-                                const float dlt = p[c] - spos[j * PD + c];
+                                const float dlt = p[c] - sst[j * SD + c];
                                 acc = (c == 0) ? dlt * dlt : acc + dlt * dlt;
                             }
                             ok = acc < d.comm_sq_thr;
@@ -851,29 +871,28 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                 if (lane + 32 < APC) s_off[lane + 33] = tot0 + inc1;
                 __syncwarp();
                 const int total = s_off[APC];
-                if (soft) {
-                    if (lane == 0) P.gtot[env * 8 + rank] = total;
-                } else if (lane < C) {           // my total -> slot [rank] of every CTA of the cluster (DSMEM)
+                if (lane < L) {                  // my total -> slot [lrank] of every CTA of my hardware cluster (DSMEM)
                     uint32_t ra;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(&s_tot[rank])), "r"(lane));
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(&s_tot[lrank])), "r"(lane));
                     asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(total) : "memory");
                 }
             }
-            GROUP_SYNC();
+            SYNC_LOCAL();
             if (stamp) pr[6] = gtime();
-            int base = 0, env_total = 0;
-            for (int r2 = 0; r2 < C; ++r2) {
-                const int v = soft ? P.gtot[env * 8 + r2] : s_tot[r2];
-                base += (r2 < rank) ? v : 0;
+            int base = 0, env_total = 0;         // (rows before mine, rows of my local group's segment)
+            for (int r2 = 0; r2 < L; ++r2) {
+                const int v = s_tot[r2];
+                base += (r2 < lrank) ? v : 0;
                 env_total += v;
             }
             // ---- fill pass: rows [goal | agents ascending | active hits ascending], agent order inside the environment
             for (int slot = warp; slot < n_slots; slot += PW) {
                 const int i = a_lo + slot;
                 const int a_id = env_a0 + i;
-                const int rbase = base + s_off[slot];
                 const int deg = s_off[slot + 1] - s_off[slot];
-                if (rbase + deg > cap) {
+                const bool over = base + s_off[slot] + deg > seg_cap;
+                const int rbase = seg_off + base + s_off[slot];       // row offset inside the environment's lists
+                if (over) {
                     if (lane == 0) {
                         atomicOr(&P.counters[(size_t)tn * 4 + 1], 1);
                         rs_n[a_id] = 0;
@@ -909,13 +928,14 @@ rollout_persist_kernel(const __grid_constant__ PArgs P, const __grid_constant__ 
                     es[e] = -2 - lane;
                 }
             }
-            if (rank == 0 && tid == 0) atomicAdd(&P.counters[(size_t)tn * 4 + 0], min(env_total, cap));
-            M_cur = min(env_total, cap);
-            GROUP_SYNC();
+            if (lrank == 0 && tid == 0) atomicAdd(&P.counters[(size_t)tn * 4 + 0], min(env_total, seg_cap));
+            M_cur = min(env_total, seg_cap);
+            SYNC_LOCAL();
             if (stamp) pr[7] = gtime();
         }
     }
-#undef GROUP_SYNC
+#undef SYNC_LOCAL
+#undef SYNC_ENV
     if (P.prof != nullptr && rank == 0 && tid == 0) P.prof[(size_t)(P.T + 1) * 8 + 2 * env + 1] = gtime();   // cluster end
     tc_fence_before();
     __syncthreads();
@@ -936,7 +956,7 @@ static WsLayout make_ws_layout(int E, int N, int cap_env) {   // (+ 16 (T + 1) f
     W.logit = take(EC);
     W.ag = take(A * 128 + 128 * 128);      // + one tile of slack: the last environment's row tile may overhang
     W.v1 = take(A * 256 + 128 * 256);
-    W.z = take(2 * A * 4);
+    W.z = take(2 * 2 * A * 4);             // [step parity][column half][A][4]
     W.row_start = take(2 * A);
     W.row_deg = take(2 * A);
     W.edge_recv = take(2 * EC);
@@ -981,13 +1001,17 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persisten
         const int n = gcbf_rollout_persistent_max_clusters(C);
         cached[C] = n > 0 ? n : -1;
     }
-    if (cached[C] > 0 && desc->n_graphs <= cached[C]) return 2;          // hardware clusters, all resident
-    if (desc->n_graphs * C <= sm_count()) return 2;                       // software groups of a cooperative launch
+    if (cached[C] > 0 && desc->n_graphs <= cached[C]) return 2;          // one hardware cluster per environment, all resident
+    if (cached[2] == 0) {
+        const int n = gcbf_rollout_persistent_max_clusters(2);
+        cached[2] = n > 0 ? n : -1;
+    }
+    if (C >= 2 && desc->n_graphs * C <= sm_count() && desc->n_graphs * (C / 2) <= cached[2]) return 2;   // pair mode
     return 1;
 }
 
 static int persist_smem_bytes() {
-    return 3 * rp::STG + 512 + 7 * 256 * 4 + rp::MAX_N * 2 * 4 + rp::MAX_OBS * 24 * 4 + 64 * 4 + 64 * 16 * 4 + 72 * 4 + 64 * 4 +
+    return 3 * rp::STG + 512 + 7 * 256 * 4 + rp::MAX_N * 4 * 4 + rp::MAX_OBS * 24 * 4 + 64 * 4 + 64 * 16 * 4 + 72 * 4 + 64 * 4 +
            3 * rp::PW * 4 + 1024;
 }
 
@@ -1046,11 +1070,13 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persisten
     P.cap_env = cap_env;
     P.C = rp::cluster_size(N, cap_env);
     const int max_cl = gcbf_rollout_persistent_max_clusters(P.C);
-    // hardware clusters when every environment's cluster is resident at once; otherwise (B200: 16 environments x 8 CTAs,
-    // 15 clusters fit) software groups of a cooperative launch when the grid fits on the device (1 CTA / SM)
+    // mode 0: one hardware cluster per environment when all of them are resident at once; otherwise (B200: 16 environments
+    // x 8 CTAs, 15 such clusters fit) mode 1: clusters of 2 + one software barrier per step, when the grid fits on the
+    // device (1 CTA / SM).  GCBF_PERSIST_SOFT=1 forces mode 1 (tests).
     static const int force_soft = [] { const char* e = getenv("GCBF_PERSIST_SOFT"); return e ? atoi(e) : -1; }();
-    P.soft = (force_soft >= 0) ? force_soft : ((E <= max_cl) ? 0 : ((E * P.C <= sm_count()) ? 1 : 0));
-    GCBF_REQUIRE(!P.soft || E * P.C <= sm_count(), "soft persistent mode needs n_graphs * %d <= %d CTAs", P.C, sm_count());
+    P.soft = (force_soft >= 0) ? (force_soft != 0) : ((E <= max_cl) ? 0 : 1);
+    GCBF_REQUIRE(!P.soft || (P.C >= 2 && E * P.C <= sm_count()), "pair mode needs n_graphs * %d <= %d CTAs", P.C, sm_count());
+    GCBF_REQUIRE(P.soft || E <= max_cl || force_soft == 0, "more environments (%d) than resident clusters (%d)", E, max_cl);
     P.gbar = reinterpret_cast<unsigned*>(workspace + W.gbar);
     P.gtot = reinterpret_cast<int*>(workspace + W.gtot);
     P.W1 = actor_params + L.w[L_MSG0];
@@ -1104,18 +1130,22 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_rollout_persisten
     cfg.blockDim = dim3(rp::PT, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    if (P.soft) {
-        attr[0].id = cudaLaunchAttributeCooperative;      // co-residency of the whole grid is guaranteed or the launch fails
-        attr[0].val.cooperative = 1;
-    } else {
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)P.C;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-    }
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)(P.soft ? 2 : P.C);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // pair mode spins on a counter the other CTAs of the environment must reach: every CTA has to be resident.  The grid
+    // was checked against the SM count (1 CTA / SM) and the cluster-of-2 occupancy above; GCBF_PERSIST_COOP=1 additionally
+    // asks the driver to guarantee it (cooperative launch attribute).  A protocol failure ends in a trap, not a hang.
+    static const bool coop = [] { const char* e = getenv("GCBF_PERSIST_COOP"); return e && e[0] == '1'; }();
+    if (P.soft && coop) {
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.numAttrs = 2;
+    }
     cudaError_t e = cudaSuccess;
     if (P.soft && (e = cudaMemsetAsync(P.gbar, 0, sizeof(unsigned) * E, (cudaStream_t)stream)) != cudaSuccess) {
         set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
