@@ -133,7 +133,10 @@ def test_chained_gate_gemm_is_bit_identical_to_separate_launch():
 @pytest.mark.parametrize("env_id,N,E,area,n_obs,T", [("DoubleIntegrator", 48, 3, 3.0, 6, 12), ("SingleIntegrator", 8, 16, 4.0, 0, 40),
                                                       ("DubinsCar", 12, 2, 2.0, 4, 24), ("DoubleIntegrator", 200, 2, 6.0, 8, 8),
                                                       ("DoubleIntegrator", 130, 1, 4.0, 3, 6),
-                                                      ("DoubleIntegrator", 512, 3, 16.0, 8, 5)])
+                                                      ("DoubleIntegrator", 512, 3, 16.0, 8, 5),
+                                                      # BASELINE configs[2] shape: 16 environments x 8 CTAs do not fit as 16
+                                                      # hardware clusters of 8 on a B200 (15 resident) -> pair mode
+                                                      ("DoubleIntegrator", 512, 16, 32.0, 8, 4)])
 def test_persistent_rollout_is_bit_identical_to_5_launch_path(env_id, N, E, area, n_obs, T):
     """The single-launch persistent rollout (one thread-block cluster per environment, csrc/rollout_persist.cu) against
     the 5-launch env-step path: same operand splits, MMA order, epilogues and reduction orders -> the same bits for

@@ -30,7 +30,8 @@ def main():
     env.edge_cap_per_agent = 48
     algo = product_algo(env, env_id)
     g0 = env.reset(3, n_envs=E)
-    eng = RolloutEngine(env, E, T=T, n_obs=4, use_cuda_graph=False)
+    persistent = os.environ.get("GCBF_SANITIZE_PERSISTENT", "0") == "1"        # the single-launch rollout kernel instead
+    eng = RolloutEngine(env, E, T=T, n_obs=4, use_cuda_graph=False, persistent=persistent)
     eng.set_params(algo.actor_params)
     eng.set_initial(g0.agent, g0.goal, g0.obstacle)
     eng.run()
