@@ -392,13 +392,17 @@ def step_kernel_rooflines(torch, _lib, env, eng, cfg, n_edges: float, n_agents: 
     dom = max(range(5), key=lambda k: us[k])
     fl, by = work[dom]
     tensor = dom in (0, 2, 3)
-    achieved = fl / (us[dom] * 1e-6) / 1e12 if tensor else by / (us[dom] * 1e-6) / 1e9
-    peak = tf_burst if tensor else hbm
+    alu = dom == 4 and pd == 3          # 3-D ray cast (514 rays x O spheres per agent): fp32-ALU work, tiny bytes
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12      # SMs x lanes x FMA x max SM clock = 74.4 TFLOP/s
+    achieved = fl / (us[dom] * 1e-6) / 1e12 if (tensor or alu) else by / (us[dom] * 1e-6) / 1e9
+    peak = tf_burst if tensor else (fp32_peak if alu else hbm)
     traffic = load_traffic(dom)
-    return {"kernel": STEP_KERNELS[dom], "bound": "tensor" if tensor else "hbm", "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s" if tensor else "GB/s", "frac": achieved / peak,
+    return {"kernel": STEP_KERNELS[dom], "bound": "tensor" if tensor else ("fp32-alu" if alu else "hbm"), "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s" if (tensor or alu) else "GB/s", "frac": achieved / peak,
             "peak_source": src + (" bf16 cuBLAS burst (MEASURED_PEAKS.json; the kernel computes fp32-class results with "
-                                  "3 tf32 MMAs per product, so its own ceiling is 1/6 of this)" if tensor else " HBM copy"),
+                                  "3 tf32 MMAs per product, so its own ceiling is 1/6 of this)" if tensor else
+                                  (" -- no measured fp32 figure: 148 SMs x 128 lanes x 2 x 1.965 GHz (stated fallback)" if alu
+                                   else " HBM copy")),
             "us_per_launch": us[dom], "share_of_step": us[dom] / total,
             "algorithmic_flops": fl, "algorithmic_bytes": by, "traffic": traffic["bytes"] if traffic else None,
             "traffic_source": traffic["source"] if traffic else "no ncu capture of this build under profiles/ (null)",

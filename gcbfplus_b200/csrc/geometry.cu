@@ -38,6 +38,7 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
     float* salpha = stab + d.n_rays * PD;       // 3-D only: [GB_WARPS, n_rays]
     const int n_words = (N + 31) / 32;
     unsigned* sbits = reinterpret_cast<unsigned*>(salpha + (PD == 3 ? GB_WARPS * d.n_rays : 0));  // [GB_WARPS, n_words]
+    int* stk = reinterpret_cast<int*>(sbits + GB_WARPS * n_words);                                 // 3-D only: [GB_WARPS, 80] top-k scratch
     __shared__ int s_off[GB_WARPS + 1];
     __shared__ int s_base;
 
@@ -238,8 +239,63 @@ graph_build_kernel(const gcbf_env_desc d, const float* __restrict__ agent, const
                 al[r] = alpha;
             }
             __syncwarp();
-            // R rounds of stable arg-min with removal == argsort(alpha)[:R]
-            for (int rank = 0; rank < R; ++rank) {
+            // ---- argsort(alpha)[:R] (env/utils.py:127-131), stable.  Almost every ray misses (alpha == 1e6 exactly) and
+            // argsort is stable, so the result is [the few real returns sorted by (alpha, ray)] followed by the first
+            // missing rays in ray order.  Fast path (measured: the R-round arg-min below was more than half of this kernel
+            // at 514 rays): if at most 32 rays have alpha < 1e6 and no alpha is NaN / above 1e6, compact those rays, sort
+            // them with one 32-key warp sort and fill up with the lowest-index misses -- the same permutation.
+            bool fast = false;
+            if (R <= 32) {
+                int nA = 0;
+                bool odd = false;
+                for (int r = lane; r < d.n_rays; r += 32) {
+                    const float a = al[r];
+                    odd = odd || !(a <= NO_HIT);            // NaN or above the miss value: leave it to the general path
+                    nA += (a < NO_HIT) ? 1 : 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) nA += __shfl_xor_sync(0xffffffffu, nA, o);
+                fast = !__any_sync(0xffffffffu, odd) && nA <= 32 && (d.n_rays - nA) >= R;
+                if (fast) {
+                    int* tk = stk + warp * 80;              // [0,32) ray of a return, [32,64) its alpha bits, [64,80) first misses
+                    const unsigned lt = (1u << lane) - 1u;
+                    int nret = 0, nmiss = 0;
+                    for (int r0 = 0; r0 < d.n_rays; r0 += 32) {
+                        const int r = r0 + lane;
+                        const float a = (r < d.n_rays) ? al[r] : NO_HIT;
+                        const bool is_ret = (r < d.n_rays) && (a < NO_HIT);
+                        const bool is_miss = (r < d.n_rays) && !(a < NO_HIT);
+                        const unsigned rb = __ballot_sync(0xffffffffu, is_ret), mb = __ballot_sync(0xffffffffu, is_miss);
+                        if (is_ret) {
+                            const int pos = nret + __popc(rb & lt);
+                            tk[pos] = r;
+                            tk[32 + pos] = __float_as_int(a);
+                        }
+                        if (is_miss) {
+                            const int pos = nmiss + __popc(mb & lt);
+                            if (pos < 16) tk[64 + pos] = r;
+                        }
+                        nret += __popc(rb);
+                        nmiss += __popc(mb);
+                    }
+                    __syncwarp();
+                    SortKey k;
+                    k.flag = (lane < nret) ? 0 : 2;
+                    k.alpha = (lane < nret) ? __int_as_float(tk[32 + lane]) : 0.f;
+                    k.idx = (lane < nret) ? tk[lane] : (0x40000000 + lane);
+                    if (nret > 1) k = warp_sort32(k, lane);
+                    if (lane < R) {
+                        const int r = (lane < nret) ? k.idx : tk[64 + min(lane - nret, 15)];
+                        const float a = (lane < nret) ? k.alpha : NO_HIT;
+                        const float x2 = x1 + stab[r * PD + 0], y2 = y1 + stab[r * PD + 1], z2 = z1 + stab[r * PD + PD - 1];
+                        my_hits[lane * PD + 0] = x1 + (x2 - x1) * a;
+                        my_hits[lane * PD + 1] = y1 + (y2 - y1) * a;
+                        my_hits[lane * PD + PD - 1] = z1 + (z2 - z1) * a;
+                    }
+                }
+            }
+            // general path: R rounds of stable arg-min with removal
+            for (int rank = 0; rank < (fast ? 0 : R); ++rank) {
                 SortKey best;
                 best.flag = 3;
                 best.alpha = 0.f;
@@ -663,7 +719,7 @@ int32_t gcbf::graph_build_impl(const gcbf_env_desc* desc, const float* agent, co
     const int obw = pd == 2 ? 16 : 4;
     const size_t smem = sizeof(float) * ((size_t)desc->n_agents * pd + (size_t)desc->n_obs * (pd == 2 ? 24 : 4) +
                                          (size_t)desc->n_rays * pd + (pd == 3 ? (size_t)GB_WARPS * desc->n_rays : 0) +
-                                         (size_t)GB_WARPS * ((desc->n_agents + 31) / 32));
+                                         (size_t)GB_WARPS * ((desc->n_agents + 31) / 32) + (pd == 3 ? (size_t)GB_WARPS * 80 : 0));
     GCBF_REQUIRE(smem <= 200 * 1024, "graph_build needs %zu B shared memory (> 200 KB): too many agents/obstacles", smem);
     if (!(flags & 4)) {   // bit 2: the caller's previous kernel already cleared counters[0]
         cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t), st);
