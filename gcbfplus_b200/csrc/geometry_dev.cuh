@@ -69,6 +69,11 @@ __device__ __forceinline__ float sphere_raytrace(const float* ob, float x1, floa
     float B = 2.f * (dx * ex + dy * ey + dz * ez);
     float C = ex * ex + ey * ey + ez * ez - ob[3] * ob[3];
     float delta = B * B - 4.f * A * C;
+    // the line misses the sphere (the common case: 4 small spheres, 514 rays): valid1 = 0 makes both roots
+    // (-B -+ 0) / (2A) * 0 + 1 = 1 exactly (finite operands), alphas = 1 and the result 0 * 1 + 1 * 1e6 = 1e6 -- returned
+    // directly, skipping the square root and the two divisions (identical bits; NaN inputs fail `delta < 0` and take the
+    // full path)
+    if (delta < 0.f && A > 1e-20f && fabsf(B) < 1e18f) return NO_HIT;
     float valid1 = (delta >= 0.f) ? 1.f : 0.f;
     float sq = sqrtf(delta * valid1);
     float alpha1 = (-B - sq) / (2.f * A) * valid1 + (1.f - valid1);
