@@ -2,7 +2,7 @@
 
 ``python -m gcbfplus_b200.build`` or ``gcbfplus_b200.build.build()``.  The shared library
 lands in gcbfplus_b200/lib/ (git-ignored, shipped to the GPU box by gpurun).
-geometry.cu is compiled with -fmad=false (bit-exact index / mask work).
+All CUDA units are compiled with -fmad=false (bit-exact index / mask work, one numeric path).
 """
 from __future__ import annotations
 
@@ -17,12 +17,16 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgcbf_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+# Every unit is compiled with -fmad=false: geometry.cu / rollout_persist.cu need one rounding per operation for the
+# bit-exact LiDAR / index / mask work, and the others share device functions with them (edge features: sinf / cosf of
+# the DubinsCar heading are inlined under the translation unit's contraction setting, so mixed settings made the
+# persistent kernel and the 5-launch path differ in the last bit).  The GEMM-side hot loops use explicit fmaf.
 UNITS = {  # translation unit -> extra flags
     "api.cu": [],
     "geometry.cu": ["-fmad=false"],
-    "gnn.cu": [],
+    "gnn.cu": ["-fmad=false"],
     "rollout_persist.cu": ["-fmad=false"],
-    "train.cu": [],
+    "train.cu": ["-fmad=false"],
 }
 
 

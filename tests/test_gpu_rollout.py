@@ -141,7 +141,7 @@ def test_persistent_rollout_is_bit_identical_to_5_launch_path(env_id, N, E, area
     """The single-launch persistent rollout (one thread-block cluster per environment, csrc/rollout_persist.cu) against
     the 5-launch env-step path: same operand splits, MMA order, epilogues and reduction orders -> the same bits for
     states, LiDAR hits, actions, rewards, costs and per-step edge counts (dense scenes: several edge tiles per CTA,
-    ragged last tiles, N not a multiple of the cluster size).  DubinsCar: equal to closed-loop rounding (see below)."""
+    ragged last tiles, N not a multiple of the cluster size)."""
     from gcbfplus_b200.trainer.rollout import RolloutEngine
     env, g0 = _reset_scene(env_id, N, E, area, n_obs, seed=21)
     algo = product_algo(env, env_id)
@@ -159,13 +159,8 @@ def test_persistent_rollout_is_bit_identical_to_5_launch_path(env_id, N, E, area
         assert eng.launches_per_run == (1 if persistent else 1 + 5 * T)
     for k in outs[0]:
         a, b = outs[0][k], outs[1][k]
-        if env_id == "DubinsCar" and k != "n_edges":
-            # the heading enters the edge features through sinf / cosf, which nvcc inlines under each translation
-            # unit's own contraction setting (rollout_persist.cu is -fmad=false, gnn.cu is not): last-bit differences
-            # in (v cos th, v sin th), amplified by the closed loop (measured 1.6e-5 after 24 steps)
-            if k != "hits":          # (missed rays sit 1e6 ranges away: their ulp is 0.03)
-                assert float((a.float() - b.float()).abs().nan_to_num().max()) <= 2e-4, k
-            continue
+        # (DubinsCar used to differ in the last bit: sinf / cosf of the heading are inlined under each translation
+        #  unit's contraction setting; since every unit is compiled with -fmad=false the two paths agree exactly)
         same = torch.equal(a, b) or bool(((a == b) | (torch.isnan(a.float()) & torch.isnan(b.float()))).all())
         assert same, (k, float((a.float() - b.float()).abs().nan_to_num().max()))
 
