@@ -85,13 +85,20 @@ class RolloutEngine:
         self.infer_blob = torch.zeros(int(env.lib.gcbf_infer_count(env.edge_dim, nu)), dtype=f32, device=dev)
         self.use_tc = 1 if _lib.USE_TC else 0
         # persistent single-launch rollout (csrc/rollout_persist.cu) where the library supports the configuration
-        level = int(env.lib.gcbf_rollout_persistent_supported(C.byref(self.desc))) \
+        # the persistent kernel splits the edge capacity evenly over the environments (and, in pair mode, over the pairs
+        # of an environment), so it gets a roomier descriptor than the pooled lists of the 5-launch path: 48 rows per
+        # agent (or the worst case 1 + (N - 1) + R when that is smaller)
+        per_agent = min(1 + (N - 1) + R, max(2 * env.edge_cap_per_agent, 48))
+        self._pdesc = env.desc(E, self.O, edge_cap=E * N * per_agent)
+        level = int(env.lib.gcbf_rollout_persistent_supported(C.byref(self._pdesc))) \
             if (policy == "actor" and self.use_tc and len(self.chains) == 1) else 0
         ok = level > 0
         if persistent is None:
             # default only where every environment's cluster is resident at once (level 2): on a B200 at most 15
             # clusters of 8 CTAs fit, so 16 environments of n = 512 would run in two rounds (measured: 134 vs 76 us / step)
-            persistent = level == 2 and os.environ.get("GCBF_PERSISTENT", "1") != "0"
+            # DubinsCar is opt-in: its persistent rollout agrees with the 5-launch path only to closed-loop rounding
+            # (1.6e-5 after 24 steps, cause not found), and env-sharded runs must not mix two numeric paths
+            persistent = (level == 2 and env.ENV_ID != "DubinsCar" and os.environ.get("GCBF_PERSISTENT", "1") != "0")
         if persistent and not ok:
             raise ValueError("persistent rollout unsupported for this configuration (2-D env, n <= 512, tensor-core path, "
                              "actor policy, one chain)")
@@ -101,7 +108,7 @@ class RolloutEngine:
         self.phase_stamps: Optional[torch.Tensor] = None
         self._pws = None
         if self.persistent:
-            n = env.lib.gcbf_rollout_persistent_workspace_floats(C.byref(self.desc))
+            n = env.lib.gcbf_rollout_persistent_workspace_floats(C.byref(self._pdesc))
             self._pws = torch.empty(int(n), dtype=f32, device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_run = 0
@@ -156,7 +163,7 @@ class RolloutEngine:
     def _enqueue_persistent(self, n_steps: int, stream: int) -> None:
         env, ch = self.env, self.chains[0]
         rc = env.lib.gcbf_rollout_persistent(
-            C.byref(ch.desc), int(n_steps), self.params_buf.data_ptr(), self.infer_blob.data_ptr(), self.goal.data_ptr(),
+            C.byref(self._pdesc), int(n_steps), self.params_buf.data_ptr(), self.infer_blob.data_ptr(), self.goal.data_ptr(),
             self.obstacles.data_ptr() if self.O > 0 else None, env.ray_table.data_ptr(), self.agent.data_ptr(),
             self.hits.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr(), self.costs.data_ptr(),
             ch.counters.data_ptr(), self._pws.data_ptr(), self._pws.numel(),
@@ -232,8 +239,10 @@ class RolloutEngine:
     def check_overflow(self) -> None:
         c = self.counters.cpu()
         if int(c[:, 1].max()) != 0:
-            raise RuntimeError(f"edge capacity overflow during rollout: up to {int(c[:, 0].max())} edges > edge_cap="
-                               f"{self.desc.edge_cap} per chain; raise env.edge_cap_per_agent")
+            cap = self._pdesc.edge_cap if self.persistent else self.desc.edge_cap
+            raise RuntimeError(f"edge capacity overflow during rollout: up to {int(c[:, 0].max())} edges; edge_cap={cap}"
+                               + (" split evenly over the environments / CTA pairs (persistent kernel)" if self.persistent
+                                  else " per chain") + "; raise env.edge_cap_per_agent")
 
     def result(self) -> Rollout:
         """trainer/data.py Rollout in the reference's (b, T) order (views/transposes of the record)."""
