@@ -13,6 +13,10 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))
 
 
+def _say(rank, msg):
+    print(f"[rank {rank}] {msg}", flush=True)
+
+
 def main(out_path):
     from helpers import product_algo, product_env, product_obstacles, random_scene
     from gcbfplus_b200 import dist as gd
@@ -32,6 +36,7 @@ def main(out_path):
     unsafe = env.unsafe_mask(full)
     safe = (~unsafe) & torch.from_numpy(rng.uniform(size=(B, N)) < 0.6).to(dev)
     u_qp = env.u_ref(full) + 0.1
+    _say(rank, "scene ready")
     # --- reference: full minibatch on this GPU, collectives disabled
     T._dist = lambda: None
     ts = T.train_minibatch(algo, full, safe, unsafe, u_qp, apply=False)
@@ -56,6 +61,7 @@ def main(out_path):
     torch.distributed.all_reduce(pmax, op=torch.distributed.ReduceOp.MAX)
     torch.distributed.all_reduce(pmin, op=torch.distributed.ReduceOp.MIN)
     same = bool(torch.equal(pmax, pmin))
+    _say(rank, f"sharded eager step done (grad err {err:.2e})")
     # --- the captured optimizer step (algo/train.py MinibatchRunner): gather + graph build + train step + the packed
     # all-reduce INSIDE one CUDA graph, label counts all-reduced once for the "epoch"; 4 steps (eager warm-up, capture,
     # 2 replays) must leave identical parameters on every rank
@@ -68,9 +74,10 @@ def main(out_path):
     den = T._minibatch_counts(batch, torch.arange(B, device=dev), np.array([lo, hi]))
     torch.distributed.all_reduce(den)
     before = algo.cbf_params.flat.clone()
-    for _ in range(4):
+    for i in range(4):
         runner.run(torch.arange(lo, hi, device=dev), den[0])
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        _say(rank, f"captured-step runner call {i} done")
     runner.graph.check_overflow()
     p2 = torch.cat([algo.cbf_params.flat, algo.actor_net_params.flat])
     p2max, p2min = p2.clone(), p2.clone()

@@ -28,8 +28,15 @@ def test_sharded_train_step_matches_single_gpu(tmp_path):
     out = str(tmp_path / "res.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mp_train_worker.py"), out]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, start_new_session=True)
+    try:
+        out_txt, _ = proc.communicate(timeout=420)
+    except subprocess.TimeoutExpired:
+        import signal
+        os.killpg(proc.pid, signal.SIGKILL)                 # exactly the process group this test started
+        out_txt, _ = proc.communicate()
+        raise AssertionError("multi-GPU worker timed out; output so far:\n" + out_txt[-4000:])
+    assert proc.returncode == 0, out_txt[-4000:]
     res = json.load(open(out))
     assert res["world"] == n and res["params_identical"]
     assert res["grad_err"] <= 1e-4 * res["grad_max"] + 1e-8, res
