@@ -251,6 +251,9 @@ def run_ours(args):
         }
         print(json.dumps(out))
     if world > 1:
+        import gc
+        gc.collect()                      # captured graphs holding NCCL kernels must be freed before the communicator
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
