@@ -96,8 +96,11 @@ class RolloutEngine:
         if persistent is None:
             # default only where every environment's cluster is resident at once (level 2): on a B200 at most 15
             # clusters of 8 CTAs fit, so 16 environments of n = 512 would run in two rounds (measured: 134 vs 76 us / step)
-            # DubinsCar is opt-in: its persistent rollout agrees with the 5-launch path only to closed-loop rounding
-            # (1.6e-5 after 24 steps, cause not found), and env-sharded runs must not mix two numeric paths
+            # DubinsCar is opt-in: its persistent rollout agrees with the 5-launch path only to closed-loop rounding.
+            # profiles/r02_dubins_persistent_vs_5launch.log: states and actions are identical while every speed is 0
+            # (step 0); from the first step with v != 0 a few policy outputs differ by 1-2 ulp (1.8e-7) -- the
+            # (v cos th, v sin th) edge features are evaluated in two translation units -- which the closed loop
+            # amplifies to 1.6e-5 after 24 steps.  Env-sharded runs must not mix two numeric paths.
             persistent = (level == 2 and env.ENV_ID != "DubinsCar" and os.environ.get("GCBF_PERSISTENT", "1") != "0")
         if persistent and not ok:
             raise ValueError("persistent rollout unsupported for this configuration (2-D env, n <= 512, tensor-core path, "

@@ -160,8 +160,10 @@ def test_persistent_rollout_is_bit_identical_to_5_launch_path(env_id, N, E, area
     for k in outs[0]:
         a, b = outs[0][k], outs[1][k]
         if env_id == "DubinsCar" and k != "n_edges":
-            # DubinsCar agrees to closed-loop rounding only (1.6e-5 after 24 steps; not a contraction-flag effect: all
-            # units are -fmad=false; cause not found) -> RolloutEngine does not pick the persistent kernel for it by default
+            # DubinsCar agrees to closed-loop rounding only: identical while all speeds are 0, then a few policy outputs
+            # differ by 1-2 ulp per step (profiles/r02_dubins_persistent_vs_5launch.log; the heading's sin / cos enter
+            # the edge features in two translation units) -> 1.6e-5 after 24 steps.  RolloutEngine therefore does not
+            # pick the persistent kernel for DubinsCar by default
             if k != "hits":          # (missed rays sit 1e6 ranges away: their ulp is 0.03)
                 assert float((a.float() - b.float()).abs().nan_to_num().max()) <= 2e-4, k
             continue
