@@ -57,3 +57,31 @@ def test_env_descriptor_thresholds_are_exact_fp32_images():
         cand.insert(0, np.nextafter(cand[0], np.float32(0), dtype=np.float32))
     for c in cand:
         assert (np.sqrt(np.float32(c)) < R) == (np.float32(c) < thr), (c, thr)
+
+
+def test_epoch_label_counts_match_a_per_minibatch_loop():
+    """algo/train.py _minibatch_counts: the (n_unsafe, n_safe, n_agents) triples of every minibatch of an epoch, computed
+    on the device without a loop (per-graph counts -> permutation -> cumulative sums at the np.array_split points), equal
+    the per-minibatch counts gcbf_plus.py:377,384 uses as denominators; and the counts of the two halves of every
+    minibatch (what two ranks hold) add up to it -- the identity behind ONE count all-reduce per epoch."""
+    from gcbfplus_b200.algo.train import _minibatch_counts
+    rng = np.random.default_rng(3)
+    n, N, n_mb = 53, 7, 5
+    batch = {"safe": torch.from_numpy((rng.uniform(size=(n, N)) < 0.5).astype(np.uint8)),
+             "unsafe": torch.from_numpy((rng.uniform(size=(n, N)) < 0.2).astype(np.uint8))}
+    idx = torch.from_numpy(rng.permutation(n))
+    splits = np.array_split(np.arange(n), n_mb)
+    bounds = np.concatenate([[0], np.cumsum([len(m) for m in splits])]).astype(np.int64)
+    got = _minibatch_counts(batch, idx, bounds)
+    assert got.shape == (n_mb, 4)
+    for i, mb in enumerate(splits):
+        sel = idx[torch.from_numpy(mb)]
+        want = [float(batch["unsafe"][sel].sum()), float(batch["safe"][sel].sum()), float(len(mb) * N), 0.0]
+        assert got[i].tolist() == want, (i, got[i].tolist(), want)
+    # shards: rank r holds graphs [lo_r, hi_r) of every minibatch's selection -> counts add up
+    for i, mb in enumerate(splits):
+        sel = idx[torch.from_numpy(mb)]
+        half = len(sel) // 2
+        parts = [_minibatch_counts({k: v[s] for k, v in batch.items()}, torch.arange(len(s)), np.array([0, len(s)]))
+                 for s in (sel[:half], sel[half:])]
+        assert torch.equal(parts[0][0] + parts[1][0], got[i])
