@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 # step-kernel index of bench.py STEP_KERNELS <- substring of the ncu kernel name
-MATCH = [(0, "gemm_tc_prod_kernel"), (1, "attn_aggregate_kernel"), (2, "gemm_tc_kernel<128, 1,"), (3, "gemm_tc_kernel<128, 5,"),
+TIME_US = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}
+MATCH = [(0, "edge_chain_kernel"), (0, "gemm_tc_prod_kernel"), (1, "attn_aggregate_kernel"), (2, "gemm_tc_kernel<128, 1,"), (3, "gemm_tc_kernel<128, 5,"),
          (4, "graph_build_kernel"), (5, "rollout_persist_kernel")]
 
 
@@ -33,7 +34,7 @@ def main(paths):
                 continue
             rd = float(r[ix["dram__bytes_read.sum"]]) * UNIT[units[ix["dram__bytes_read.sum"]]]
             wr = float(r[ix["dram__bytes_write.sum"]]) * UNIT[units[ix["dram__bytes_write.sum"]]]
-            dur = float(r[ix["gpu__time_duration.sum"]])
+            dur = float(r[ix["gpu__time_duration.sum"]]) * TIME_US.get(units[ix["gpu__time_duration.sum"]], 1.0)
             a = acc.setdefault(k, {"name": name.split("(")[0], "rd": [], "wr": [], "us": []})
             a["rd"].append(rd), a["wr"].append(wr), a["us"].append(dur)
     for k, a in acc.items():
