@@ -245,7 +245,8 @@ def run_ours(args):
                 "algorithmic_tflops_per_gpu": value / (N * E * world) * flop_step / 1e12 / world,
                 "note": f"whole rollout vs HBM ({cfg['B_alg']} B/agent-step) and achieved TFLOP/s per GPU counting the "
                         "reference's unfolded F_edge / F_node (SURVEY 8d); the path is latency-bound "
-                        f"({eng.launches_per_run // max(T, 1)} dependent single-wave launches per env-step), not HBM-bound"},
+                        f"({eng.launches_per_run} launch(es) per {T}-step rollout; a dependent chain of phases per "
+                        "env-step), not HBM-bound"},
             "train_step": train,
             "cpu_baseline": cpu,
         }
@@ -446,7 +447,8 @@ def persistent_roofline(torch, env, algo, g0, cfg, E, n_edges, n_agents, ms_roll
     d = (st[:, 1:] - st[:, :-1]).mean(axis=0) / 1e3                      # us per phase
     step_us = float((st[-1, 7] - st[0, 0]) / 1e3 / (len(st) - 1 + 1e-9)) if len(st) > 1 else float(d.sum())
     traffic = load_traffic(5)
-    return {"kernel": "rollout_persist_kernel (one launch = the whole T-step rollout; one 8-CTA cluster per environment)",
+    return {"kernel": "rollout_persist_kernel (one launch = the whole T-step rollout; 8 CTAs per environment as hardware "
+                      "clusters of 2 + one software barrier per step when 16 x 8-CTA clusters do not co-reside)",
             "bound": "tensor", "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
             "peak_source": src + " bf16 cuBLAS burst (MEASURED_PEAKS.json); fp32-class results cost 3 tf32 MMAs per "
                                  "product, so the kernel's own tensor ceiling is 1/6 of this",
