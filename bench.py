@@ -172,6 +172,17 @@ def run_ours(args):
     n_edges = eng.counters[:, 0].float().mean().item()
     deg_real = n_edges / (E * N)
 
+    if args.train_only:
+        tr = train_step_bench(torch, dist if world > 1 else None, env, algo, eng, rank, world, cfg, max_over_ranks, barrier)
+        if rank == 0:
+            print(json.dumps({"train_step": tr}))
+        if world > 1:
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+            dist.destroy_process_group()
+        return
+
     # ---- value: device-resident inputs
     sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -588,6 +599,8 @@ def main():
     ap.add_argument("--T", type=int, default=T_STEPS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-only", action="store_true",
+                    help="profiling aid: one short rollout, then the train-step measurement alone (prints its dict)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

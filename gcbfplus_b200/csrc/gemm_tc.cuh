@@ -15,6 +15,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -122,6 +124,24 @@ struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// k-blocks of 16 floats (64-byte rows, SWIZZLE_64B) halve the stage size: twice the stages in flight for the same
+// shared memory, which is what hides the TMA latency behind the 3 MMAs per k-step (the 32-float ring had 2 stages).
+template <int BN, int BKc>
+struct CfgK {
+    static constexpr int A_BYTES = BM * BKc * 4;
+    static constexpr int B_BYTES = BN * BKc * 4;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;          // 2 / 3 (BKc = 32), 4 / 6 (BKc = 16)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+// K-major descriptor for a row of BKc floats: SWIZZLE_128B (layout 2, SBO 1024) or SWIZZLE_64B (layout 4, SBO 512)
+template <int BKc>
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {
+    constexpr uint64_t sbo = (BKc == 32) ? 1024 : 512;
+    constexpr uint64_t layout = (BKc == 32) ? 2 : 4;
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
 // hi = tf32(x) rounded to nearest (13 low mantissa bits cleared, so the tensor core's own fp32->tf32
 // conversion is exact), lo = tf32(x - hi): |x - hi - lo| <= 2^-24 |x|.
 __device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
@@ -136,14 +156,14 @@ static __global__ void split_tf32_kernel(const float* __restrict__ in, float* __
     }
 }
 
-template <int BN, int EPI, bool ACCUM>
+template <int BN, int EPI, bool ACCUM, int BKc>
 __global__ void __launch_bounds__(THREADS_NN, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                const __grid_constant__ CUtensorMap tmBl, const float* __restrict__ bias,
                const float* __restrict__ bias2, float* __restrict__ C, const float* __restrict__ aux,
                const int32_t* __restrict__ m_ptr, const int m_fixed, const int m_cap, const int K, const int N,
                const int ndot) {
-    using CF = Cfg<BN>;
+    using CF = CfgK<BN, BKc>;
     constexpr int STAGES = CF::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -157,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = N / BN;                // 1, or 2 when a 256-wide layer is split to fill more SMs
-    const int nkb = K / BK;
+    const int nkb = K / BKc;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -197,9 +217,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * CF::STAGE_BYTES;
                     mbar_expect_tx(&full[s], CF::A_BYTES + 2 * CF::B_BYTES);
-                    tma_load_2d(st, &tmA, &full[s], kb * BK, m0);
-                    tma_load_2d(st + 2 * CF::A_BYTES, &tmBh, &full[s], kb * BK, n0);
-                    tma_load_2d(st + 2 * CF::A_BYTES + CF::B_BYTES, &tmBl, &full[s], kb * BK, n0);
+                    tma_load_2d(st, &tmA, &full[s], kb * BKc, m0);
+                    tma_load_2d(st + 2 * CF::A_BYTES, &tmBh, &full[s], kb * BKc, n0);
+                    tma_load_2d(st + 2 * CF::A_BYTES + CF::B_BYTES, &tmBl, &full[s], kb * BKc, n0);
                 }
             }
         }
@@ -223,10 +243,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t b_hi = a_hi + 2 * CF::A_BYTES;
                     const uint32_t b_lo = b_hi + CF::B_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                    for (int k = 0; k < BKc / UMMA_K; ++k) {
                         const uint32_t koff = k * UMMA_K * 4;  // bytes inside the 128-byte swizzle row
-                        const uint64_t dah = make_desc(a_hi + koff), dal = make_desc(a_lo + koff);
-                        const uint64_t dbh = make_desc(b_hi + koff), dbl = make_desc(b_lo + koff);
+                        const uint64_t dah = make_desc_k<BKc>(a_hi + koff), dal = make_desc_k<BKc>(a_lo + koff);
+                        const uint64_t dbh = make_desc_k<BKc>(b_hi + koff), dbl = make_desc_k<BKc>(b_lo + koff);
                         umma_tf32(tmem_d, dal, dbh, idesc, (kb | k) != 0);   // small terms first
                         umma_tf32(tmem_d, dah, dbl, idesc, 1u);
                         umma_tf32(tmem_d, dah, dbh, idesc, 1u);
@@ -247,11 +267,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&full[s], ph);
                 float4* h4 = reinterpret_cast<float4*>(smem + s * CF::STAGE_BYTES);
                 float4* l4 = reinterpret_cast<float4*>(smem + s * CF::STAGE_BYTES + CF::A_BYTES);
-                float4 v[8];
+                constexpr int NV = BKc / 4;                                  // A tile = 128 NV float4
+                float4 v[NV];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = h4[et + 128 * j];       // A tile = 1024 float4
+                for (int j = 0; j < NV; ++j) v[j] = h4[et + 128 * j];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < NV; ++j) {
                     float4 h, l;
                     h.x = rn_tf32(v[j].x); h.y = rn_tf32(v[j].y); h.z = rn_tf32(v[j].z); h.w = rn_tf32(v[j].w);
                     l.x = rn_tf32(v[j].x - h.x); l.y = rn_tf32(v[j].y - h.y);
@@ -391,8 +412,8 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, 32 cols], 128-byte swizzle.
-inline int32_t make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int box_rows) {
+// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, bk cols], 128-byte (bk = 32) or 64-byte (bk = 16) swizzle.
+inline int32_t make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int box_rows, int bk = BK) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled unavailable");
@@ -400,10 +421,11 @@ inline int32_t make_map(CUtensorMap* map, const float* ptr, int rows, int cols, 
     }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d", (int)r, rows, cols);
@@ -412,15 +434,24 @@ inline int32_t make_map(CUtensorMap* map, const float* ptr, int rows, int cols, 
     return 0;
 }
 
-template <int BN>
+// k-block size of the NN kernel: 16 (default) or 32 (GCBF_TC_BK=32)
+inline int tc_bk() {
+    static const int bk = [] {
+        const char* e = getenv("GCBF_TC_BK");
+        return (e && atoi(e) == 32) ? 32 : 16;
+    }();
+    return bk;
+}
+
+template <int BN, int BKc>
 inline int32_t launch_bn(int epi, bool accum, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBl,
                          const float* bias,
                          const float* bias2, float* C, const float* aux, RowCount rc, int K, int N, int grid,
                          cudaStream_t st, int ndot = 0) {
-    constexpr int smem = Cfg<BN>::SMEM_BYTES;
+    constexpr int smem = CfgK<BN, BKc>::SMEM_BYTES;
 #define GCBF_TC_CASE(E, ACC)                                                                                      \
     do {                                                                                                          \
-        auto kern = gemm_tc_kernel<BN, E, ACC>;                                                                   \
+        auto kern = gemm_tc_kernel<BN, E, ACC, BKc>;                                                                 \
         static bool attr_done = false;                                                                            \
         if (!attr_done) {                                                                                         \
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                        \
@@ -467,13 +498,18 @@ inline int32_t launch_gemm_tc(int epi, bool accum, const float* A, const float* 
     // busy), half the weight traffic and MMA time per CTA, 3 pipeline stages instead of 2
     const int bn = (N == 256 && 2 * tiles_m <= sm_count() && epi != EPI_RELU_DOT) ? 128 : N;
     CUtensorMap tmA, tmB, tmBl;
-    if (int32_t r = make_map(&tmA, A, rc.cap, K, BM)) return r;
-    if (int32_t r = make_map(&tmB, Bt_hi, N, K, bn)) return r;
-    if (int32_t r = make_map(&tmBl, Bt_lo, N, K, bn)) return r;
+    const int bk = tc_bk();
+    if (int32_t r = make_map(&tmA, A, rc.cap, K, BM, bk)) return r;
+    if (int32_t r = make_map(&tmB, Bt_hi, N, K, bn, bk)) return r;
+    if (int32_t r = make_map(&tmBl, Bt_lo, N, K, bn, bk)) return r;
     const int grid = min(tiles_m * (N / bn), sm_count());
     if (parts_out) *parts_out = N / bn;
-    if (bn == 256) return launch_bn<256>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st, ndot);
-    return launch_bn<128>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st, ndot);
+    if (bk == 32) {
+        if (bn == 256) return launch_bn<256, 32>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st, ndot);
+        return launch_bn<128, 32>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st, ndot);
+    }
+    if (bn == 256) return launch_bn<256, 16>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st, ndot);
+    return launch_bn<128, 16>(epi, accum, tmA, tmB, tmBl, bias, bias2, C, aux, rc, K, N, grid, st, ndot);
 }
 
 
@@ -487,24 +523,34 @@ inline int32_t launch_gemm_tc(int epi, bool accum, const float* A, const float* 
 // along K at SBO = 512 B.
 // Split over M: CTA (tile, split) walks 32-row chunks {split, split + S, ...}; result red.add'ed to C.
 // =====================================================================================================
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t box_bytes = 4096) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(box_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
            (1ull << 46) | (1ull << 61);
 }
 __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
     return make_idesc(M, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
 }
 
-template <int BN>
-__global__ void __launch_bounds__(THREADS, 1)
+constexpr int THREADS_TN = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 operand split + column sums + epilogue
+
+// `cs1` / `cs2` (optional): column sums sum_m w(m) dY[m, n] -- the bias gradient of the same layer (and the agent
+// one-hot row of the update layer) -- accumulated by the operand-split warps from the very values they convert, so no
+// separate pass over dY is needed.  Only the CTAs of k1-tile 0 contribute.
+// RCH = rows (MMA-K extent) per pipeline stage: 16 (default; 4 / 6 stages) or 32 (2 / 3 stages)
+template <int BN, int RCH>
+__global__ void __launch_bounds__(THREADS_TN, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                   float* __restrict__ C, const float* __restrict__ roww, const int32_t* __restrict__ row2agent,
                   const int32_t* __restrict__ m_ptr, const int m_fixed, const int m_cap, const int N, const int splits,
-                  const int n_agents_total) {
-    constexpr int STAGES = (BN == 256) ? 2 : 3;
-    constexpr int A_BYTES = 128 * 32 * 4;            // 4 boxes of [32 m x 32 k1]
-    constexpr int B_BYTES = BN * 32 * 4;             // BN/32 boxes of [32 m x 32 n]
+                  const int n_agents_total, float* __restrict__ cs1, float* __restrict__ cs2) {
+    constexpr int A_BYTES = 128 * RCH * 4;           // 4 boxes of [RCH m x 32 k1]
+    constexpr int B_BYTES = BN * RCH * 4;            // BN/32 boxes of [RCH m x 32 n]
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+    constexpr int BOX = RCH * 128;                   // bytes of one box
+    constexpr int BOX4 = BOX / 16;                   // float4 per box
+    constexpr int NB = BN / 32;
+    constexpr int NJA = (4 * BOX4) / 256, NJB = (NB * BOX4) / 256;   // float4 per thread and plane
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -519,13 +565,13 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     M = min(M, m_cap);
     const int tile = blockIdx.x / splits, split = blockIdx.x % splits;
     const int k1_0 = tile * 128;
-    const int n_chunks = (M + 31) / 32;
+    const int n_chunks = (M + RCH - 1) / RCH;
     const int n_my = (split < n_chunks) ? (n_chunks - split + splits - 1) / splits : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&conv[s], 128);
+            mbar_init(&conv[s], 256);
             mbar_init(&empty[s], 1);
         }
         mbar_init(tmem_full, 1);
@@ -547,14 +593,14 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             for (int it = 0; it < n_my; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                const int m0 = (split + it * splits) * 32;
+                const int m0 = (split + it * splits) * RCH;
                 mbar_wait(&empty[s], ph ^ 1);
                 uint8_t* st = smem + s * STAGE_BYTES;
                 mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) tma_load_2d(st + i * 4096, &tmX, &full[s], k1_0 + 32 * i, m0);
+                for (int i = 0; i < 4; ++i) tma_load_2d(st + i * BOX, &tmX, &full[s], k1_0 + 32 * i, m0);
 #pragma unroll
-                for (int j = 0; j < BN / 32; ++j) tma_load_2d(st + 2 * A_BYTES + j * 4096, &tmY, &full[s], 32 * j, m0);
+                for (int j = 0; j < NB; ++j) tma_load_2d(st + 2 * A_BYTES + j * BOX, &tmY, &full[s], 32 * j, m0);
             }
         }
     } else if (warp == 1) {
@@ -570,10 +616,10 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const uint32_t b_hi = a_hi + 2 * A_BYTES;
                 const uint32_t b_lo = b_hi + B_BYTES;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < RCH / 8; ++k) {
                     const uint32_t koff = k * 1024;      // 8 m-rows
-                    const uint64_t dah = make_desc_mn(a_hi + koff), dal = make_desc_mn(a_lo + koff);
-                    const uint64_t dbh = make_desc_mn(b_hi + koff), dbl = make_desc_mn(b_lo + koff);
+                    const uint64_t dah = make_desc_mn(a_hi + koff, BOX), dal = make_desc_mn(a_lo + koff, BOX);
+                    const uint64_t dbh = make_desc_mn(b_hi + koff, BOX), dbl = make_desc_mn(b_lo + koff, BOX);
                     umma_tf32(tmem_base, dal, dbh, idesc, (it | k) != 0);
                     umma_tf32(tmem_base, dah, dbl, idesc, 1u);
                     umma_tf32(tmem_base, dah, dbh, idesc, 1u);
@@ -583,58 +629,95 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (n_my > 0) umma_commit(tmem_full);
         }
     } else {
+        // 256 operand-split threads: float4 index i = et + 256 j of a plane lies in box i / BOX4, box row (i % BOX4) / 8
+        // (the same for every j: 256 % BOX4 == 0), 16-byte unit et % 8
         const int et = threadIdx.x - 64;
         const int quarter = warp & 3;
+        const int brow = (et % BOX4) >> 3;
+        const bool do_cs = (cs1 != nullptr) && tile == 0;
         auto rn = [](float x) { return rn_tf32(x); };
+        float4 csum[NJB];
+#pragma unroll
+        for (int j = 0; j < NJB; ++j) csum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int it = 0; it < n_my; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
-            const int m0 = (split + it * splits) * 32;
-            // float4 index i covers smem bytes [16 i, 16 i + 16): box row = (i % 256) / 8; this thread sees 2 rows
-            float wrow[2], vrow[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int m = m0 + ((et + 128 * h) % 256) / 8;
-                vrow[h] = (m < M) ? 1.f : 0.f;
-                float w = 1.f;
-                if (roww && m < M) {
-                    int ag = row2agent ? row2agent[m] : m;
-                    ag = min(max(ag, 0), n_agents_total - 1);
-                    w = roww[ag];
-                }
-                wrow[h] = w * vrow[h];
+            const int m = (split + it * splits) * RCH + brow;
+            const bool vrow = m < M;
+            float wrow = 1.f;
+            if (roww && vrow) {
+                int ag = row2agent ? row2agent[m] : m;
+                ag = min(max(ag, 0), n_agents_total - 1);
+                wrow = roww[ag];
             }
             mbar_wait(&full[s], ph);
             uint8_t* st = smem + s * STAGE_BYTES;
-            auto split_op = [&](uint8_t* hi_p, uint8_t* lo_p, int n_vec, const float* scale) {
-                float4* h4 = reinterpret_cast<float4*>(hi_p);
-                float4* l4 = reinterpret_cast<float4*>(lo_p);
-#pragma unroll 4
-                for (int i = et, j = 0; i < n_vec; i += 128, ++j) {
+            {   // X: rows >= M hold stale data (possibly NaN): select, do not multiply
+                float4* h4 = reinterpret_cast<float4*>(st);
+                float4* l4 = reinterpret_cast<float4*>(st + A_BYTES);
+#pragma unroll
+                for (int j = 0; j < NJA; ++j) {
+                    const int i = et + 256 * j;
                     float4 v = h4[i];
-                    const float sc = scale[j & 1];
-                    // rows >= M hold stale data (possibly NaN): select, do not multiply
-                    v.x = sc != 0.f ? v.x * sc : 0.f; v.y = sc != 0.f ? v.y * sc : 0.f;
-                    v.z = sc != 0.f ? v.z * sc : 0.f; v.w = sc != 0.f ? v.w * sc : 0.f;
+                    if (!vrow) v = make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 h, l;
                     h.x = rn(v.x); h.y = rn(v.y); h.z = rn(v.z); h.w = rn(v.w);
                     l.x = rn(v.x - h.x); l.y = rn(v.y - h.y); l.z = rn(v.z - h.z); l.w = rn(v.w - h.w);
                     h4[i] = h;
                     l4[i] = l;
                 }
-            };
-            split_op(st, st + A_BYTES, A_BYTES / 16, vrow);
-            split_op(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, B_BYTES / 16, wrow);
+            }
+            {   // dY, scaled by the row weight
+                float4* h4 = reinterpret_cast<float4*>(st + 2 * A_BYTES);
+                float4* l4 = reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                for (int j = 0; j < NJB; ++j) {
+                    const int i = et + 256 * j;
+                    float4 v = h4[i];
+                    if (vrow) { v.x *= wrow; v.y *= wrow; v.z *= wrow; v.w *= wrow; }
+                    else v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    csum[j].x += v.x; csum[j].y += v.y; csum[j].z += v.z; csum[j].w += v.w;
+                    float4 h, l;
+                    h.x = rn(v.x); h.y = rn(v.y); h.z = rn(v.z); h.w = rn(v.w);
+                    l.x = rn(v.x - h.x); l.y = rn(v.y - h.y); l.z = rn(v.z - h.z); l.w = rn(v.w - h.w);
+                    h4[i] = h;
+                    l4[i] = l;
+                }
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&conv[s]);
         }
         if (n_my > 0) {
             mbar_wait(tmem_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (do_cs) {
+                // every MMA has retired: stage 0 is free.  SWIZZLE_128B_ATOM_32B: the 32-byte chunk q of box row r sits at
+                // position q ^ (r % 4), so 16-byte unit u of row r holds columns 8 ((u / 2) ^ (r % 4)) + 4 (u % 2) .. + 3
+                float* s_cs = reinterpret_cast<float*>(smem);
+                for (int c = et; c < BN; c += 256) s_cs[c] = 0.f;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int u = et & 7;
+                const int col0 = 8 * ((u >> 1) ^ (brow & 3)) + 4 * (u & 1);
+#pragma unroll
+                for (int j = 0; j < NJB; ++j) {
+                    const int box = (et + 256 * j) / BOX4;
+                    atomicAdd(&s_cs[32 * box + col0 + 0], csum[j].x);
+                    atomicAdd(&s_cs[32 * box + col0 + 1], csum[j].y);
+                    atomicAdd(&s_cs[32 * box + col0 + 2], csum[j].z);
+                    atomicAdd(&s_cs[32 * box + col0 + 3], csum[j].w);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int c = et; c < BN; c += 256) {
+                    const float v = s_cs[c];
+                    atomicAdd(cs1 + c, v);
+                    if (cs2) atomicAdd(cs2 + c, v);
+                }
+            }
             const int row = quarter * 32 + lane;
             float* crow = C + (size_t)(k1_0 + row) * N;
+            const int chalf = (warp - 2) >> 2;          // two warps per TMEM lane quarter: each takes half of the columns
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
                 // 128-bit vector reductions (REDG.E.ADD.F32x4): 8 per 32 columns instead of 32 scalar atomics -- the
@@ -677,35 +760,39 @@ inline int32_t make_map_box(CUtensorMap* map, const float* ptr, int rows, int co
 }
 
 // C[K1, N] += sum_m w(m) X[m, :K1] dY[m, :N]; X row stride ldx (>= K1, multiple of 4), K1 % 128 == 0, N in {128, 256}.
+// cs1 / cs2 (optional): += sum_m w(m) dY[m, :N] (bias gradient fused into the same pass over dY).
 inline int32_t launch_gemm_tn_tc(const float* X, int ldx, const float* dY, float* C, const float* roww,
                                  const int32_t* row2agent, RowCount rc, int K1, int N, int n_agents_total,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, float* cs1 = nullptr, float* cs2 = nullptr) {
     if (K1 % 128 != 0 || (N != 128 && N != 256) || ldx % 4 != 0) {
         set_error("gemm_tn_tc: K1=%d N=%d ldx=%d unsupported", K1, N, ldx);
         return -1;
     }
     const int rows = rc.ptr ? rc.cap : min(rc.fixed, rc.cap);
     if (rows <= 0) return 0;
+    static const int rch = [] {
+        const char* e = getenv("GCBF_TC_TN_ROWS");
+        return (e && atoi(e) == 32) ? 32 : 16;
+    }();
     CUtensorMap tmX, tmY;
-    if (int32_t r = make_map_box(&tmX, X, rc.cap, K1, ldx, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return r;
-    if (int32_t r = make_map_box(&tmY, dY, rc.cap, N, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return r;
+    if (int32_t r = make_map_box(&tmX, X, rc.cap, K1, ldx, rch, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return r;
+    if (int32_t r = make_map_box(&tmY, dY, rc.cap, N, N, rch, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return r;
     const int tiles = K1 / 128;
-    const int chunks = (rows + 31) / 32;
+    const int chunks = (rows + rch - 1) / rch;
     int splits = max(1, sm_count() / tiles);
-    splits = min(splits, max(1, chunks / 4));       // >= 128 rows per CTA
+    splits = min(splits, max(1, chunks * rch / 128));       // >= 128 rows per CTA
     const int grid = tiles * splits;
-    const int smem = ((N == 256) ? 2 : 3) * (2 * 128 * 32 * 4 + 2 * N * 32 * 4) + 1024 + 256;
-    if (N == 256) {
-        static bool done = false;
-        if (!done) { cudaFuncSetAttribute(gemm_tn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); done = true; }
-        gemm_tn_tc_kernel<256><<<grid, THREADS, smem, st>>>(tmX, tmY, C, roww, row2agent, rc.ptr, rc.fixed, rc.cap, N, splits,
-                                                            n_agents_total);
-    } else {
-        static bool done = false;
-        if (!done) { cudaFuncSetAttribute(gemm_tn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); done = true; }
-        gemm_tn_tc_kernel<128><<<grid, THREADS, smem, st>>>(tmX, tmY, C, roww, row2agent, rc.ptr, rc.fixed, rc.cap, N, splits,
-                                                            n_agents_total);
-    }
+    const int smem = 192 * 1024 + 1024 + 256;
+#define GCBF_TN_CASE(BN_, R_)                                                                                         \
+    do {                                                                                                              \
+        static bool done = false;                                                                                     \
+        if (!done) { cudaFuncSetAttribute(gemm_tn_tc_kernel<BN_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); done = true; } \
+        gemm_tn_tc_kernel<BN_, R_><<<grid, THREADS_TN, smem, st>>>(tmX, tmY, C, roww, row2agent, rc.ptr, rc.fixed, rc.cap, N,  \
+                                                                   splits, n_agents_total, cs1, cs2);                \
+    } while (0)
+    if (N == 256) { if (rch == 32) GCBF_TN_CASE(256, 32); else GCBF_TN_CASE(256, 16); }
+    else { if (rch == 32) GCBF_TN_CASE(128, 32); else GCBF_TN_CASE(128, 16); }
+#undef GCBF_TN_CASE
     count_launch();
     return check_launch("gemm_tn_tc_kernel");
 }

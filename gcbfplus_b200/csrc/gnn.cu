@@ -6,6 +6,7 @@
 #include "gnn.cuh"
 #include "gemm_tc_prod.cuh"
 #include "translayout.cuh"
+#include "smalljobs.cuh"
 
 using namespace gcbf;
 
@@ -167,18 +168,74 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_params_t_count(in
 
 namespace gcbf {
 // Builds the prepared-parameter blob (PreparedLayout) of one network.
+// One launch builds the whole prepared blob: the transposed tf32 planes of the 9 GEMM weights (32 x 32 tiles through
+// shared memory, split on the way out) and the split planes of the untransposed parameters (the blocks after the tiles).
+struct PrepJobs {
+    int n;
+    int src[12], dst[12], rows[12], cols[12], tile0[13];
+};
+static __global__ void __launch_bounds__(256)
+prepare_kernel(const PrepJobs J, const float* __restrict__ P, float* __restrict__ pt_hi, float* __restrict__ pt_lo,
+               float* __restrict__ p_hi, float* __restrict__ p_lo, const int n_params) {
+    const int n_tiles = J.tile0[J.n];
+    if ((int)blockIdx.x < n_tiles) {
+        __shared__ float tile[32][33];
+        int j = 0;
+        while (j + 1 < J.n && (int)blockIdx.x >= J.tile0[j + 1]) ++j;
+        const int t = blockIdx.x - J.tile0[j];
+        const int rows = J.rows[j], cols = J.cols[j];
+        const int tiles_c = (cols + 31) / 32;
+        const int c0 = (t % tiles_c) * 32, r0 = (t / tiles_c) * 32;
+        const float* in = P + J.src[j];
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        for (int i = ty; i < 32; i += 8) {
+            const int r = r0 + i, c = c0 + tx;
+            if (r < rows && c < cols) tile[i][tx] = in[(size_t)r * cols + c];
+        }
+        __syncthreads();
+        for (int i = ty; i < 32; i += 8) {
+            const int c = c0 + i, r = r0 + tx;
+            if (r < rows && c < cols) {
+                const float x = tile[tx][i];
+                const float h = tc::rn_tf32(x);
+                pt_hi[J.dst[j] + (size_t)c * rows + r] = h;
+                pt_lo[J.dst[j] + (size_t)c * rows + r] = tc::rn_tf32(x - h);
+            }
+        }
+        return;
+    }
+    const int nb = gridDim.x - n_tiles;
+    for (int i = (blockIdx.x - n_tiles) * 256 + threadIdx.x; i < n_params; i += nb * 256) {
+        const float x = P[i];
+        const float h = tc::rn_tf32(x);
+        p_hi[i] = h;
+        p_lo[i] = tc::rn_tf32(x - h);
+    }
+}
+
 int32_t build_prepared(const ParamLayout& L, const float* P, float* out, cudaStream_t st) {
     const TransLayout TL = make_trans_layout(L);
     const PreparedLayout Q = make_prepared_layout(L, TL);
-    if (int32_t rc = build_transposes(L, TL, P, out + Q.pt_hi, st)) return rc;
-    const int nsm = sm_count();
-    tc::split_tf32_kernel<<<min((TL.total + 255) / 256, 4 * nsm), 256, 0, st>>>(out + Q.pt_hi, out + Q.pt_hi, out + Q.pt_lo,
-                                                                               TL.total);
+    PrepJobs J;
+    J.n = 0;
+    int tiles = 0;
+    for (int i = 0; i < 12; ++i) {
+        if (TL.w[i] < 0) continue;
+        const int rows = (i == L_UPD0) ? 128 : L.in[i];
+        J.src[J.n] = L.w[i] + (i == L_UPD0 ? 3 * 256 : 0);
+        J.dst[J.n] = TL.w[i];
+        J.rows[J.n] = rows;
+        J.cols[J.n] = L.out[i];
+        J.tile0[J.n] = tiles;
+        tiles += ((rows + 31) / 32) * ((L.out[i] + 31) / 32);
+        ++J.n;
+    }
+    J.tile0[J.n] = tiles;
+    const int split_blocks = min((L.total + 255) / 256, 2 * sm_count());
+    prepare_kernel<<<tiles + split_blocks, 256, 0, st>>>(J, P, out + Q.pt_hi, out + Q.pt_lo, out + Q.p_hi, out + Q.p_lo,
+                                                         L.total);
     count_launch();
-    if (int32_t rc = check_launch("split_tf32_kernel")) return rc;
-    tc::split_tf32_kernel<<<min((L.total + 255) / 256, 4 * nsm), 256, 0, st>>>(P, out + Q.p_hi, out + Q.p_lo, L.total);
-    count_launch();
-    return check_launch("split_tf32_kernel");
+    return check_launch("prepare_kernel");
 }
 }  // namespace gcbf
 
@@ -221,66 +278,53 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_gemm_tn_tc(const 
 // =====================================================================================================
 namespace gcbf {
 
-// C[m,n] = A[m,k] @ B[k,n] (+ bias[n]); one thread per output, fp32 sequential accumulation (setup work).
-static __global__ void small_matmul_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                           const float* __restrict__ bias, float* __restrict__ C, int m, int k, int n) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= m * n) return;
-    const int r = idx / n, c = idx % n;
-    float s = 0.f;
-    for (int j = 0; j < k; ++j) s = fmaf(A[(size_t)r * k + j], B[(size_t)j * n + c], s);
-    C[idx] = s + (bias ? bias[c] : 0.f);
-}
-static int32_t small_matmul(const float* A, const float* B, const float* bias, float* C, int m, int k, int n,
-                            cudaStream_t st) {
-    small_matmul_kernel<<<(m * n + 127) / 128, 128, 0, st>>>(A, B, bias, C, m, k, n);
-    count_launch();
-    return check_launch("small_matmul_kernel");
-}
-
-static int32_t prepare_infer_impl(int ed, int out_dim, const float* P, float* blob, cudaStream_t st) {
+// Folded weights + operand planes of one network: 3 launches (two dependency waves of small products, then all planes).
+int32_t prepare_infer_impl(int ed, int out_dim, const float* P, float* blob, cudaStream_t st) {
     const ParamLayout L = make_layout(ed, out_dim);
     const InferLayout I = make_infer_layout(out_dim);
     int32_t rc;
 #define RC(x) do { if ((rc = (x))) return rc; } while (0)
-    // message tail
-    RC(small_matmul(P + L.w[L_MSG1], P + L.w[L_MSGOUT], nullptr, blob + I.w23, 256, 256, 128, st));
-    RC(small_matmul(P + L.b[L_MSG1], P + L.w[L_MSGOUT], P + L.b[L_MSGOUT], blob + I.b23, 1, 256, 128, st));
+    SmallJobList J;
+    // message tail: W23 = W2 W3, b23 = b2 W3 + b3
+    J.add(blob + I.w23, 256, 128, 256, P + L.w[L_MSG1], 256, 1, P + L.w[L_MSGOUT], 128, 1, nullptr, nullptr, nullptr, false);
+    J.add(blob + I.b23, 1, 128, 256, P + L.b[L_MSG1], 0, 1, P + L.w[L_MSGOUT], 128, 1, nullptr, nullptr, P + L.b[L_MSGOUT], false);
     // gate tail: a23 = A2 a3 ; c = ba2 . a3 + ba3
-    RC(small_matmul(P + L.w[L_ATT1], P + L.w[L_GATE], nullptr, blob + I.a23, 128, 128, 1, st));
-    RC(small_matmul(P + L.b[L_ATT1], P + L.w[L_GATE], P + L.b[L_GATE], blob + I.c23, 1, 128, 1, st));
-    // update tail + head first layer: UH = U2 U3 H1 (scratch for U2 U3 lives in the t_uh region until it is overwritten)
-    float* tmp = blob + I.t_uh;                          // 256*128 (+128) floats of scratch
-    RC(small_matmul(P + L.w[L_UPD1], P + L.w[L_UPDOUT], nullptr, tmp, 256, 256, 128, st));
-    RC(small_matmul(tmp, P + L.w[L_HEAD0], nullptr, blob + I.uh, 256, 128, 256, st));
-    RC(small_matmul(P + L.b[L_UPD1], P + L.w[L_UPDOUT], P + L.b[L_UPDOUT], tmp, 1, 256, 128, st));
-    RC(small_matmul(tmp, P + L.w[L_HEAD0], P + L.b[L_HEAD0], blob + I.buh, 1, 128, 256, st));
-    // head tail
-    RC(small_matmul(P + L.w[L_HEAD1], P + L.w[L_OUT], nullptr, blob + I.ho, 256, 256, out_dim, st));
-    RC(small_matmul(P + L.b[L_HEAD1], P + L.w[L_OUT], P + L.b[L_OUT], blob + I.bho, 1, 256, out_dim, st));
-    // transposed + tf32-split planes of the 4 GEMM weights (tensor-core path)
-    struct { const float* src; int rows, cols, dst; } T[4] = {
-        {blob + I.w23, 256, 128, I.t_w23}, {P + L.w[L_ATT0], 128, 128, I.t_a1},
-        {P + L.w[L_UPD0] + 3 * 256, 128, 256, I.t_u1}, {blob + I.uh, 256, 256, I.t_uh}};
-    const int nsm = sm_count();
+    J.add(blob + I.a23, 128, 1, 128, P + L.w[L_ATT1], 128, 1, P + L.w[L_GATE], 1, 1, nullptr, nullptr, nullptr, false);
+    J.add(blob + I.c23, 1, 1, 128, P + L.b[L_ATT1], 0, 1, P + L.w[L_GATE], 1, 1, nullptr, nullptr, P + L.b[L_GATE], false);
+    // update tail: Q = U2 U3, b' = bu2 U3 + bu3
+    J.add(blob + I.q_u12, 256, 128, 256, P + L.w[L_UPD1], 256, 1, P + L.w[L_UPDOUT], 128, 1, nullptr, nullptr, nullptr, false);
+    J.add(blob + I.b_u12, 1, 128, 256, P + L.b[L_UPD1], 0, 1, P + L.w[L_UPDOUT], 128, 1, nullptr, nullptr, P + L.b[L_UPDOUT], false);
+    // head tail: HO = H2 H3, bho = bh2 H3 + bh3
+    J.add(blob + I.ho, 256, out_dim, 256, P + L.w[L_HEAD1], 256, 1, P + L.w[L_OUT], out_dim, 1, nullptr, nullptr, nullptr, false);
+    J.add(blob + I.bho, 1, out_dim, 256, P + L.b[L_HEAD1], 0, 1, P + L.w[L_OUT], out_dim, 1, nullptr, nullptr, P + L.b[L_OUT], false);
+    RC(J.launch(st));
+    // update tail folded into the head's first layer: UH = Q H1, buh = b' H1 + bh1
+    J.add(blob + I.uh, 256, 256, 128, blob + I.q_u12, 128, 1, P + L.w[L_HEAD0], 256, 1, nullptr, nullptr, nullptr, false);
+    J.add(blob + I.buh, 1, 256, 128, blob + I.b_u12, 0, 1, P + L.w[L_HEAD0], 256, 1, nullptr, nullptr, P + L.b[L_HEAD0], false);
+    RC(J.launch(st));
+    // tf32 planes: transposed (forward B operands) and straight (backward-data B operands) of the 4 GEMM weights
+    struct { const float* src; int rows, cols, t, p; } T[4] = {
+        {blob + I.w23, 256, 128, I.t_w23, I.p_w23}, {P + L.w[L_ATT0], 128, 128, I.t_a1, I.p_a1},
+        {P + L.w[L_UPD0] + 3 * 256, 128, 256, I.t_u1, I.p_u1}, {blob + I.uh, 256, 256, I.t_uh, I.p_uh}};
+    PlaneJobList PJ;
     for (int i = 0; i < 4; ++i) {
         const int n = T[i].rows * T[i].cols;
-        RC(launch_transpose(T[i].src, blob + T[i].dst, T[i].rows, T[i].cols, st));
-        tc::split_tf32_kernel<<<min((n + 255) / 256, 4 * nsm), 256, 0, st>>>(blob + T[i].dst, blob + T[i].dst,
-                                                                            blob + T[i].dst + n, n);
-        count_launch();
-        RC(check_launch("split_tf32_kernel"));
+        PJ.add(T[i].src, T[i].rows, T[i].cols, true, blob + T[i].t, blob + T[i].t + n);
+        PJ.add(T[i].src, T[i].rows, T[i].cols, false, blob + T[i].p, blob + T[i].p + n);
     }
+    RC(PJ.launch(st));
 #undef RC
     return 0;
 }
 
-static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* blob, int use_tc,
+int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* blob, int use_tc,
                               const float* agent, const float* goal, const float* hits, const int32_t* row_start,
                               const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src,
                               const int32_t* counters, int clip_all, float* out, float* ws, cudaStream_t st,
                               float* z_out = nullptr, int* z_parts = nullptr, int32_t* zero_counter = nullptr,
-                              int select = 0xF) {
+                              int select = 0xF, int keep_activations = 0) {
+    // keep_activations (folded train step): the unfused launch sequence, every layer output left in the workspace
+    // (feat, x1, msg, g1, att, ag, v1, h1) for the backward pass; GEMMs still on the tensor-core path when use_tc
     // select (gcbf_rollout_step_select, measurement hook): bit 0 edge message (+ chained gate) kernel, bit 1 attention
     // aggregate, bit 2 update layer, bit 3 folded update/head layer; a cleared bit skips that launch
     // z_out != nullptr (rollout step): instead of `out`, write the output layer's pre-activation partial sums
@@ -299,7 +343,7 @@ static int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* 
         if (use_tc) return tc::launch_gemm_tc(epi, false, X, blob + t_off, blob + t_off + K * N, bias, bias2, Y, nullptr, rows, K, N, st);
         return launch_gemm_nn(epi, false, X, Wf, bias, bias2, Y, nullptr, rows, K, N, st);
     };
-    if (use_tc) {
+    if (use_tc && !keep_activations) {
         // tensor-core path, 4 launches: {edge features + layer 1 produced in-kernel -> folded message GEMM},
         // {gate layer + folded gate vector -> logits}, {softmax-aggregate produced in-kernel -> update layer 1},
         // {update/head folded layer (+ output layer) below}

@@ -38,8 +38,11 @@ inline GnnWs make_ws(int64_t cap, int64_t A) {
 
 // Folded inference weights (gcbf_prepare_infer, gnn.cu): float offsets inside the blob.
 struct InferLayout {
-    int w23, b23, a23, c23, uh, buh, ho, bho;          // folded fp32 weights
+    int w23, b23, a23, c23, uh, buh, ho, bho;          // folded fp32 weights (the gradient of the folded train step uses
+                                                       // the same offsets: [0, t_w23) floats)
     int t_w23, t_a1, t_u1, t_uh;                       // transposed tf32 planes: hi at t_x, lo at t_x + size
+    int q_u12, b_u12;                                  // U2 U3 and bu2 U3 + bu3 (needed to un-fold the gradient of uh)
+    int p_w23, p_a1, p_u1, p_uh;                       // straight tf32 planes (backward-data operands): hi, lo at + size
     int total;
 };
 inline InferLayout make_infer_layout(int out_dim) {
@@ -58,6 +61,12 @@ inline InferLayout make_infer_layout(int out_dim) {
     I.t_a1 = take(2 * 128 * 128);
     I.t_u1 = take(2 * 256 * 128);
     I.t_uh = take(2 * 256 * 256);
+    I.q_u12 = take(256 * 128);
+    I.b_u12 = take(128);
+    I.p_w23 = take(2 * 256 * 128);
+    I.p_a1 = take(2 * 128 * 128);
+    I.p_u1 = take(2 * 128 * 256);
+    I.p_uh = take(2 * 256 * 256);
     I.total = o;
     return I;
 }
@@ -215,6 +224,50 @@ attn_aggregate_kernel(const int A, const int edge_cap, const float* __restrict__
                     acc.y = fmaf(att, mv[q].y, acc.y);
                     acc.z = fmaf(att, mv[q].z, acc.z);
                     acc.w = fmaf(att, mv[q].w, acc.w);
+                }
+            }
+            *reinterpret_cast<float4*>(AG + (size_t)a * 128 + lane * 4) = acc;
+            continue;
+        }
+        if (G2 && rd <= 4) {
+            // training fast path: the gate rows and the message rows of all (<= 4) edges are requested up front and the
+            // 4 dot products are reduced together; same arithmetic order as the general path below
+            float sg[4];
+            float4 mv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = rs + min(q, max(rd - 1, 0));
+                const bool on = q < rd;
+                const float4 g = on ? *reinterpret_cast<const float4*>(G2 + (size_t)e * 128 + lane * 4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                mv[q] = on ? *reinterpret_cast<const float4*>(MSG + (size_t)e * 128 + lane * 4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                sg[q] = g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sg[q] += __shfl_xor_sync(0xffffffffu, sg[q], off);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                sg[q] = (q < rd) ? sg[q] + bias : -INFINITY;
+                mx = fmaxf(mx, sg[q]);
+            }
+            float den = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < rd) den += expf(sg[q] - mx);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < rd) {
+                    const float att = expf(sg[q] - mx) / den;
+                    acc.x = fmaf(att, mv[q].x, acc.x);
+                    acc.y = fmaf(att, mv[q].y, acc.y);
+                    acc.z = fmaf(att, mv[q].z, acc.z);
+                    acc.w = fmaf(att, mv[q].w, acc.w);
+                    if (lane == 0) ATT[rs + q] = att;
                 }
             }
             *reinterpret_cast<float4*>(AG + (size_t)a * 128 + lane * 4) = acc;

@@ -6,10 +6,13 @@
 // Replaces gcbfplus/algo/gcbf_plus.py:354-447 (update_inner / get_loss / value_and_grad),
 // trainer/utils.py:62-75 (compute_norm_and_clip), optax.adamw + optax.apply_if_finite
 // (gcbf_plus.py:109-110,127-128) and gcbf_plus.py:188-191 (update_tgt).
+#include <stdlib.h>
+
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
 #include "gnn.cuh"
 #include "translayout.cuh"
+#include "smalljobs.cuh"
 
 namespace gcbf {
 
@@ -226,7 +229,8 @@ __global__ void mask_count_kernel(const int A, const uint8_t* __restrict__ safe_
 __global__ void __launch_bounds__(256)
 head_out_bwd_kernel(const int A, const int nout, const float* __restrict__ H2, const float* __restrict__ W,
                     const float* __restrict__ out, const float* __restrict__ d_out, const float* __restrict__ roww,
-                    float* __restrict__ dH2, float* __restrict__ dW, float* __restrict__ db) {
+                    float* __restrict__ dH2, float* __restrict__ dW, float* __restrict__ db, const int mask_relu) {
+    // mask_relu (folded train step): H2 is the ReLU output feeding the folded output layer; dH2 is masked by H2 > 0 here
     const int lane = threadIdx.x & 31;
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
     float wacc[8][4], bacc[4];
@@ -241,44 +245,71 @@ head_out_bwd_kernel(const int A, const int nout, const float* __restrict__ H2, c
     for (int k = 0; k < 8; ++k)
 #pragma unroll
         for (int j = 0; j < 4; ++j) wl[k][j] = (j < nout) ? W[(lane * 8 + k) * nout + j] : 0.f;
-    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < A; a += warps_total) {
-        const float4 h0 = *reinterpret_cast<const float4*>(H2 + (size_t)a * 256 + lane * 8);
-        const float4 h1 = *reinterpret_cast<const float4*>(H2 + (size_t)a * 256 + lane * 8 + 4);
-        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-        const float rw = roww ? roww[a] : 1.f;
-        float dz[4];
+    // two agents per iteration: every load of both rows is issued before the first use (the loop is latency-bound)
+    for (int a0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a0 < A; a0 += 2 * warps_total) {
+        const int a1 = a0 + warps_total;
+        const bool two = a1 < A;
+        const int a1c = two ? a1 : a0;
+        float4 hq[2][2];
+        hq[0][0] = *reinterpret_cast<const float4*>(H2 + (size_t)a0 * 256 + lane * 8);
+        hq[0][1] = *reinterpret_cast<const float4*>(H2 + (size_t)a0 * 256 + lane * 8 + 4);
+        hq[1][0] = *reinterpret_cast<const float4*>(H2 + (size_t)a1c * 256 + lane * 8);
+        hq[1][1] = *reinterpret_cast<const float4*>(H2 + (size_t)a1c * 256 + lane * 8 + 4);
+        float rwq[2], dzq[2][4];
+        rwq[0] = roww ? roww[a0] : 1.f;
+        rwq[1] = roww ? roww[a1c] : 1.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j < nout) {
-                const float o = out[(size_t)a * nout + j];
-                dz[j] = d_out[(size_t)a * nout + j] * (1.f - o * o);
-            } else {
-                dz[j] = 0.f;
-            }
-        }
-        float dh[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float s = 0.f;
+        for (int q = 0; q < 2; ++q) {
+            const int a = q ? a1c : a0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                s = fmaf(dz[j], wl[k][j], s);
-                wacc[k][j] = fmaf(hv[k], rw * dz[j], wacc[k][j]);
+                if (j < nout) {
+                    const float o = out[(size_t)a * nout + j];
+                    dzq[q][j] = d_out[(size_t)a * nout + j] * (1.f - o * o);
+                } else {
+                    dzq[q][j] = 0.f;
+                }
             }
-            dh[k] = s;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bacc[j] += rw * dz[j];
-        float4* dst = reinterpret_cast<float4*>(dH2 + (size_t)a * 256 + lane * 8);
-        dst[0] = make_float4(dh[0], dh[1], dh[2], dh[3]);
-        dst[1] = make_float4(dh[4], dh[5], dh[6], dh[7]);
+        for (int q = 0; q < 2; ++q) {
+            if (q == 1 && !two) break;
+            const int a = q ? a1 : a0;
+            const float hv[8] = {hq[q][0].x, hq[q][0].y, hq[q][0].z, hq[q][0].w, hq[q][1].x, hq[q][1].y, hq[q][1].z, hq[q][1].w};
+            const float rw = rwq[q];
+            float dh[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s = fmaf(dzq[q][j], wl[k][j], s);
+                    wacc[k][j] = fmaf(hv[k], rw * dzq[q][j], wacc[k][j]);
+                }
+                dh[k] = (mask_relu && !(hv[k] > 0.f)) ? 0.f : s;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bacc[j] += rw * dzq[q][j];
+            float4* dst = reinterpret_cast<float4*>(dH2 + (size_t)a * 256 + lane * 8);
+            dst[0] = make_float4(dh[0], dh[1], dh[2], dh[3]);
+            dst[1] = make_float4(dh[4], dh[5], dh[6], dh[7]);
+        }
     }
     if (!dW) return;   // data-only backward (QP labels): no parameter gradient
+    // block-level reduction first: one atomic per (row, column) and CTA instead of one per warp
+    __shared__ float s_w[256 * 4 + 4];
+    for (int i = threadIdx.x; i < 256 * 4 + 4; i += blockDim.x) s_w[i] = 0.f;
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-        for (int j = 0; j < nout; ++j) atomicAdd(dW + (lane * 8 + k) * nout + j, wacc[k][j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nout) atomicAdd(&s_w[(lane * 8 + k) * 4 + j], wacc[k][j]);
     if (lane == 0)
-        for (int j = 0; j < nout; ++j) atomicAdd(db + j, bacc[j]);
+        for (int j = 0; j < nout; ++j) atomicAdd(&s_w[1024 + j], bacc[j]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256 * nout; i += blockDim.x) atomicAdd(dW + i, s_w[(i / nout) * 4 + (i % nout)]);
+    if (threadIdx.x < nout) atomicAdd(db + threadIdx.x, s_w[1024 + threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------ backward: attention + aggregation
@@ -290,7 +321,9 @@ attn_aggregate_bwd_kernel(const int A, const int edge_cap, const float* __restri
                           const float* __restrict__ G2, const float* __restrict__ ATT, const float* __restrict__ a3,
                           const int32_t* __restrict__ row_start, const int32_t* __restrict__ row_deg,
                           const float* __restrict__ roww, float* __restrict__ dMSG, float* __restrict__ dG2,
-                          float* __restrict__ da3, float* __restrict__ dba3) {
+                          float* __restrict__ da3, float* __restrict__ dba3, const int mask_relu) {
+    // mask_relu (folded train step): G2 is the ReLU output of the gate's first layer and a3 the folded gate vector;
+    // dG2 is masked by G2 > 0 here
     const int lane = threadIdx.x & 31;
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
     const float4 w3 = *reinterpret_cast<const float4*>(a3 + lane * 4);
@@ -303,6 +336,51 @@ attn_aggregate_bwd_kernel(const int A, const int edge_cap, const float* __restri
         const float4 dag = *reinterpret_cast<const float4*>(dAG + (size_t)a * 128 + lane * 4);
         const float rw = roww ? roww[a] : 1.f;
         float dot_sum = 0.f;
+        if (rd <= 4) {
+            // the common case (goal row + a few neighbours): MSG is read once, the 4 dot products are reduced together
+            float p[4], at[4];
+            float4 g[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = rs + min(q, max(rd - 1, 0));
+                const bool on = q < rd;
+                const float4 m = on ? *reinterpret_cast<const float4*>(MSG + (size_t)e * 128 + lane * 4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                g[q] = on ? *reinterpret_cast<const float4*>(G2 + (size_t)e * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                at[q] = on ? ATT[e] : 0.f;
+                p[q] = dag.x * m.x + dag.y * m.y + dag.z * m.z + dag.w * m.w;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) p[q] += __shfl_xor_sync(0xffffffffu, p[q], off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < rd) dot_sum = fmaf(at[q], p[q], dot_sum);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < rd) {
+                    const int e = rs + q;
+                    const float att = at[q];
+                    const float dgate = att * (p[q] - dot_sum);
+                    *reinterpret_cast<float4*>(dMSG + (size_t)e * 128 + lane * 4) =
+                        make_float4(att * dag.x, att * dag.y, att * dag.z, att * dag.w);
+                    float4 dg = make_float4(dgate * w3.x, dgate * w3.y, dgate * w3.z, dgate * w3.w);
+                    if (mask_relu) {
+                        dg.x = g[q].x > 0.f ? dg.x : 0.f; dg.y = g[q].y > 0.f ? dg.y : 0.f;
+                        dg.z = g[q].z > 0.f ? dg.z : 0.f; dg.w = g[q].w > 0.f ? dg.w : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(dG2 + (size_t)e * 128 + lane * 4) = dg;
+                    const float wd = rw * dgate;
+                    acc3.x = fmaf(wd, g[q].x, acc3.x);
+                    acc3.y = fmaf(wd, g[q].y, acc3.y);
+                    acc3.z = fmaf(wd, g[q].z, acc3.z);
+                    acc3.w = fmaf(wd, g[q].w, acc3.w);
+                    accb += wd;
+                }
+            }
+            continue;
+        }
         for (int e = rs; e < rs + rd; ++e) {
             const float4 m = *reinterpret_cast<const float4*>(MSG + (size_t)e * 128 + lane * 4);
             const float datt = warp_sum(dag.x * m.x + dag.y * m.y + dag.z * m.z + dag.w * m.w);
@@ -315,9 +393,13 @@ attn_aggregate_bwd_kernel(const int A, const int edge_cap, const float* __restri
             const float dgate = att * (datt - dot_sum);
             *reinterpret_cast<float4*>(dMSG + (size_t)e * 128 + lane * 4) =
                 make_float4(att * dag.x, att * dag.y, att * dag.z, att * dag.w);
-            *reinterpret_cast<float4*>(dG2 + (size_t)e * 128 + lane * 4) =
-                make_float4(dgate * w3.x, dgate * w3.y, dgate * w3.z, dgate * w3.w);
             const float4 g = *reinterpret_cast<const float4*>(G2 + (size_t)e * 128 + lane * 4);
+            float4 dg = make_float4(dgate * w3.x, dgate * w3.y, dgate * w3.z, dgate * w3.w);
+            if (mask_relu) {
+                dg.x = g.x > 0.f ? dg.x : 0.f; dg.y = g.y > 0.f ? dg.y : 0.f;
+                dg.z = g.z > 0.f ? dg.z : 0.f; dg.w = g.w > 0.f ? dg.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(dG2 + (size_t)e * 128 + lane * 4) = dg;
             const float wd = rw * dgate;
             acc3.x = fmaf(wd, g.x, acc3.x);
             acc3.y = fmaf(wd, g.y, acc3.y);
@@ -327,11 +409,18 @@ attn_aggregate_bwd_kernel(const int A, const int edge_cap, const float* __restri
         }
     }
     if (!da3) return;  // data-only backward
-    atomicAdd(da3 + lane * 4 + 0, acc3.x);
-    atomicAdd(da3 + lane * 4 + 1, acc3.y);
-    atomicAdd(da3 + lane * 4 + 2, acc3.z);
-    atomicAdd(da3 + lane * 4 + 3, acc3.w);
-    if (lane == 0) atomicAdd(dba3, accb);
+    __shared__ float s_a[132];
+    for (int i = threadIdx.x; i < 132; i += blockDim.x) s_a[i] = 0.f;
+    __syncthreads();
+    atomicAdd(&s_a[lane * 4 + 0], acc3.x);
+    atomicAdd(&s_a[lane * 4 + 1], acc3.y);
+    atomicAdd(&s_a[lane * 4 + 2], acc3.z);
+    atomicAdd(&s_a[lane * 4 + 3], acc3.w);
+    accb = warp_sum(accb);
+    if (lane == 0) atomicAdd(&s_a[128], accb);
+    __syncthreads();
+    if (threadIdx.x < 128) atomicAdd(da3 + threadIdx.x, s_a[threadIdx.x]);
+    if (threadIdx.x == 128) atomicAdd(dba3, s_a[128]);
 }
 
 // ------------------------------------------------------------------------------------ backward: edge layer 1
@@ -343,24 +432,56 @@ edge_l1_bwd_w_kernel(const int edge_cap, const int n_agents_total, const int32_t
                      const float* __restrict__ dY, const float* __restrict__ feat,
                      const int32_t* __restrict__ edge_src, const int32_t* __restrict__ edge_recv,
                      const float* __restrict__ roww, float* __restrict__ dW1, float* __restrict__ db1) {
+    // chunks of 64 edges: the per-edge metadata (features, sender type, row weight) is staged in shared memory so that the
+    // dY loads of a chunk are independent of it and 8 of them are in flight per thread
+    constexpr int CH = 64;
+    __shared__ float s_feat[CH][ED];
+    __shared__ float s_w[CH];
+    __shared__ int s_t[CH];
     const int nE = min(counters[0], edge_cap);
     const int c = threadIdx.x;
     float accw[ED], acct[3], accall = 0.f;
 #pragma unroll
     for (int i = 0; i < ED; ++i) accw[i] = 0.f;
     acct[0] = acct[1] = acct[2] = 0.f;
-    for (int e = blockIdx.x; e < nE; e += gridDim.x) {
-        float w = 1.f;
-        if (roww) w = roww[min(max(edge_recv[e], 0), n_agents_total - 1)];
-        const float g = w * dY[(size_t)e * 256 + c];
-        const int code = edge_src[e];
-        const int t = (code >= 0) ? 2 : ((code == -1) ? 1 : 0);
+    const int n_chunks = (nE + CH - 1) / CH;
+    for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const int e0 = ch * CH;
+        const int n = min(CH, nE - e0);
+        __syncthreads();
+        if (c < CH) {
+            float w = 0.f;
+            int t = 0;
+            if (c < n) {
+                w = roww ? roww[min(max(edge_recv[e0 + c], 0), n_agents_total - 1)] : 1.f;
+                const int code = edge_src[e0 + c];
+                t = (code >= 0) ? 2 : ((code == -1) ? 1 : 0);
+            }
+            s_w[c] = w;
+            s_t[c] = t;
+        }
+        for (int i = c; i < CH * ED; i += 256) {
+            const int r = i / ED, k = i % ED;
+            s_feat[r][k] = (r < n) ? feat[(size_t)(e0 + r) * FEAT_LD + k] : 0.f;
+        }
+        __syncthreads();
+        for (int r0 = 0; r0 < n; r0 += 8) {
+            float g[8];
 #pragma unroll
-        for (int i = 0; i < ED; ++i) accw[i] = fmaf(feat[(size_t)e * FEAT_LD + i], g, accw[i]);
-        acct[0] += (t == 0) ? g : 0.f;
-        acct[1] += (t == 1) ? g : 0.f;
-        acct[2] += (t == 2) ? g : 0.f;
-        accall += g;
+            for (int q = 0; q < 8; ++q) g[q] = (r0 + q < n) ? dY[(size_t)(e0 + r0 + q) * 256 + c] : 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = r0 + q;       // rows >= n carry w = 0 and g = 0
+                const float gg = s_w[r & (CH - 1)] * g[q];
+                const int t = s_t[r & (CH - 1)];
+#pragma unroll
+                for (int i = 0; i < ED; ++i) accw[i] = fmaf(s_feat[r & (CH - 1)][i], gg, accw[i]);
+                acct[0] += (t == 0) ? gg : 0.f;
+                acct[1] += (t == 1) ? gg : 0.f;
+                acct[2] += (t == 2) ? gg : 0.f;
+                accall += gg;
+            }
+        }
     }
 #pragma unroll
     for (int i = 0; i < ED; ++i) atomicAdd(dW1 + i * 256 + c, accw[i]);
@@ -515,11 +636,16 @@ struct BwdArgs {
     int use_tc;            // 1: backward-data GEMMs on the tcgen05 path
 };
 
-// dW += X^T (w dY): tensor-core (MN-major 3xTF32) or SIMT split-M kernel.
-static int32_t dense_bwd_weight(const BwdArgs& b, const float* X, int ldx, const float* dY, float* C,
-                                const int32_t* row2agent, RowCount rc, int K1, int N, int A, cudaStream_t st) {
-    if (b.use_tc) return tc::launch_gemm_tn_tc(X, ldx, dY, C, b.roww, row2agent, rc, K1, N, A, st);
-    return launch_gemm_tn(X, ldx, dY, C, b.roww, row2agent, rc, K1, N, A, st);
+// dW += X^T (w dY) and db (+ db2) += sum_m w dY: tensor-core kernel (MN-major 3xTF32, column sums fused into its
+// operand-split pass) or the SIMT split-M kernel followed by column-sum launches.
+static int32_t dense_bwd_weight(const BwdArgs& b, const float* X, int ldx, const float* dY, float* C, float* db,
+                                float* db2, const int32_t* row2agent, RowCount rc, int K1, int N, int A,
+                                cudaStream_t st) {
+    if (b.use_tc) return tc::launch_gemm_tn_tc(X, ldx, dY, C, b.roww, row2agent, rc, K1, N, A, st, db, db2);
+    if (int32_t r = launch_gemm_tn(X, ldx, dY, C, b.roww, row2agent, rc, K1, N, A, st)) return r;
+    if (int32_t r = launch_colsum(dY, db, b.roww, row2agent, rc, N, A, st)) return r;
+    if (db2) return launch_colsum(dY, db2, b.roww, row2agent, rc, N, A, st);
+    return 0;
 }
 
 // dX = epi(dY @ W_i^T) (+= if accum).  SIMT: B = W^T from PT; tensor core: Bt = W itself (K-major).
@@ -557,54 +683,44 @@ static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
     {
         const int grid = min((A + 7) / 8, 2 * nsm);
         head_out_bwd_kernel<<<grid, 256, 0, st>>>(A, b.out_dim, fw + W.h2, b.P + L.w[L_OUT], b.out, b.d_out, b.roww,
-                                                  gw + W.h2, wgrad ? Gz + L.w[L_OUT] : nullptr, wgrad ? Gz + L.b[L_OUT] : nullptr);
+                                                  gw + W.h2, wgrad ? Gz + L.w[L_OUT] : nullptr, wgrad ? Gz + L.b[L_OUT] : nullptr, 0);
         count_launch();
         RC(check_launch("head_out_bwd_kernel"));
     }
     // ---- head MLP
-    WG(dense_bwd_weight(b, fw + W.h1, 256, gw + W.h2, b.G + L.w[L_HEAD1], nullptr, ra, 256, 256, A, st));
-    WG(launch_colsum(gw + W.h2, b.G + L.b[L_HEAD1], b.roww, nullptr, ra, 256, A, st));
+    WG(dense_bwd_weight(b, fw + W.h1, 256, gw + W.h2, b.G + L.w[L_HEAD1], b.G + L.b[L_HEAD1], nullptr, nullptr, ra, 256, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_HEAD1, EPI_RELU_MASK, false, gw + W.h2, gw + W.h1, fw + W.h1, ra, st));
-    WG(dense_bwd_weight(b, fw + W.v3, 128, gw + W.h1, b.G + L.w[L_HEAD0], nullptr, ra, 128, 256, A, st));
-    WG(launch_colsum(gw + W.h1, b.G + L.b[L_HEAD0], b.roww, nullptr, ra, 256, A, st));
+    WG(dense_bwd_weight(b, fw + W.v3, 128, gw + W.h1, b.G + L.w[L_HEAD0], b.G + L.b[L_HEAD0], nullptr, nullptr, ra, 128, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_HEAD0, EPI_NONE, false, gw + W.h1, gw + W.v3, nullptr, ra, st));
     // ---- update MLP
-    WG(dense_bwd_weight(b, fw + W.v2, 256, gw + W.v3, b.G + L.w[L_UPDOUT], nullptr, ra, 256, 128, A, st));
-    WG(launch_colsum(gw + W.v3, b.G + L.b[L_UPDOUT], b.roww, nullptr, ra, 128, A, st));
+    WG(dense_bwd_weight(b, fw + W.v2, 256, gw + W.v3, b.G + L.w[L_UPDOUT], b.G + L.b[L_UPDOUT], nullptr, nullptr, ra, 256, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_UPDOUT, EPI_NONE, false, gw + W.v3, gw + W.v2, nullptr, ra, st));
-    WG(dense_bwd_weight(b, fw + W.v1, 256, gw + W.v2, b.G + L.w[L_UPD1], nullptr, ra, 256, 256, A, st));
-    WG(launch_colsum(gw + W.v2, b.G + L.b[L_UPD1], b.roww, nullptr, ra, 256, A, st));
+    WG(dense_bwd_weight(b, fw + W.v1, 256, gw + W.v2, b.G + L.w[L_UPD1], b.G + L.b[L_UPD1], nullptr, nullptr, ra, 256, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_UPD1, EPI_RELU_MASK, false, gw + W.v2, gw + W.v1, fw + W.v1, ra, st));
-    WG(dense_bwd_weight(b, fw + W.ag, 128, gw + W.v1, b.G + L.w[L_UPD0] + 3 * 256, nullptr, ra, 128, 256, A, st));
-    WG(launch_colsum(gw + W.v1, b.G + L.b[L_UPD0], b.roww, nullptr, ra, 256, A, st));
-    WG(launch_colsum(gw + W.v1, b.G + L.w[L_UPD0] + 2 * 256, b.roww, nullptr, ra, 256, A, st));  // agent one-hot row
+    WG(dense_bwd_weight(b, fw + W.ag, 128, gw + W.v1, b.G + L.w[L_UPD0] + 3 * 256, b.G + L.b[L_UPD0], b.G + L.w[L_UPD0] + 2 * 256, nullptr, ra, 128, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_UPD0, EPI_NONE, false, gw + W.v1, gw + W.ag, nullptr, ra, st));
     // ---- attention + aggregation
     {
         const int grid = min((A + 7) / 8, 2 * nsm);
         attn_aggregate_bwd_kernel<<<grid, 256, 0, st>>>(A, cap, gw + W.ag, fw + W.msg, fw + W.g2, fw + W.att,
                                                         b.P + L.w[L_GATE], b.row_start, b.row_deg, b.roww, gw + W.msg,
-                                                        gw + W.g2, wgrad ? Gz + L.w[L_GATE] : nullptr, wgrad ? Gz + L.b[L_GATE] : nullptr);
+                                                        gw + W.g2, wgrad ? Gz + L.w[L_GATE] : nullptr, wgrad ? Gz + L.b[L_GATE] : nullptr, 0);
         count_launch();
         RC(check_launch("attn_aggregate_bwd_kernel"));
     }
     // ---- gate MLP (edge rows; dW weighted by the receiver's weight)
-    WG(dense_bwd_weight(b, fw + W.g1, 128, gw + W.g2, b.G + L.w[L_ATT1], b.edge_recv, re, 128, 128, A, st));
-    WG(launch_colsum(gw + W.g2, b.G + L.b[L_ATT1], b.roww, b.edge_recv, re, 128, A, st));
+    WG(dense_bwd_weight(b, fw + W.g1, 128, gw + W.g2, b.G + L.w[L_ATT1], b.G + L.b[L_ATT1], nullptr, b.edge_recv, re, 128, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_ATT1, EPI_RELU_MASK, false, gw + W.g2, gw + W.g1, fw + W.g1, re, st));
-    WG(dense_bwd_weight(b, fw + W.msg, 128, gw + W.g1, b.G + L.w[L_ATT0], b.edge_recv, re, 128, 128, A, st));
-    WG(launch_colsum(gw + W.g1, b.G + L.b[L_ATT0], b.roww, b.edge_recv, re, 128, A, st));
+    WG(dense_bwd_weight(b, fw + W.msg, 128, gw + W.g1, b.G + L.w[L_ATT0], b.G + L.b[L_ATT0], nullptr, b.edge_recv, re, 128, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_ATT0, EPI_NONE, true, gw + W.g1, gw + W.msg, nullptr, re, st));
     // ---- message MLP
-    WG(dense_bwd_weight(b, fw + W.x2, 256, gw + W.msg, b.G + L.w[L_MSGOUT], b.edge_recv, re, 256, 128, A, st));
-    WG(launch_colsum(gw + W.msg, b.G + L.b[L_MSGOUT], b.roww, b.edge_recv, re, 128, A, st));
+    WG(dense_bwd_weight(b, fw + W.x2, 256, gw + W.msg, b.G + L.w[L_MSGOUT], b.G + L.b[L_MSGOUT], nullptr, b.edge_recv, re, 256, 128, A, st));
     RC(dense_bwd_data(b, L, TL, L_MSGOUT, EPI_NONE, false, gw + W.msg, gw + W.x2, nullptr, re, st));
-    WG(dense_bwd_weight(b, fw + W.x1, 256, gw + W.x2, b.G + L.w[L_MSG1], b.edge_recv, re, 256, 256, A, st));
-    WG(launch_colsum(gw + W.x2, b.G + L.b[L_MSG1], b.roww, b.edge_recv, re, 256, A, st));
+    WG(dense_bwd_weight(b, fw + W.x1, 256, gw + W.x2, b.G + L.w[L_MSG1], b.G + L.b[L_MSG1], nullptr, b.edge_recv, re, 256, 256, A, st));
     RC(dense_bwd_data(b, L, TL, L_MSG1, EPI_RELU_MASK, false, gw + W.x2, gw + W.x1, fw + W.x1, re, st));
     // ---- edge layer 1
     if (wgrad) {
-        const int grid = min(max(cap / 64, 1), 4 * nsm);
+        const int grid = min(max(cap / 64, 1), 4 * nsm);   // one CTA walks chunks of 64 edges
         switch (ed) {
             case 2: edge_l1_bwd_w_kernel<2><<<grid, 256, 0, st>>>(cap, A, b.counters, gw + W.x1, fw + W.feat, b.edge_src, b.edge_recv, b.roww, b.G + L.w[L_MSG0], b.G + L.b[L_MSG0]); break;
             case 4: edge_l1_bwd_w_kernel<4><<<grid, 256, 0, st>>>(cap, A, b.counters, gw + W.x1, fw + W.feat, b.edge_src, b.edge_recv, b.roww, b.G + L.w[L_MSG0], b.G + L.b[L_MSG0]); break;
@@ -625,6 +741,145 @@ static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
 #undef WG
 #undef RC
     return 0;
+}
+
+// ------------------------------------------------------------------------------------ folded train step
+// Every MLP block ends in two linear layers with no activation between them (mlp.py:23-29, act_final=False), and the
+// update block's tail feeds the head's first layer directly.  The forward of the train step therefore runs on the same
+// folded weights as the rollout (gcbf_prepare_infer: W23 = W2 W3, a23 = A2 a3, UH = U2 U3 H1, HO = H2 H3) -- 4 GEMMs per
+// network instead of 9 -- keeps the ReLU outputs (x1, g1, v1, h1) plus msg / att / ag, and the backward differentiates
+// the folded network: 4 weight-gradient GEMMs and 4 data GEMMs per pass instead of 10 + 9.  The gradients of the folded
+// weights (accumulated over the passes of a network in `Gf`, InferLayout offsets) are un-folded onto the flax
+// parameters at the end by the chain rule of the products (unfold_gradients: two launches of small products).
+// Same function, same gradient; only the rounding differs (~1e-6 relative, like the rollout's folded forward).
+int32_t prepare_infer_impl(int ed, int out_dim, const float* P, float* blob, cudaStream_t st);
+int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* blob, int use_tc,
+                       const float* agent, const float* goal, const float* hits, const int32_t* row_start,
+                       const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src,
+                       const int32_t* counters, int clip_all, float* out, float* ws, cudaStream_t st, float* z_out,
+                       int* z_parts, int32_t* zero_counter, int select, int keep_activations);
+
+static int32_t gnn_backward_folded(const BwdArgs& b, const float* blob, float* Gf, cudaStream_t st) {
+    const gcbf_env_desc* d = b.d;
+    const int ed = env_ed(d->env_kind);
+    const ParamLayout L = make_layout(ed, b.out_dim);
+    const InferLayout I = make_infer_layout(b.out_dim);
+    const int A = d->n_graphs * d->n_agents, cap = d->edge_cap;
+    const GnnWs W = make_ws(cap, A);
+    const RowCount re{b.counters, 0, cap};
+    const RowCount ra{nullptr, A, A};
+    const int nsm = sm_count();
+    const float* fw = b.fw;
+    float* gw = b.gw;
+    int32_t rc;
+#define RC(x) do { if ((rc = (x))) return rc; } while (0)
+    auto data = [&](int epi, bool accum, const float* dY, int p_off, int K, int N, float* dX, const float* aux,
+                    RowCount rows) -> int32_t {
+        return tc::launch_gemm_tc(epi, accum, dY, blob + p_off, blob + p_off + K * N, nullptr, nullptr, dX, aux, rows, K, N, st);
+    };
+    // ---- folded output layer: z = h1 HO + bho, out = tanh(z); dh1 masked by h1 > 0
+    {
+        const int grid = min((A + 7) / 8, 2 * nsm);
+        head_out_bwd_kernel<<<grid, 256, 0, st>>>(A, b.out_dim, fw + W.h1, blob + I.ho, b.out, b.d_out, b.roww, gw + W.h1,
+                                                  Gf + I.ho, Gf + I.bho, 1);
+        count_launch();
+        RC(check_launch("head_out_bwd_kernel"));
+    }
+    // ---- h1 = relu(v1 UH + buh)
+    RC(tc::launch_gemm_tn_tc(fw + W.v1, 256, gw + W.h1, Gf + I.uh, b.roww, nullptr, ra, 256, 256, A, st, Gf + I.buh, nullptr));
+    RC(data(EPI_RELU_MASK, false, gw + W.h1, I.p_uh, 256, 256, gw + W.v1, fw + W.v1, ra));
+    // ---- v1 = relu(ag U1[3:] + U1[2] + bu1)
+    RC(tc::launch_gemm_tn_tc(fw + W.ag, 128, gw + W.v1, b.G + L.w[L_UPD0] + 3 * 256, b.roww, nullptr, ra, 128, 256, A, st,
+                             b.G + L.b[L_UPD0], b.G + L.w[L_UPD0] + 2 * 256));
+    RC(data(EPI_NONE, false, gw + W.v1, I.p_u1, 256, 128, gw + W.ag, nullptr, ra));
+    // ---- attention + aggregation with the folded gate vector (g1 = relu output of the gate's first layer)
+    {
+        const int grid = min((A + 7) / 8, 2 * nsm);
+        attn_aggregate_bwd_kernel<<<grid, 256, 0, st>>>(A, cap, gw + W.ag, fw + W.msg, fw + W.g1, fw + W.att, blob + I.a23,
+                                                        b.row_start, b.row_deg, b.roww, gw + W.msg, gw + W.g1, Gf + I.a23,
+                                                        Gf + I.c23, 1);
+        count_launch();
+        RC(check_launch("attn_aggregate_bwd_kernel"));
+    }
+    // ---- g1 = relu(msg A1 + ba1)
+    RC(tc::launch_gemm_tn_tc(fw + W.msg, 128, gw + W.g1, b.G + L.w[L_ATT0], b.roww, b.edge_recv, re, 128, 128, A, st,
+                             b.G + L.b[L_ATT0], nullptr));
+    RC(data(EPI_NONE, true, gw + W.g1, I.p_a1, 128, 128, gw + W.msg, nullptr, re));
+    // ---- msg = x1 W23 + b23
+    RC(tc::launch_gemm_tn_tc(fw + W.x1, 256, gw + W.msg, Gf + I.w23, b.roww, b.edge_recv, re, 256, 128, A, st, Gf + I.b23,
+                             nullptr));
+    RC(data(EPI_RELU_MASK, false, gw + W.msg, I.p_w23, 128, 256, gw + W.x1, fw + W.x1, re));
+    // ---- edge layer 1
+    {
+        const int grid = min(max(cap / 64, 1), 4 * nsm);
+        switch (ed) {
+            case 2: edge_l1_bwd_w_kernel<2><<<grid, 256, 0, st>>>(cap, A, b.counters, gw + W.x1, fw + W.feat, b.edge_src, b.edge_recv, b.roww, b.G + L.w[L_MSG0], b.G + L.b[L_MSG0]); break;
+            case 4: edge_l1_bwd_w_kernel<4><<<grid, 256, 0, st>>>(cap, A, b.counters, gw + W.x1, fw + W.feat, b.edge_src, b.edge_recv, b.roww, b.G + L.w[L_MSG0], b.G + L.b[L_MSG0]); break;
+            default: edge_l1_bwd_w_kernel<6><<<grid, 256, 0, st>>>(cap, A, b.counters, gw + W.x1, fw + W.feat, b.edge_src, b.edge_recv, b.roww, b.G + L.w[L_MSG0], b.G + L.b[L_MSG0]); break;
+        }
+        count_launch();
+        RC(check_launch("edge_l1_bwd_w_kernel"));
+    }
+    if (b.d_es) {
+        const int grid = min((cap + 7) / 8, 4 * nsm);
+        GCBF_DISPATCH_ENV(d->env_kind, {
+            edge_l1_bwd_x_kernel<KIND><<<grid, 256, 0, st>>>(*d, b.P + L.w[L_MSG0], gw + W.x1, b.agent, b.goal, b.hits,
+                                                             b.edge_recv, b.edge_src, b.counters, b.clip_all, b.d_es, nullptr);
+        });
+        count_launch();
+        RC(check_launch("edge_l1_bwd_x_kernel"));
+    }
+#undef RC
+    return 0;
+}
+
+// Chain rule of the folded products: G (flax layout) += d(folded) / d(parameters) applied to Gf.  `scratch`: 256 * 128 + 128 floats.
+//   W23 = W2 W3, b23 = b2 W3 + b3          -> dW2 = dW23 W3^T, dW3 = W2^T dW23 + b2 (x) db23, db2 = db23 W3^T, db3 = db23
+//   a23 = A2 a3, c23 = ba2 . a3 + ba3      -> dA2 = da23 (x) a3, da3 = A2^T da23 + ba2 dc23, dba2 = a3 dc23, dba3 = dc23
+//   UH = U2 U3 H1, buh = (bu2 U3 + bu3) H1 + bh1
+//        T = dUH H1^T, t = dbuh H1^T       -> dU2 = T U3^T, dU3 = U2^T T + bu2 (x) t, dH1 = (U2 U3)^T dUH + (bu2 U3 + bu3) (x) dbuh,
+//                                             dbu2 = t U3^T, dbu3 = t, dbh1 = dbuh
+//   HO = H2 H3, bho = bh2 H3 + bh3         -> dH2 = dHO H3^T, dH3 = H2^T dHO + bh2 (x) dbho, dbh2 = dbho H3^T, dbh3 = dbho
+static int32_t unfold_gradients(int ed, int out_dim, const float* P, const float* blob, const float* Gf, float* G,
+                                float* scratch, cudaStream_t st) {
+    const ParamLayout L = make_layout(ed, out_dim);
+    const InferLayout I = make_infer_layout(out_dim);
+    const int no = out_dim;
+    float* T = scratch;              // [256, 128]
+    float* t = scratch + 256 * 128;  // [128]
+    int32_t rc;
+    SmallJobList J;
+    const float* H1 = P + L.w[L_HEAD0];     // [128, 256]
+    J.add(T, 256, 128, 256, Gf + I.uh, 256, 1, H1, 1, 256, nullptr, nullptr, nullptr, false);
+    J.add(t, 1, 128, 256, Gf + I.buh, 0, 1, H1, 1, 256, nullptr, nullptr, nullptr, false);
+    if ((rc = J.launch(st))) return rc;
+    const float* W2 = P + L.w[L_MSG1];      // [256, 256]
+    const float* W3 = P + L.w[L_MSGOUT];    // [256, 128]
+    J.add(G + L.w[L_MSG1], 256, 256, 128, Gf + I.w23, 128, 1, W3, 1, 128, nullptr, nullptr, nullptr, true);
+    J.add(G + L.w[L_MSGOUT], 256, 128, 256, W2, 1, 256, Gf + I.w23, 128, 1, P + L.b[L_MSG1], Gf + I.b23, nullptr, true);
+    J.add(G + L.b[L_MSG1], 1, 256, 128, Gf + I.b23, 0, 1, W3, 1, 128, nullptr, nullptr, nullptr, true);
+    J.add(G + L.b[L_MSGOUT], 1, 128, 0, nullptr, 0, 0, nullptr, 0, 0, nullptr, nullptr, Gf + I.b23, true);
+    const float* A2 = P + L.w[L_ATT1];      // [128, 128]
+    const float* a3 = P + L.w[L_GATE];      // [128, 1]
+    J.add(G + L.w[L_ATT1], 128, 128, 0, nullptr, 0, 0, nullptr, 0, 0, Gf + I.a23, a3, nullptr, true);
+    J.add(G + L.w[L_GATE], 128, 1, 128, A2, 1, 128, Gf + I.a23, 1, 0, P + L.b[L_ATT1], Gf + I.c23, nullptr, true);
+    J.add(G + L.b[L_ATT1], 1, 128, 0, nullptr, 0, 0, nullptr, 0, 0, Gf + I.c23, a3, nullptr, true);
+    J.add(G + L.b[L_GATE], 1, 1, 0, nullptr, 0, 0, nullptr, 0, 0, nullptr, nullptr, Gf + I.c23, true);
+    const float* U2 = P + L.w[L_UPD1];      // [256, 256]
+    const float* U3 = P + L.w[L_UPDOUT];    // [256, 128]
+    J.add(G + L.w[L_UPD1], 256, 256, 128, T, 128, 1, U3, 1, 128, nullptr, nullptr, nullptr, true);
+    J.add(G + L.w[L_UPDOUT], 256, 128, 256, U2, 1, 256, T, 128, 1, P + L.b[L_UPD1], t, nullptr, true);
+    J.add(G + L.w[L_HEAD0], 128, 256, 256, blob + I.q_u12, 1, 128, Gf + I.uh, 256, 1, blob + I.b_u12, Gf + I.buh, nullptr, true);
+    J.add(G + L.b[L_UPD1], 1, 256, 128, t, 0, 1, U3, 1, 128, nullptr, nullptr, nullptr, true);
+    J.add(G + L.b[L_UPDOUT], 1, 128, 0, nullptr, 0, 0, nullptr, 0, 0, nullptr, nullptr, t, true);
+    J.add(G + L.b[L_HEAD0], 1, 256, 0, nullptr, 0, 0, nullptr, 0, 0, nullptr, nullptr, Gf + I.buh, true);
+    const float* H2 = P + L.w[L_HEAD1];     // [256, 256]
+    const float* H3 = P + L.w[L_OUT];       // [256, no]
+    J.add(G + L.w[L_HEAD1], 256, 256, no, Gf + I.ho, no, 1, H3, 1, no, nullptr, nullptr, nullptr, true);
+    J.add(G + L.w[L_OUT], 256, no, 256, H2, 1, 256, Gf + I.ho, no, 1, P + L.b[L_HEAD1], Gf + I.bho, nullptr, true);
+    J.add(G + L.b[L_HEAD1], 1, 256, no, Gf + I.bho, 0, 1, H3, 1, no, nullptr, nullptr, nullptr, true);
+    J.add(G + L.b[L_OUT], 1, no, 0, nullptr, 0, 0, nullptr, 0, 0, nullptr, nullptr, Gf + I.bho, true);
+    return J.launch(st);
 }
 
 // ------------------------------------------------------------------------------------ optimizer kernels
@@ -840,7 +1095,31 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
         return (int32_t)e;
     }
     const int use_tc = hp_host[6] != 0.f;
-    if (use_tc) {
+    // folded train step (tensor-core path; GCBF_TRAIN_FOLD=0 keeps the layer-by-layer step): the prepared-parameter
+    // regions of the workspace hold [folded blob | gradient of the folded weights | un-fold scratch] instead
+    static const bool fold_on = [] { const char* e = getenv("GCBF_TRAIN_FOLD"); return !(e && e[0] == '0'); }();
+    const bool fold = use_tc && fold_on;
+    const InferLayout Ic = make_infer_layout(1), Ia = make_infer_layout(nu);
+    auto up8 = [](int64_t n) { return (n + 7) & ~(int64_t)7; };
+    float* blob_c = ws + TW.pt_cbf;
+    float* gf_c = blob_c + up8(Ic.total);
+    float* scr_c = gf_c + up8(Ic.t_w23);
+    float* blob_a = ws + TW.pt_act;
+    float* gf_a = blob_a + up8(Ia.total);
+    float* scr_a = gf_a + up8(Ia.t_w23);
+    if (fold) {
+        const int64_t scr = 256 * 128 + 128;
+        GCBF_REQUIRE(up8(Ic.total) + up8(Ic.t_w23) + scr <= TW.pt_act - TW.pt_cbf &&
+                         up8(Ia.total) + up8(Ia.t_w23) + scr <= TW.h - TW.pt_act,
+                     "gcbf_train_step: folded blobs do not fit the prepared-parameter regions");
+        RC(prepare_infer_impl(ed, 1, cbf_params, blob_c, st));
+        RC(prepare_infer_impl(ed, nu, actor_params, blob_a, st));
+        if ((e = cudaMemsetAsync(gf_c, 0, sizeof(float) * Ic.t_w23, st)) != cudaSuccess ||
+            (e = cudaMemsetAsync(gf_a, 0, sizeof(float) * Ia.t_w23, st)) != cudaSuccess) {
+            set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+            return (int32_t)e;
+        }
+    } else if (use_tc) {
         RC(build_prepared(Lc, cbf_params, ws + TW.pt_cbf, st));
         RC(build_prepared(La, actor_params, ws + TW.pt_act, st));
     } else {
@@ -850,17 +1129,22 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
     // ---- forward: h = cbf(g), pi = actor(g), x' = f(x, clip(2 pi + u_ref)), h' = cbf(g')
     const float* ptc = use_tc ? ws + TW.pt_cbf : nullptr;
     const float* pta = use_tc ? ws + TW.pt_act : nullptr;
-    RC(gnn_forward_impl(d, 1, cbf_params, ptc, agent, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 0,
-                        ws + TW.h, ws + TW.ws0, st));
-    RC(gnn_forward_impl(d, nu, actor_params, pta, agent, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 0,
-                        ws + TW.pi, ws + TW.ws1, st));
+    auto forward = [&](int out_dim, const float* params, const float* pt, const float* blob, const float* x, int clip_all,
+                       float* out, float* fws) -> int32_t {
+        if (fold)
+            return gnn_infer_impl(d, out_dim, params, blob, 1, x, goal, hits, row_start, row_deg, edge_recv, edge_src,
+                                  counters, clip_all, out, fws, st, nullptr, nullptr, nullptr, 0xF, 1);
+        return gnn_forward_impl(d, out_dim, params, pt, x, goal, hits, row_start, row_deg, edge_recv, edge_src, counters,
+                                clip_all, out, fws, st);
+    };
+    RC(forward(1, cbf_params, ptc, blob_c, agent, 0, ws + TW.h, ws + TW.ws0));
+    RC(forward(nu, actor_params, pta, blob_a, agent, 0, ws + TW.pi, ws + TW.ws1));
     GCBF_DISPATCH_ENV(d->env_kind, {
         act_dyn_kernel<KIND><<<(A + 127) / 128, 128, 0, st>>>(*d, agent, goal, ws + TW.pi, ws + TW.act, ws + TW.xn);
     });
     count_launch();
     RC(check_launch("act_dyn_kernel"));
-    RC(gnn_forward_impl(d, 1, cbf_params, ptc, ws + TW.xn, goal, hits, row_start, row_deg, edge_recv, edge_src, counters, 1,
-                        ws + TW.hn, ws + TW.ws2, st));
+    RC(forward(1, cbf_params, ptc, blob_c, ws + TW.xn, 1, ws + TW.hn, ws + TW.ws2));
     // ---- losses and their derivatives wrt h, h', a
     {
         const int grid = min((A + 255) / 256, 2 * sm_count());
@@ -897,7 +1181,10 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
     b.d_es = ws + TW.d_es;
     b.je = nullptr;
     b.use_tc = use_tc;
-    RC(gnn_backward_impl(b, st));
+    auto backward = [&](const float* blob, float* gf) -> int32_t {
+        return fold ? gnn_backward_folded(b, blob, gf, st) : gnn_backward_impl(b, st);
+    };
+    RC(backward(blob_c, gf_c));
     // ---- through the Euler step / clips into the policy output
     GCBF_DISPATCH_ENV(d->env_kind, {
         dyn_bwd_kernel<KIND><<<(A + 127) / 128, 128, 0, st>>>(*d, agent, goal, ws + TW.act, ws + TW.xn, ws + TW.d_es,
@@ -917,7 +1204,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
     b.G = grad_actor;
     b.clip_all = 0;
     b.d_es = nullptr;
-    RC(gnn_backward_impl(b, st));
+    RC(backward(blob_a, gf_a));
     // ---- backward 3: cbf on g
     b.out_dim = 1;
     b.P = cbf_params;
@@ -926,7 +1213,11 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
     b.out = ws + TW.h;
     b.d_out = ws + TW.dh;
     b.G = grad_cbf;
-    RC(gnn_backward_impl(b, st));
+    RC(backward(blob_c, gf_c));
+    if (fold) {
+        RC(unfold_gradients(ed, 1, cbf_params, blob_c, gf_c, grad_cbf, scr_c, st));
+        RC(unfold_gradients(ed, nu, actor_params, blob_a, gf_a, grad_actor, scr_a, st));
+    }
 #undef RC
     return 0;
 }
