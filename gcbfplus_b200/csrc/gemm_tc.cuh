@@ -300,6 +300,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
+                // ReLU-mask epilogue: the 32 mask values of this row chunk are requested BEFORE the accumulator read, so
+                // the global-load latency overlaps the TMEM load instead of sitting between it and the stores
+                float4 mkp[8];
+                if (EPI == EPI_RELU_MASK && m < M) {
+                    const float* mrow = aux + (size_t)m * N + n0 + c0;
+                    if ((reinterpret_cast<uintptr_t>(mrow) & 31) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ld_global_v8(mrow + 8 * j, mkp[2 * j], mkp[2 * j + 1]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) mkp[j] = *reinterpret_cast<const float4*>(mrow + 4 * j);
+                    }
+                }
                 tmem_ld32(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
                 if (EPI == EPI_RELU_DOTN) {  // output layer partial sums over this column tile
                     const float* hw = aux + (size_t)(n0 + c0) * ndot;
@@ -349,13 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 }
                             }
                         } else if (EPI == EPI_RELU_MASK) {
-                            float4 mk[2];
-                            if (wide) {
-                                ld_global_v8(mrow + j, mk[0], mk[1]);
-                            } else {
-                                mk[0] = *reinterpret_cast<const float4*>(mrow + j);
-                                mk[1] = *reinterpret_cast<const float4*>(mrow + j + 4);
-                            }
+                            const float4 mk[2] = {mkp[j / 4], mkp[j / 4 + 1]};
 #pragma unroll
                             for (int hh = 0; hh < 2; ++hh) {
                                 o[hh].x = mk[hh].x > 0.f ? o[hh].x : 0.f; o[hh].y = mk[hh].y > 0.f ? o[hh].y : 0.f;
@@ -434,11 +441,13 @@ inline int32_t make_map(CUtensorMap* map, const float* ptr, int rows, int cols, 
     return 0;
 }
 
-// k-block size of the NN kernel: 16 (default) or 32 (GCBF_TC_BK=32)
+// k-block size of the NN kernel: 32 (default: 128-byte rows, 2 / 3 stages) or 16 (GCBF_TC_BK=16: 64-byte rows,
+// SWIZZLE_64B, 4 / 6 stages).  Measured on the train step: 9.39 ms (32) vs 9.90 ms (16) -- the kernel is bound by the
+// L2 -> SM operand stream (every tile re-reads the 64 KB weight k-blocks), not by pipeline depth; kept as an option.
 inline int tc_bk() {
     static const int bk = [] {
         const char* e = getenv("GCBF_TC_BK");
-        return (e && atoi(e) == 32) ? 32 : 16;
+        return (e && atoi(e) == 16) ? 16 : 32;
     }();
     return bk;
 }

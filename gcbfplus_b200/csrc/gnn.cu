@@ -391,7 +391,7 @@ int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* P, cons
         if ((rc = gemm(EPI_BIAS, ws + W.x1, blob + I.w23, I.t_w23, 256, 128, blob + I.b23, nullptr, ws + W.msg, re))) return rc;
         if ((rc = gemm(EPI_BIAS_RELU, ws + W.msg, P + L.w[L_ATT0], I.t_a1, 128, 128, P + L.b[L_ATT0], nullptr, ws + W.g1, re))) return rc;
         {
-            const int grid = min((A + 7) / 8, 4 * nsm);
+            const int grid = min((A + 7) / 8, 8 * nsm);
             attn_aggregate_kernel<<<grid, 256, 0, st>>>(A, cap, ws + W.g1, ws + W.msg, blob + I.a23, blob + I.c23, row_start,
                                                         row_deg, ws + W.att, ws + W.ag, zero_counter);
             count_launch();

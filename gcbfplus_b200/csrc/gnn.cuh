@@ -331,16 +331,48 @@ head_out_kernel(const int A, const int nout, const float* __restrict__ H2, const
                 const float* __restrict__ b, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
-    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < A; a += warps_total) {
-        const float4 h0 = *reinterpret_cast<const float4*>(H2 + (size_t)a * 256 + lane * 8);
-        const float4 h1 = *reinterpret_cast<const float4*>(H2 + (size_t)a * 256 + lane * 8 + 4);
-        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-        for (int j = 0; j < nout; ++j) {
-            float s = 0.f;
+    float wl[8][4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s = fmaf(hv[k], W[(lane * 8 + k) * nout + j], s);
-            s = warp_sum(s) + b[j];
-            if (lane == 0) out[(size_t)a * nout + j] = tanhf(s);
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wl[k][j] = (j < nout) ? W[(lane * 8 + k) * nout + j] : 0.f;
+    // four agents per iteration: all eight row loads are in flight before the first reduction (latency-bound loop)
+    for (int a0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a0 < A; a0 += 4 * warps_total) {
+        float4 hq[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int a = min(a0 + q * warps_total, A - 1);
+            hq[q][0] = *reinterpret_cast<const float4*>(H2 + (size_t)a * 256 + lane * 8);
+            hq[q][1] = *reinterpret_cast<const float4*>(H2 + (size_t)a * 256 + lane * 8 + 4);
+        }
+        float sv[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float hv[8] = {hq[q][0].x, hq[q][0].y, hq[q][0].z, hq[q][0].w, hq[q][1].x, hq[q][1].y, hq[q][1].z, hq[q][1].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s = fmaf(hv[k], wl[k][j], s);
+                sv[q][j] = s;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sv[q][j] += __shfl_xor_sync(0xffffffffu, sv[q][j], off);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int a = a0 + q * warps_total;
+            if (a < A && lane < nout) {
+                float s = sv[q][0];
+                if (lane == 1) s = sv[q][1];
+                if (lane == 2) s = sv[q][2];
+                if (lane == 3) s = sv[q][3];
+                out[(size_t)a * nout + lane] = tanhf(s + b[lane]);
+            }
         }
     }
 }

@@ -11,7 +11,7 @@
 namespace gcbf {
 
 // C[i, j] (+)= sum_k A(i, k) B(k, j) + u[i] v[j] + bias[j];  A(i, k) = A[i a_rs + k a_cs], B(k, j) = B[k b_rs + j b_cs].
-// One thread per output, sequential fused multiply-adds over ascending k, then the rank-1 term, then the bias.
+// One accumulator per output, sequential fused multiply-adds over ascending k, then the rank-1 term, then the bias.
 struct SmallJob {
     const float* A;
     const float* B;
@@ -30,22 +30,52 @@ struct SmallJobs {
     SmallJob j[SMALL_MAX_JOBS];
 };
 
-static __global__ void __launch_bounds__(128) small_jobs_kernel(const SmallJobs J) {
+// 32 x 32 output tile per CTA (256 threads, 4 outputs each), operand tiles staged through shared memory with the
+// global loads coalesced along whichever index has unit stride.  Every output is still ONE accumulator fed in ascending
+// k by fused multiply-adds, then the rank-1 term, then the bias: same bits as a thread-per-output loop.
+static __global__ void __launch_bounds__(256) small_jobs_kernel(const SmallJobs J) {
+    __shared__ float As[32][33];   // [i][kk]
+    __shared__ float Bs[32][33];   // [kk][j]
     int q = 0;
     while (q + 1 < J.n && (int)blockIdx.x >= J.blk0[q + 1]) ++q;
     const SmallJob& job = J.j[q];
-    const int idx = (blockIdx.x - J.blk0[q]) * 128 + threadIdx.x;
-    if (idx >= job.m * job.n) return;
-    const int r = idx / job.n, c = idx % job.n;
-    float s = 0.f;
+    const int t = blockIdx.x - J.blk0[q];
+    const int tiles_n = (job.n + 31) / 32;
+    const int r0 = (t / tiles_n) * 32, c0 = (t % tiles_n) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (job.A != nullptr) {
-        const float* a = job.A + (size_t)r * job.a_rs;
-        const float* b = job.B + (size_t)c * job.b_cs;
-        for (int kk = 0; kk < job.k; ++kk) s = fmaf(a[(size_t)kk * job.a_cs], b[(size_t)kk * job.b_rs], s);
+        const bool a_k_fast = job.a_cs == 1;     // A(i, k): k contiguous -> lanes along k, else lanes along i
+        const bool b_j_fast = job.b_cs == 1;     // B(k, j): j contiguous -> lanes along j, else lanes along k
+        for (int k0 = 0; k0 < job.k; k0 += 32) {
+            for (int s = ty; s < 32; s += 8) {
+                const int i = a_k_fast ? s : tx, kk = a_k_fast ? tx : s;
+                const int r = r0 + i, k = k0 + kk;
+                As[i][kk] = (r < job.m && k < job.k) ? job.A[(size_t)r * job.a_rs + (size_t)k * job.a_cs] : 0.f;
+                const int kb = b_j_fast ? s : tx, jb = b_j_fast ? tx : s;
+                const int kq = k0 + kb, c = c0 + jb;
+                Bs[kb][jb] = (kq < job.k && c < job.n) ? job.B[(size_t)kq * job.b_rs + (size_t)c * job.b_cs] : 0.f;
+            }
+            __syncthreads();
+            const int kmax = min(32, job.k - k0);
+            for (int kk = 0; kk < kmax; ++kk) {
+                const float bv = Bs[kk][tx];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) acc[o] = fmaf(As[ty + 8 * o][kk], bv, acc[o]);
+            }
+            __syncthreads();
+        }
     }
-    if (job.u != nullptr) s = fmaf(job.u[r], job.v[c], s);
-    if (job.bias != nullptr) s += job.bias[c];
-    job.C[idx] = job.accumulate ? job.C[idx] + s : s;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const int r = r0 + ty + 8 * o, c = c0 + tx;
+        if (r >= job.m || c >= job.n) continue;
+        float sv = acc[o];
+        if (job.u != nullptr) sv = fmaf(job.u[r], job.v[c], sv);
+        if (job.bias != nullptr) sv += job.bias[c];
+        const size_t idx = (size_t)r * job.n + c;
+        job.C[idx] = job.accumulate ? job.C[idx] + sv : sv;
+    }
 }
 
 struct SmallJobList {
@@ -59,13 +89,13 @@ struct SmallJobList {
         q.m = m; q.n = n; q.k = k;
         q.a_rs = a_rs; q.a_cs = a_cs; q.b_rs = b_rs; q.b_cs = b_cs;
         q.accumulate = accumulate ? 1 : 0;
-        J.blk0[J.n + 1] = J.blk0[J.n] + (m * n + 127) / 128;
+        J.blk0[J.n + 1] = J.blk0[J.n] + ((m + 31) / 32) * ((n + 31) / 32);
         ++J.n;
     }
     bool full() const { return J.n >= SMALL_MAX_JOBS; }
     int32_t launch(cudaStream_t st) {
         if (J.n == 0) return 0;
-        small_jobs_kernel<<<J.blk0[J.n], 128, 0, st>>>(J);
+        small_jobs_kernel<<<J.blk0[J.n], 256, 0, st>>>(J);
         count_launch();
         const int32_t rc = check_launch("small_jobs_kernel");
         J.n = 0;
