@@ -276,6 +276,8 @@ def train_step_bench(torch, dist, env, algo, eng, rank, world, cfg, max_over_ran
     from gcbfplus_b200.algo import train as T
     B_glob = 256
     B = max(B_glob // world, 1)
+    if os.environ.get("GCBF_BENCH_TRAIN_GRAPHS"):        # profiling aid: the per-rank share of an N-GPU run on one GPU
+        B = int(os.environ["GCBF_BENCH_TRAIN_GRAPHS"])
     ro = eng.result()
     n_pool = 4 * B
     tsel = torch.arange(n_pool, device=env.device) % eng.T

@@ -278,43 +278,55 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_gemm_tn_tc(const 
 // =====================================================================================================
 namespace gcbf {
 
-// Folded weights + operand planes of one network: 3 launches (two dependency waves of small products, then all planes).
-int32_t prepare_infer_impl(int ed, int out_dim, const float* P, float* blob, cudaStream_t st) {
+// Folded weights + operand planes: two dependency waves of small products, then all planes.  The jobs of several
+// networks can share the three launches (prepare_infer_pair: both networks of the train step).
+static void prepare_infer_jobs(int ed, int out_dim, const float* P, float* blob, SmallJobList& J1, SmallJobList& J2,
+                               PlaneJobList& PJ) {
     const ParamLayout L = make_layout(ed, out_dim);
     const InferLayout I = make_infer_layout(out_dim);
-    int32_t rc;
-#define RC(x) do { if ((rc = (x))) return rc; } while (0)
-    SmallJobList J;
     // message tail: W23 = W2 W3, b23 = b2 W3 + b3
-    J.add(blob + I.w23, 256, 128, 256, P + L.w[L_MSG1], 256, 1, P + L.w[L_MSGOUT], 128, 1, nullptr, nullptr, nullptr, false);
-    J.add(blob + I.b23, 1, 128, 256, P + L.b[L_MSG1], 0, 1, P + L.w[L_MSGOUT], 128, 1, nullptr, nullptr, P + L.b[L_MSGOUT], false);
+    J1.add(blob + I.w23, 256, 128, 256, P + L.w[L_MSG1], 256, 1, P + L.w[L_MSGOUT], 128, 1, nullptr, nullptr, nullptr, false);
+    J1.add(blob + I.b23, 1, 128, 256, P + L.b[L_MSG1], 0, 1, P + L.w[L_MSGOUT], 128, 1, nullptr, nullptr, P + L.b[L_MSGOUT], false);
     // gate tail: a23 = A2 a3 ; c = ba2 . a3 + ba3
-    J.add(blob + I.a23, 128, 1, 128, P + L.w[L_ATT1], 128, 1, P + L.w[L_GATE], 1, 1, nullptr, nullptr, nullptr, false);
-    J.add(blob + I.c23, 1, 1, 128, P + L.b[L_ATT1], 0, 1, P + L.w[L_GATE], 1, 1, nullptr, nullptr, P + L.b[L_GATE], false);
+    J1.add(blob + I.a23, 128, 1, 128, P + L.w[L_ATT1], 128, 1, P + L.w[L_GATE], 1, 1, nullptr, nullptr, nullptr, false);
+    J1.add(blob + I.c23, 1, 1, 128, P + L.b[L_ATT1], 0, 1, P + L.w[L_GATE], 1, 1, nullptr, nullptr, P + L.b[L_GATE], false);
     // update tail: Q = U2 U3, b' = bu2 U3 + bu3
-    J.add(blob + I.q_u12, 256, 128, 256, P + L.w[L_UPD1], 256, 1, P + L.w[L_UPDOUT], 128, 1, nullptr, nullptr, nullptr, false);
-    J.add(blob + I.b_u12, 1, 128, 256, P + L.b[L_UPD1], 0, 1, P + L.w[L_UPDOUT], 128, 1, nullptr, nullptr, P + L.b[L_UPDOUT], false);
+    J1.add(blob + I.q_u12, 256, 128, 256, P + L.w[L_UPD1], 256, 1, P + L.w[L_UPDOUT], 128, 1, nullptr, nullptr, nullptr, false);
+    J1.add(blob + I.b_u12, 1, 128, 256, P + L.b[L_UPD1], 0, 1, P + L.w[L_UPDOUT], 128, 1, nullptr, nullptr, P + L.b[L_UPDOUT], false);
     // head tail: HO = H2 H3, bho = bh2 H3 + bh3
-    J.add(blob + I.ho, 256, out_dim, 256, P + L.w[L_HEAD1], 256, 1, P + L.w[L_OUT], out_dim, 1, nullptr, nullptr, nullptr, false);
-    J.add(blob + I.bho, 1, out_dim, 256, P + L.b[L_HEAD1], 0, 1, P + L.w[L_OUT], out_dim, 1, nullptr, nullptr, P + L.b[L_OUT], false);
-    RC(J.launch(st));
+    J1.add(blob + I.ho, 256, out_dim, 256, P + L.w[L_HEAD1], 256, 1, P + L.w[L_OUT], out_dim, 1, nullptr, nullptr, nullptr, false);
+    J1.add(blob + I.bho, 1, out_dim, 256, P + L.b[L_HEAD1], 0, 1, P + L.w[L_OUT], out_dim, 1, nullptr, nullptr, P + L.b[L_OUT], false);
     // update tail folded into the head's first layer: UH = Q H1, buh = b' H1 + bh1
-    J.add(blob + I.uh, 256, 256, 128, blob + I.q_u12, 128, 1, P + L.w[L_HEAD0], 256, 1, nullptr, nullptr, nullptr, false);
-    J.add(blob + I.buh, 1, 256, 128, blob + I.b_u12, 0, 1, P + L.w[L_HEAD0], 256, 1, nullptr, nullptr, P + L.b[L_HEAD0], false);
-    RC(J.launch(st));
+    J2.add(blob + I.uh, 256, 256, 128, blob + I.q_u12, 128, 1, P + L.w[L_HEAD0], 256, 1, nullptr, nullptr, nullptr, false);
+    J2.add(blob + I.buh, 1, 256, 128, blob + I.b_u12, 0, 1, P + L.w[L_HEAD0], 256, 1, nullptr, nullptr, P + L.b[L_HEAD0], false);
     // tf32 planes: transposed (forward B operands) and straight (backward-data B operands) of the 4 GEMM weights
     struct { const float* src; int rows, cols, t, p; } T[4] = {
         {blob + I.w23, 256, 128, I.t_w23, I.p_w23}, {P + L.w[L_ATT0], 128, 128, I.t_a1, I.p_a1},
         {P + L.w[L_UPD0] + 3 * 256, 128, 256, I.t_u1, I.p_u1}, {blob + I.uh, 256, 256, I.t_uh, I.p_uh}};
-    PlaneJobList PJ;
     for (int i = 0; i < 4; ++i) {
         const int n = T[i].rows * T[i].cols;
         PJ.add(T[i].src, T[i].rows, T[i].cols, true, blob + T[i].t, blob + T[i].t + n);
         PJ.add(T[i].src, T[i].rows, T[i].cols, false, blob + T[i].p, blob + T[i].p + n);
     }
-    RC(PJ.launch(st));
-#undef RC
-    return 0;
+}
+static int32_t prepare_infer_launch(SmallJobList& J1, SmallJobList& J2, PlaneJobList& PJ, cudaStream_t st) {
+    if (int32_t rc = J1.launch(st)) return rc;
+    if (int32_t rc = J2.launch(st)) return rc;
+    return PJ.launch(st);
+}
+int32_t prepare_infer_impl(int ed, int out_dim, const float* P, float* blob, cudaStream_t st) {
+    SmallJobList J1, J2;
+    PlaneJobList PJ;
+    prepare_infer_jobs(ed, out_dim, P, blob, J1, J2, PJ);
+    return prepare_infer_launch(J1, J2, PJ, st);
+}
+int32_t prepare_infer_pair(int ed, int out_a, const float* Pa, float* blob_a, int out_b, const float* Pb, float* blob_b,
+                           cudaStream_t st) {
+    SmallJobList J1, J2;
+    PlaneJobList PJ;
+    prepare_infer_jobs(ed, out_a, Pa, blob_a, J1, J2, PJ);
+    prepare_infer_jobs(ed, out_b, Pb, blob_b, J1, J2, PJ);
+    return prepare_infer_launch(J1, J2, PJ, st);
 }
 
 int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* blob, int use_tc,

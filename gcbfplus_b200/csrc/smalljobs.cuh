@@ -23,7 +23,7 @@ struct SmallJob {
     int a_rs, a_cs, b_rs, b_cs;
     int accumulate;
 };
-constexpr int SMALL_MAX_JOBS = 20;
+constexpr int SMALL_MAX_JOBS = 40;   // 40 x 80 B + offsets < the 4 KB kernel-parameter limit
 struct SmallJobs {
     int n;
     int blk0[SMALL_MAX_JOBS + 1];
@@ -47,21 +47,44 @@ static __global__ void __launch_bounds__(256) small_jobs_kernel(const SmallJobs 
     if (job.A != nullptr) {
         const bool a_k_fast = job.a_cs == 1;     // A(i, k): k contiguous -> lanes along k, else lanes along i
         const bool b_j_fast = job.b_cs == 1;     // B(k, j): j contiguous -> lanes along j, else lanes along k
-        for (int k0 = 0; k0 < job.k; k0 += 32) {
-            for (int s = ty; s < 32; s += 8) {
+        // register double buffer: the global loads of k-tile t + 1 are in flight while tile t is consumed
+        float ra[4], rb[4];
+        auto fetch = [&](int k0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int s = ty + 8 * q;
                 const int i = a_k_fast ? s : tx, kk = a_k_fast ? tx : s;
                 const int r = r0 + i, k = k0 + kk;
-                As[i][kk] = (r < job.m && k < job.k) ? job.A[(size_t)r * job.a_rs + (size_t)k * job.a_cs] : 0.f;
+                ra[q] = (r < job.m && k < job.k) ? job.A[(size_t)r * job.a_rs + (size_t)k * job.a_cs] : 0.f;
                 const int kb = b_j_fast ? s : tx, jb = b_j_fast ? tx : s;
                 const int kq = k0 + kb, c = c0 + jb;
-                Bs[kb][jb] = (kq < job.k && c < job.n) ? job.B[(size_t)kq * job.b_rs + (size_t)c * job.b_cs] : 0.f;
+                rb[q] = (kq < job.k && c < job.n) ? job.B[(size_t)kq * job.b_rs + (size_t)c * job.b_cs] : 0.f;
+            }
+        };
+        fetch(0);
+        for (int k0 = 0; k0 < job.k; k0 += 32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int s = ty + 8 * q;
+                As[a_k_fast ? s : tx][a_k_fast ? tx : s] = ra[q];
+                Bs[b_j_fast ? s : tx][b_j_fast ? tx : s] = rb[q];
             }
             __syncthreads();
+            if (k0 + 32 < job.k) fetch(k0 + 32);
             const int kmax = min(32, job.k - k0);
-            for (int kk = 0; kk < kmax; ++kk) {
-                const float bv = Bs[kk][tx];
+            if (kmax == 32) {
+#pragma unroll 8
+                for (int kk = 0; kk < 32; ++kk) {
+                    const float bv = Bs[kk][tx];
 #pragma unroll
-                for (int o = 0; o < 4; ++o) acc[o] = fmaf(As[ty + 8 * o][kk], bv, acc[o]);
+                    for (int o = 0; o < 4; ++o) acc[o] = fmaf(As[ty + 8 * o][kk], bv, acc[o]);
+                }
+            } else {
+                for (int kk = 0; kk < kmax; ++kk) {
+                    const float bv = Bs[kk][tx];
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) acc[o] = fmaf(As[ty + 8 * o][kk], bv, acc[o]);
+                }
             }
             __syncthreads();
         }
@@ -106,7 +129,7 @@ struct SmallJobList {
 // ---- tf32 hi / lo planes of a [rows, cols] matrix, straight or transposed, several matrices per launch
 __device__ __forceinline__ float sj_rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
-constexpr int PLANE_MAX_JOBS = 14;
+constexpr int PLANE_MAX_JOBS = 16;
 struct PlaneJobs {
     int n;
     int tile0[PLANE_MAX_JOBS + 1];

@@ -297,18 +297,21 @@ head_out_bwd_kernel(const int A, const int nout, const float* __restrict__ H2, c
     }
     if (!dW) return;   // data-only backward (QP labels): no parameter gradient
     // block-level reduction first: one atomic per (row, column) and CTA instead of one per warp
-    __shared__ float s_w[256 * 4 + 4];
+    __shared__ float s_w[256 * 4 + 4];       // [k][j][lane]: the 32 lanes of a warp hit 32 different banks
     for (int i = threadIdx.x; i < 256 * 4 + 4; i += blockDim.x) s_w[i] = 0.f;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; ++k)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (j < nout) atomicAdd(&s_w[(lane * 8 + k) * 4 + j], wacc[k][j]);
-    if (lane == 0)
+            if (j < nout) atomicAdd(&s_w[(k * 4 + j) * 32 + lane], wacc[k][j]);
+    if (lane == 0)      // bacc is warp-uniform (every lane sees the same dz)
         for (int j = 0; j < nout; ++j) atomicAdd(&s_w[1024 + j], bacc[j]);
     __syncthreads();
-    for (int i = threadIdx.x; i < 256 * nout; i += blockDim.x) atomicAdd(dW + i, s_w[(i / nout) * 4 + (i % nout)]);
+    for (int i = threadIdx.x; i < 256 * nout; i += blockDim.x) {
+        const int row = i / nout, j = i % nout;          // W row = lane * 8 + k
+        atomicAdd(dW + i, s_w[((row & 7) * 4 + j) * 32 + (row >> 3)]);
+    }
     if (threadIdx.x < nout) atomicAdd(db + threadIdx.x, s_w[1024 + threadIdx.x]);
 }
 
@@ -412,14 +415,14 @@ attn_aggregate_bwd_kernel(const int A, const int edge_cap, const float* __restri
     __shared__ float s_a[132];
     for (int i = threadIdx.x; i < 132; i += blockDim.x) s_a[i] = 0.f;
     __syncthreads();
-    atomicAdd(&s_a[lane * 4 + 0], acc3.x);
-    atomicAdd(&s_a[lane * 4 + 1], acc3.y);
-    atomicAdd(&s_a[lane * 4 + 2], acc3.z);
-    atomicAdd(&s_a[lane * 4 + 3], acc3.w);
+    atomicAdd(&s_a[0 * 32 + lane], acc3.x);       // [component][lane]: conflict-free
+    atomicAdd(&s_a[1 * 32 + lane], acc3.y);
+    atomicAdd(&s_a[2 * 32 + lane], acc3.z);
+    atomicAdd(&s_a[3 * 32 + lane], acc3.w);
     accb = warp_sum(accb);
     if (lane == 0) atomicAdd(&s_a[128], accb);
     __syncthreads();
-    if (threadIdx.x < 128) atomicAdd(da3 + threadIdx.x, s_a[threadIdx.x]);
+    if (threadIdx.x < 128) atomicAdd(da3 + threadIdx.x, s_a[(threadIdx.x & 3) * 32 + (threadIdx.x >> 2)]);
     if (threadIdx.x == 128) atomicAdd(dba3, s_a[128]);
 }
 
@@ -750,9 +753,10 @@ static int32_t gnn_backward_impl(const BwdArgs& b, cudaStream_t st) {
 // network instead of 9 -- keeps the ReLU outputs (x1, g1, v1, h1) plus msg / att / ag, and the backward differentiates
 // the folded network: 4 weight-gradient GEMMs and 4 data GEMMs per pass instead of 10 + 9.  The gradients of the folded
 // weights (accumulated over the passes of a network in `Gf`, InferLayout offsets) are un-folded onto the flax
-// parameters at the end by the chain rule of the products (unfold_gradients: two launches of small products).
+// parameters at the end by the chain rule of the products (unfold_jobs: two launches of small products for both networks).
 // Same function, same gradient; only the rounding differs (~1e-6 relative, like the rollout's folded forward).
-int32_t prepare_infer_impl(int ed, int out_dim, const float* P, float* blob, cudaStream_t st);
+int32_t prepare_infer_pair(int ed, int out_a, const float* Pa, float* blob_a, int out_b, const float* Pb, float* blob_b,
+                           cudaStream_t st);
 int32_t gnn_infer_impl(const gcbf_env_desc* d, int out_dim, const float* P, const float* blob, int use_tc,
                        const float* agent, const float* goal, const float* hits, const int32_t* row_start,
                        const int32_t* row_deg, const int32_t* edge_recv, const int32_t* edge_src,
@@ -840,19 +844,16 @@ static int32_t gnn_backward_folded(const BwdArgs& b, const float* blob, float* G
 //        T = dUH H1^T, t = dbuh H1^T       -> dU2 = T U3^T, dU3 = U2^T T + bu2 (x) t, dH1 = (U2 U3)^T dUH + (bu2 U3 + bu3) (x) dbuh,
 //                                             dbu2 = t U3^T, dbu3 = t, dbh1 = dbuh
 //   HO = H2 H3, bho = bh2 H3 + bh3         -> dH2 = dHO H3^T, dH3 = H2^T dHO + bh2 (x) dbho, dbh2 = dbho H3^T, dbh3 = dbho
-static int32_t unfold_gradients(int ed, int out_dim, const float* P, const float* blob, const float* Gf, float* G,
-                                float* scratch, cudaStream_t st) {
+static void unfold_jobs(int ed, int out_dim, const float* P, const float* blob, const float* Gf, float* G, float* scratch,
+                        SmallJobList& JT, SmallJobList& J) {
     const ParamLayout L = make_layout(ed, out_dim);
     const InferLayout I = make_infer_layout(out_dim);
     const int no = out_dim;
     float* T = scratch;              // [256, 128]
     float* t = scratch + 256 * 128;  // [128]
-    int32_t rc;
-    SmallJobList J;
     const float* H1 = P + L.w[L_HEAD0];     // [128, 256]
-    J.add(T, 256, 128, 256, Gf + I.uh, 256, 1, H1, 1, 256, nullptr, nullptr, nullptr, false);
-    J.add(t, 1, 128, 256, Gf + I.buh, 0, 1, H1, 1, 256, nullptr, nullptr, nullptr, false);
-    if ((rc = J.launch(st))) return rc;
+    JT.add(T, 256, 128, 256, Gf + I.uh, 256, 1, H1, 1, 256, nullptr, nullptr, nullptr, false);
+    JT.add(t, 1, 128, 256, Gf + I.buh, 0, 1, H1, 1, 256, nullptr, nullptr, nullptr, false);
     const float* W2 = P + L.w[L_MSG1];      // [256, 256]
     const float* W3 = P + L.w[L_MSGOUT];    // [256, 128]
     J.add(G + L.w[L_MSG1], 256, 256, 128, Gf + I.w23, 128, 1, W3, 1, 128, nullptr, nullptr, nullptr, true);
@@ -879,7 +880,6 @@ static int32_t unfold_gradients(int ed, int out_dim, const float* P, const float
     J.add(G + L.w[L_OUT], 256, no, 256, H2, 1, 256, Gf + I.ho, no, 1, P + L.b[L_HEAD1], Gf + I.bho, nullptr, true);
     J.add(G + L.b[L_HEAD1], 1, 256, no, Gf + I.bho, 0, 1, H3, 1, no, nullptr, nullptr, nullptr, true);
     J.add(G + L.b[L_OUT], 1, no, 0, nullptr, 0, 0, nullptr, 0, 0, nullptr, nullptr, Gf + I.bho, true);
-    return J.launch(st);
 }
 
 // ------------------------------------------------------------------------------------ optimizer kernels
@@ -1112,8 +1112,7 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
         GCBF_REQUIRE(up8(Ic.total) + up8(Ic.t_w23) + scr <= TW.pt_act - TW.pt_cbf &&
                          up8(Ia.total) + up8(Ia.t_w23) + scr <= TW.h - TW.pt_act,
                      "gcbf_train_step: folded blobs do not fit the prepared-parameter regions");
-        RC(prepare_infer_impl(ed, 1, cbf_params, blob_c, st));
-        RC(prepare_infer_impl(ed, nu, actor_params, blob_a, st));
+        RC(prepare_infer_pair(ed, 1, cbf_params, blob_c, nu, actor_params, blob_a, st));
         if ((e = cudaMemsetAsync(gf_c, 0, sizeof(float) * Ic.t_w23, st)) != cudaSuccess ||
             (e = cudaMemsetAsync(gf_a, 0, sizeof(float) * Ia.t_w23, st)) != cudaSuccess) {
             set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
@@ -1215,8 +1214,11 @@ extern "C" __attribute__((visibility("default"))) int32_t gcbf_train_step(
     b.G = grad_cbf;
     RC(backward(blob_c, gf_c));
     if (fold) {
-        RC(unfold_gradients(ed, 1, cbf_params, blob_c, gf_c, grad_cbf, scr_c, st));
-        RC(unfold_gradients(ed, nu, actor_params, blob_a, gf_a, grad_actor, scr_a, st));
+        SmallJobList JT, JU;      // both networks share the two un-fold launches
+        unfold_jobs(ed, 1, cbf_params, blob_c, gf_c, grad_cbf, scr_c, JT, JU);
+        unfold_jobs(ed, nu, actor_params, blob_a, gf_a, grad_actor, scr_a, JT, JU);
+        RC(JT.launch(st));
+        RC(JU.launch(st));
     }
 #undef RC
     return 0;

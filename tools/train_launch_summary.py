@@ -10,7 +10,7 @@ ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Met
 data = rows[1:]
 names = [r[ki] for r in data]
 idx = [i for i, n in enumerate(names) if "small_jobs_kernel" in n]
-start = idx[-8] if len(idx) >= 8 else 0        # 2 networks x 2 fold waves + 2 x 2 un-fold waves per step
+start = idx[-4] if len(idx) >= 4 else 0        # per step: 2 fold waves + 2 un-fold waves (both networks share them)
 pre = ("gather", "graph_build", "reduce_kernel", "elementwise", "mask_count", "fill")
 while start > 0 and any(t in names[start - 1] for t in pre):
     start -= 1
