@@ -326,9 +326,11 @@ def train_step_bench(torch, dist, env, algo, eng, rank, world, cfg, max_over_ran
     return {"ms_per_minibatch": ms, "graphs_per_s": B * world / (ms * 1e-3),
             "agent_samples_per_s": B * world * N / (ms * 1e-3), "global_batch_graphs": B * world,
             "graphs_per_rank": B, "edges_per_rank": n_edges, "kernels_per_step": int(launches),
-            "launch_mode": "one CUDA-graph replay per optimizer step (gather + graph build + train step + all-reduce + "
-                           "clip/AdamW)",
+            "launch_mode": "one CUDA-graph replay per optimizer step (gather + graph build + folded train step + "
+                           "all-reduce + clip/AdamW)",
             "approx_tflops_per_gpu": flops / world / (ms * 1e-3) / 1e12,
+            "flops_basis": "the reference's layer-by-layer algorithmic FLOPs (SURVEY 8d: 3 passes x (fwd + 2x bwd)); the "
+                           "folded step (DESIGN 4.3) executes ~2.6x fewer tensor-core FLOPs for the same gradient",
             "collectives_per_step": 1 if world > 1 else 0,
             "allreduce_bytes_per_step": 4 * algo._trainer_state.packed.numel() if world > 1 else 0}
 

@@ -505,7 +505,8 @@ inline int32_t launch_gemm_tc(int epi, bool accum, const float* A, const float* 
     const int tiles_m = (rows + BM - 1) / BM;
     // a 256-wide layer over few row tiles is split into two 128-wide column tiles: twice the CTAs (more SMs
     // busy), half the weight traffic and MMA time per CTA, 3 pipeline stages instead of 2
-    const int bn = (N == 256 && 2 * tiles_m <= sm_count() && epi != EPI_RELU_DOT) ? 128 : N;
+    static const bool force128 = [] { const char* e = getenv("GCBF_TC_BN128"); return e && e[0] == '1'; }();   // A/B switch
+    const int bn = (N == 256 && (2 * tiles_m <= sm_count() || force128) && epi != EPI_RELU_DOT) ? 128 : N;
     CUtensorMap tmA, tmB, tmBl;
     const int bk = tc_bk();
     if (int32_t r = make_map(&tmA, A, rc.cap, K, BM, bk)) return r;
