@@ -1,7 +1,9 @@
 // train.cu -- the GCBF+ train step: three GNN forwards with saved activations, the four
 // losses, hand-written backward (dW via split-M GEMMs, dX through the edge features, the Euler
 // step and the action clip back into the actor), global-norm clip + AdamW + apply_if_finite,
-// and the target-network polyak update.
+// and the target-network polyak update.  On the tensor-core path the step runs on the folded
+// network (gnn_backward_folded / unfold_jobs below: 4 GEMMs per pass and direction instead of
+// 9-10, same gradient); the layer-by-layer step remains for the SIMT path and GCBF_TRAIN_FOLD=0.
 //
 // Replaces gcbfplus/algo/gcbf_plus.py:354-447 (update_inner / get_loss / value_and_grad),
 // trainer/utils.py:62-75 (compute_norm_and_clip), optax.adamw + optax.apply_if_finite

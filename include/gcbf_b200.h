@@ -136,7 +136,8 @@ int32_t gcbf_gnn_forward(const gcbf_env_desc* desc, int32_t net_kind, int32_t ou
 /* Inference-only forward with FOLDED weights (rollouts; same functions replaced as gcbf_gnn_forward).
  * Each MLP block ends in two activation-free linear layers (nn/mlp.py:23-29, act_final=False), which are
  * multiplied together once per parameter update by gcbf_prepare_infer: 4 GEMMs instead of 9 per forward and
- * 2.4x fewer FLOPs; no activations are saved.  infer_blob: gcbf_infer_count() floats. */
+ * 2.4x fewer FLOPs; no activations are saved.  infer_blob: gcbf_infer_count() floats (folded weights, their
+ * transposed and straight tf32 hi / lo planes, U2 U3 for the train step's un-folding). */
 int32_t gcbf_infer_count(int32_t edge_dim, int32_t out_dim);
 int32_t gcbf_prepare_infer(int32_t edge_dim, int32_t out_dim, const float* params, float* infer_blob,
                            void* stream);
@@ -269,7 +270,9 @@ int32_t gcbf_safe_horizon(const uint8_t* unsafe, uint8_t* safe, int32_t n_rollou
  * c_h mean relu(-h_dot - alpha h + eps) with the reference's stop-gradient routing for
  * unlabelled agents (:399-407); jax.value_and_grad wrt (cbf_params, actor_params).
  *   hp_host[7] (HOST): alpha, eps, loss_action_coef, loss_unsafe_coef, loss_safe_coef, loss_h_dot_coef,
- *     use_tensor_cores (0: strict-fp32 SIMT GEMMs, 1: tcgen05 3xTF32 for forward + backward-data GEMMs)
+ *     use_tensor_cores (0: strict-fp32 SIMT GEMMs, layer by layer; 1: tcgen05 3xTF32 GEMMs on the FOLDED network --
+ *     the activation-free layer pairs of every MLP block multiplied together as in gcbf_prepare_infer, the
+ *     gradient un-folded onto the flax parameters by the chain rule; same gradient, ~1e-6 relative rounding)
  *   denoms[4] (device): GLOBAL n_unsafe, n_safe, n_agents of the minibatch (gcbf_mask_counts, then
  *     summed over ranks by the host when the minibatch is sharded)
  *   grad_cbf / grad_actor: flat gradients in the parameter layout (overwritten)
